@@ -1,0 +1,194 @@
+// ac.cuh — batched small-signal AC: per instance and per angular frequency one
+// complex128 solve of (MNA + Gmin + J(x_op) + j*omega*AC) x = -Nac.
+//
+// Replaces ac.ac_analysis and its helpers (ahkab/ac.py:146-443).  The reference
+// routes every frequency through dc_solve/mdn_solver with a dummy *linear*
+// circuit (ac.py:293-305), i.e. exactly one iteration x = x_prev + solve(A,
+// -(A x_prev + Nac)); the same update is done here, frequency after frequency,
+// by the group that owns the instance (x_prev chains inside a frequency chunk).
+// Complex LU: partial pivoting on |re|+|im| as LAPACK zgesv (izamax) does.
+#pragma once
+#include "core.cuh"
+#include "program_build.hpp"
+
+namespace ahk {
+
+struct cd { double re, im; };
+AHK_DEV cd cmul(cd a, cd b) { return cd{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+AHK_DEV cd csub(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
+AHK_DEV cd cadd(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
+AHK_DEV cd cdivv(cd a, cd b) {   // Smith's algorithm (what C / numpy use)
+  if (fabs(b.re) >= fabs(b.im)) {
+    double r = b.im / b.re, den = b.re + b.im * r;
+    return cd{(a.re + a.im * r) / den, (a.im - a.re * r) / den};
+  } else {
+    double r = b.re / b.im, den = b.re * r + b.im;
+    return cd{(a.re * r + a.im) / den, (a.im * r - a.re) / den};
+  }
+}
+
+struct AcLayout {
+  Layout L;          // real arrays shared with core.cuh (Mv, Dv, Bv, dout, dst, x=xr, bytes)
+  int RS;            // complex row stride (elements)
+  int Ac, xc, dxc, Nac;   // offsets in doubles of the complex arrays
+  int stride;
+};
+
+inline AcLayout make_ac_layout(const HostProg& H, int G) {
+  AcLayout A; std::memset(&A, 0, sizeof A);
+  const Prog& h = H.hdr;
+  const int n = h.n;
+  A.RS = n + 1;
+  int off = 0;
+  auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
+  A.Ac = take(2 * n * A.RS);
+  A.xc = take(2 * n); A.dxc = take(2 * n); A.Nac = take(2 * n);
+  A.L.RS = A.RS;
+  A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos);
+  A.L.x = take(n);
+  A.L.dout = take(h.ndout); A.L.dst = take(2 * h.ndev);
+  A.L.bytes = take(16);
+  A.L.buflen = 1;
+  int want = (2 * G) % 16;   // 16-byte elements: spread consecutive groups over banks
+  while (off % 16 != want) off++;
+  A.stride = off;
+  A.L.stride = off;
+  return A;
+}
+
+struct AcArgs {
+  const double* x_op;      // [B][n] or null
+  const double* omegas;    // device [npts]
+  int npts;
+  int f0, f1;              // host emulation: the chunk; kernels compute their own
+  double* x_out;           // [B][npts][n] complex
+  int* status;
+};
+
+template <int G>
+AHK_DEV int zlu_solve(Ctx& c, const AcLayout& AL) {
+  const int n = c.p->n, RS = AL.RS;
+  cd* A = (cd*)(c.sm + AL.Ac);
+  cd* dx = (cd*)(c.sm + AL.dxc);
+  unsigned char* prow = c.prow();
+  unsigned char* stepof = c.stepof();
+  unsigned long long used = 0ull;
+  for (int k = 0; k < n; k++) {
+    double best = -1.0;
+    int bi = -1;
+    for (int r = c.sub; r < n; r += G) {
+      if ((used >> r) & 1ull) continue;
+      cd a = A[r * RS + k];
+      double v = fabs(a.re) + fabs(a.im);
+      if (bi < 0 || v > best) { best = v; bi = r; }
+    }
+    Grp<G>::argmax(best, bi, c.mask);
+    if (best == 0.0) return 0;
+    used |= 1ull << bi;
+    if (c.sub == 0) { prow[k] = (unsigned char)bi; stepof[bi] = (unsigned char)k; }
+    const cd* Ap = A + bi * RS;
+    cd one = {1.0, 0.0};
+    cd inv = cdivv(one, Ap[k]);
+    for (int r = c.sub; r < n; r += G) {
+      if ((used >> r) & 1ull) continue;
+      cd* Ar = A + r * RS;
+      cd l = cmul(Ar[k], inv);
+      if (l.re == 0.0 && l.im == 0.0) continue;
+      for (int j = k + 1; j <= n; j++) Ar[j] = csub(Ar[j], cmul(l, Ap[j]));
+    }
+    Grp<G>::sync(c.mask);
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    int pr = prow[k];
+    cd xk = cdivv(A[pr * RS + n], A[pr * RS + k]);
+    if (c.sub == 0) dx[k] = xk;
+    for (int r = c.sub; r < n; r += G)
+      if ((int)stepof[r] < k) A[r * RS + n] = csub(A[r * RS + n], cmul(A[r * RS + k], xk));
+    Grp<G>::sync(c.mask);
+  }
+  return 1;
+}
+
+template <int G>
+AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
+  const Prog& p = *c.p;
+  const Opts& o = *c.o;
+  const int n = p.n, RS = AL.RS;
+  c.L = &AL.L;
+  c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0;
+  build_values(c, true);
+  double* Bv = c.sm + AL.L.Bv;
+  const double* Mv = c.sm + AL.L.Mv;
+  const double* Dv = c.sm + AL.L.Dv;
+  double* xr = c.sm + AL.L.x;
+  cd* A = (cd*)(c.sm + AL.Ac);
+  cd* x = (cd*)(c.sm + AL.xc);
+  cd* dx = (cd*)(c.sm + AL.dxc);
+  cd* Nac = (cd*)(c.sm + AL.Nac);
+  const bool have_op = a.x_op != nullptr;
+  for (int i = c.sub; i < n; i += G) {
+    xr[i] = have_op ? a.x_op[c.inst * n + i] : 0.0;
+    x[i] = cd{(p.ndev && have_op) ? xr[i] : 0.0, 0.0};   // x = x0 (ac.py:290)
+    Nac[i] = cd{0.0, 0.0};
+  }
+  Grp<G>::sync(c.mask);
+  if (p.ndev) eval_devices<G>(c, xr);   // J at the linearisation point (ac.py:417-443)
+  const double* dout = c.sm + AL.L.dout;
+  for (int k = c.sub; k < p.npos; k += G) {
+    double v = Mv[k];
+    for (int q = p.nl_ptr[k]; q < p.nl_ptr[k + 1]; q++) v += (double)p.nl_sgn[q] * dout[p.nl_src[q]];
+    if (p.pdiag[k]) v += o.gmin;
+    Bv[k] = v;
+  }
+  if (c.sub == 0) {   // _generate_Nac, ac.py:380-414
+    for (int k = 0; k < p.nsrc; k++) {
+      const SrcOp& s = p.src[k];
+      if (!s.has_ac) continue;
+      double mag = c.P(s.pbase + 1), ph = c.P(s.pbase + 2);
+      cd v = {mag * cos(ph), mag * sin(ph)};
+      if (s.is_v) Nac[s.row0] = cd{-1.0 * v.re, -1.0 * v.im};
+      else {
+        if (s.row0 >= 0) Nac[s.row0] = cadd(Nac[s.row0], v);
+        if (s.row1 >= 0) Nac[s.row1] = csub(Nac[s.row1], v);
+      }
+    }
+  }
+  Grp<G>::sync(c.mask);
+  int st = AHK_ST_OK;
+  for (int f = a.f0; f < a.f1; f++) {
+    const double om = a.omegas[f];
+    for (int r = c.sub; r < n; r += G) {
+      cd* Ar = A + r * RS;
+      for (int j = 0; j < n; j++) Ar[j] = cd{0.0, 0.0};
+      cd s = Nac[r];
+      for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
+        int col = p.pcol[k];
+        cd v = {Bv[k], om * Dv[k]};
+        Ar[col] = v;
+        s = cadd(s, cmul(v, x[col]));
+      }
+      Ar[n] = cd{-s.re, -s.im};
+    }
+    Grp<G>::sync(c.mask);
+    double* xo = a.x_out + ((c.inst * a.npts + f) * n) * 2;
+    if (!zlu_solve<G>(c, AL)) {
+      st = AHK_ST_SINGULAR;
+      const double qn = nan("");
+      for (int g = f; g < a.f1; g++) {
+        double* xg = a.x_out + ((c.inst * a.npts + g) * n) * 2;
+        for (int i = c.sub; i < n; i += G) { xg[2 * i] = qn; xg[2 * i + 1] = qn; }
+      }
+      break;
+    }
+    for (int i = c.sub; i < n; i += G) {
+      cd v = cadd(x[i], dx[i]);
+      x[i] = v;
+      xo[2 * i] = v.re; xo[2 * i + 1] = v.im;
+    }
+    Grp<G>::sync(c.mask);
+  }
+  // status[] is pre-filled with AHK_ST_OK by the caller; chunks only downgrade it
+  if (c.sub == 0 && a.status && st != AHK_ST_OK) a.status[c.inst] = st;
+}
+
+}  // namespace ahk

@@ -1,0 +1,322 @@
+// devices.cuh — non-linear device evaluators and source waveforms, FP64.
+//
+// One call = one evaluation of a device at given port voltages, returning the
+// current and the small-signal conductances the Newton Jacobian needs.  The
+// formulas (including their quirks) are the reference's:
+//   diode   ahkab/diode.py:352-424      EKV     ahkab/ekv.py:444-752
+//   mosq    ahkab/mosq.py:552-803       switch  ahkab/switch.py:310-399
+//   sources ahkab/time_functions.py:402-745
+// Unlike the reference (which re-runs the whole EKV current computation four
+// times per Newton iteration, ekv.py:676,687,698), each device is evaluated
+// once and every output is derived from that single evaluation.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define AHK_DEV __device__ __forceinline__
+#define AHK_MEM __device__ __forceinline__
+#else
+#define AHK_DEV static inline
+#define AHK_MEM inline
+#endif
+
+namespace ahk {
+
+// constants.py:30-53 — k*T/e at T = Tref = 300 K
+#define AHK_VTH (1.3806503e-23 * 300 / 1.60217646e-19)
+#define AHK_EPS 2.220446049250313e-16
+#define AHK_ESI 104.5e-12
+
+// ---- diode -----------------------------------------------------------------
+AHK_DEV double safe_exp(double x) { return x < 70 ? exp(x) : exp(70.0) + 10 * x; }
+
+struct DiodeP { double IS, N, NBV, ISR, NR, RS, BV, IKF, VT, AREA; };
+
+AHK_DEV double diode_i_raw(const DiodeP& m, double v) {  // diode.py:387-395
+  double i_fwd = m.IS * (safe_exp(v / (m.N * m.VT)) - 1);
+  double i_rec = m.ISR != 0.0 ? m.ISR * (safe_exp(v / (m.NR * m.VT)) - 1) : 0.0;
+  double i_rev = -m.IS * (safe_exp(-(v + m.BV) / (m.NBV * m.VT)) - 1);
+  double k_inj = 1;
+  if (!isinf(m.IKF) && m.IKF > 0 && i_fwd > 0) k_inj = sqrt(m.IKF / (m.IKF + i_fwd));
+  return k_inj * i_fwd + i_rec + i_rev;
+}
+
+AHK_DEV double diode_gm_raw(const DiodeP& m, double v) {  // diode.py:402-406 (not d i/dv)
+  double g = m.IS / (m.N * m.VT) * safe_exp(v / (m.N * m.VT)) +
+             -m.IS / m.VT * (safe_exp(-(v + m.BV) / m.VT));
+  if (m.ISR != 0.0) g += m.ISR / (m.NR * m.VT) * safe_exp(v / (m.NR * m.VT));
+  return g;
+}
+
+// out[0] = i, out[1] = gm (with the gm==0 -> 2*gmin rule of diode.py:178-179);
+// *last_vd is the device state used by the RS != 0 inner Newton (diode.py:359-365).
+AHK_DEV void diode_eval(const DiodeP& m, double v, double vea, double gmin,
+                        double* last_vd, double* out) {
+  double gm = diode_gm_raw(m, v);
+  if (m.RS != 0.0) gm = 1. / (m.RS + 1. / (gm + 1e-3 * gmin));
+  gm *= m.AREA;
+  if (gm == 0) gm = gmin * 2;
+  double i;
+  if (!(m.RS != 0.0)) {
+    i = diode_i_raw(m, v) * m.AREA;
+    *last_vd = v;
+  } else {
+    // scipy.optimize.newton (Newton branch), tol = vea, x0 = last_vd
+    double p0 = *last_vd, p = p0;
+    for (int it = 0; it < 500; it++) {
+      double fval = p0 / m.RS - diode_i_raw(m, v - p0) * m.AREA;
+      if (fval == 0) { p = p0; break; }
+      double fder = 1. / m.RS + m.AREA * diode_gm_raw(m, v - p0);
+      if (fder == 0) { p = p0; break; }
+      p = p0 - fval / fder;
+      if (fabs(p - p0) <= vea) break;
+      p0 = p;
+    }
+    *last_vd = p;
+    i = diode_i_raw(m, v - p);  // AREA dropped, as diode.py:363 does
+  }
+  out[0] = i;
+  out[1] = gm;
+}
+
+// ---- EKV ---------------------------------------------------------------------
+struct EkvP { double VTO, KP, GAMMA, PHI, COX, LAMBDA, XJ, UCRIT, W, L, M, N; int NP; };
+
+// Solve ln(sqrt(1/4+i)-1/2) + 2 sqrt(1/4+i) - 1 = v for i (ekv.py:703-752) with
+// the Halley iteration scipy.optimize.newton runs (tol 1.48e-8, warm start).
+AHK_DEV double ekv_ismall(double vsmall, double iguess) {
+  double p0 = iguess, p = p0;
+  for (int it = 0; it < 500; it++) {
+    double fval, fder, fder2;
+    if (p0 > 0) {
+      double s = sqrt(.25 + p0);
+      fval = log(s - 0.5) + 2.0 * s - 1.0 - vsmall;
+    } else {
+      fval = p0 - vsmall;
+    }
+    if (fval == 0) { p = p0; break; }
+    {
+      double xx = p0 < AHK_EPS ? 10 * AHK_EPS : p0;
+      double a = xx + 0.25, s = sqrt(a), q = s - 0.5;
+      double is = 1.0 / s, iq = 1.0 / q;
+      fder = 0.5 * iq * is + is;
+      double ia = 1.0 / a;
+      fder2 = -0.25 * ia * iq * iq - 0.5 * ia * is - 0.25 * ia * is * iq;
+    }
+    double step = fval / fder;
+    double adj = step * fder2 / fder * 0.5;
+    if (fabs(adj) < 1) step /= 1.0 - adj;
+    p = p0 - step;
+    if (fabs(p - p0) <= 1.48e-8) break;
+    p0 = p;
+  }
+  return p > 10 * AHK_EPS ? p : 10 * AHK_EPS;
+}
+
+AHK_DEV void ekv_vp(const EkvP& m, double VG, double sqphi, double& VP) {  // ekv.py:524-540
+  double VGeff = VG - m.VTO + m.PHI + m.GAMMA * sqphi;
+  double t = sqphi + m.GAMMA * 0.5;
+  double arg = VG - m.VTO + t * t;
+  if (VGeff > 0 && arg > 0) {
+    VP = VG - m.VTO - m.GAMMA * (sqrt(arg) - t);
+    if (isnan(VP)) VP = 0;
+  } else {
+    VP = -m.PHI;
+  }
+}
+
+// out[0] = Ids, out[1..3] = gmd, gmg, gms ; st[0..1] = ifn, irn warm starts.
+// (vd, vg, vs) are the drive-port voltages w.r.t. bulk.
+AHK_DEV void ekv_eval(const EkvP& m, double vd, double vg, double vs, double gmin,
+                      double* st, double* out) {
+  const double Ut = AHK_VTH;
+  double VD = vd * m.NP, VG = vg * m.NP, VS = vs * m.NP;  // ekv.py:481-507
+  int CS = +1;
+  if (VS > VD) { double t = VD; VD = VS; VS = t; CS = -1; }
+  double sqphi = sqrt(m.PHI);
+  double VP;
+  ekv_vp(m, VG, sqphi, VP);
+  double nq = 1.0 + .5 * m.GAMMA / sqrt(m.PHI + .5 * VP);
+  double KWL = m.KP * m.W / m.L;
+  double Is = 2 * nq * Ut * Ut * KWL;  // ekv.py:509-522
+  double Gs = 2 * nq * Ut * KWL;
+  double vp = VP / Ut, vsn = VS / Ut, vdn = VD / Ut;
+  double ifn = ekv_ismall(vp - vsn, fmax(st[0], 1e-10));
+  // get_leq_virp, ekv.py:629-670 (normalised vd, vs => half Vds, quirk 11)
+  double Leq, v_irn;
+  {
+    double Vc = m.UCRIT * m.N * m.L;
+    double sif = sqrt(ifn);
+    double Vdss = Vc * (sqrt(.25 + Ut / Vc * sif) - .5);
+    double Vdssp = Vc * (sqrt(.25 + Ut / Vc * (sif - .75 * log(ifn))) - .5) +
+                   Ut * (log(.5 * Vc / Ut) - .6);
+    double vser_1 = sif - Vdss / Ut;
+    double Vds = (vdn - vsn) * .5 * Ut;
+    double delta_v = 4.0 * Ut * sqrt(m.LAMBDA * vser_1 + 1.0 / 64);
+    double dv2 = delta_v * delta_v;
+    double Vip = sqrt(Vdss * Vdss + dv2) - sqrt((Vds - Vdss) * (Vds - Vdss) + dv2);
+    double Lc = sqrt(AHK_ESI * m.XJ / m.COX);
+    double delta_l = m.LAMBDA * Lc * log(1 + (Vds - Vip) / (Lc * m.UCRIT));
+    double Lp = m.N * m.L - delta_l + (Vds + Vip) / m.UCRIT;
+    double Lmin = m.N * m.L / 10.0;
+    Leq = .5 * (Lp + sqrt(Lp * Lp + Lmin * Lmin));
+    v_irn = (VP - Vds - vsn * Ut - sqrt(Vdssp * Vdssp + dv2) +
+             sqrt((Vds - Vdssp) * (Vds - Vdssp) + dv2)) / Ut;
+  }
+  double irn = ekv_ismall(v_irn, fmax(st[1], 1e-10));
+  st[0] = ifn; st[1] = irn;
+  double qf = sqrt(.25 + fmax(ifn, 0.0)) - .5;  // ekv.py:783-789
+  double qr = sqrt(.25 + fmax(irn, 0.0)) - .5;
+  out[0] = CS * m.NP * m.L / Leq * m.M * Is * (ifn - irn);  // ekv.py:601-602
+  double gmd = CS == 1 ? Gs * qr : Gs * qf;                 // ekv.py:672-692
+  double gms = CS == 1 ? -1.0 * Gs * qf : -Gs * qr;
+  // get_gmg: nv from the UN-flipped vg (ekv.py:697, quirk 11)
+  double VPu;
+  ekv_vp(m, vg, sqphi, VPu);
+  double nv = 1.0 + .5 * m.GAMMA / sqrt(m.PHI + VPu + 1e-12);
+  double gmg = CS * Gs * (qf - qr) / nv;
+  if (gmd == 0) gmd = gmin * 2.0;  // ekv.py:331-336
+  if (gmg == 0) gmg = gmin * 2.0;
+  if (gms == 0) gms = -gmin * 2.0;
+  out[1] = gmd; out[2] = gmg; out[3] = gms;
+}
+
+// ---- square-law MOS ----------------------------------------------------------
+struct MosqP { double VTO, KP, GAMMA, PHI, LAMBDA, AVT, AKP, W, L, M, N, ZVT, ZKP; int NP; };
+
+// out[0] = CS*Ids; out[1..4] = stamp row "d" (cols d,g,s,b); out[5..8] = row "s".
+// Swapped case keeps only [d][s] and [s][d] (element-wise T1*stamp*T2, mosq.py:380-381).
+AHK_DEV void mosq_eval(const MosqP& m, double vds, double vgs, double vbs, double iea,
+                       double gmin, double* out) {
+  vds *= m.NP; vgs *= m.NP; vbs *= m.NP;  // mosq.py:552-582
+  int CS = +1;
+  if (vds < 0) { vgs = vgs - vds; vbs = vbs - vds; vds = -vds; CS = -1; }
+  double svt = 0, skp = 0;
+  if (m.ZVT != 0 || m.ZKP != 0) {  // mosq.py:584-594
+    double r = sqrt(2 * m.W * m.L);
+    svt = m.ZVT * m.AVT / r;
+    skp = m.ZKP * m.AKP / r;
+  }
+  double vsqrt1 = fmax(-vbs + 2 * m.PHI, 0.), vsqrt2 = fmax(2 * m.PHI, 0.);
+  double s1 = sqrt(vsqrt1), s2 = sqrt(vsqrt2);
+  double VT = m.VTO + svt + m.GAMMA * (s1 - s2);
+  double KWL = m.KP * m.W / m.L;
+  double ids, gmd, gm, gmb = 0;
+  if (vgs < VT) {  // mosq.py:642-643
+    ids = iea * (vgs / VT + vds / VT) / 100;
+    gmd = iea / VT / 100;
+    gm = iea / VT / 100;
+  } else {
+    double ov = vgs - VT;
+    if (vds < ov - 0.5 * m.LAMBDA * ov * ov) {  // mosq.py:647-654
+      ids = (skp + 1) * KWL * (ov * vds - .5 * vds * vds);
+      gmd = KWL * (vgs - vds - VT);
+    } else {
+      ids = (skp + 1) * .5 * KWL * ov * ov *
+            (1 + m.LAMBDA * (vds - vgs + VT + 0.25 * m.LAMBDA * ov * ov));
+      gmd = 0.5 * m.KP * m.LAMBDA * m.W / m.L * ov * ov;
+    }
+    if (vds < ov) {  // gm / gmb region test has no LAMBDA term (mosq.py:700,789)
+      gm = KWL * vds;
+      if (vsqrt1 > 0) gmb = m.KP * m.GAMMA * vds * m.W / (2 * m.L * s1);
+    } else {
+      double a = -m.GAMMA * (-s2 + s1) + vgs - m.VTO;
+      gm = -0.5 * m.KP * m.LAMBDA * m.W / m.L * a * a +
+           0.5 * m.KP * m.W / m.L *
+               (m.LAMBDA * (m.GAMMA * (-s2 + s1) + vds - vgs + m.VTO) + 1.0) *
+               (-2 * m.GAMMA * (-s2 + s1) + 2 * vgs - 2 * m.VTO);
+      if (vsqrt1 > 0) {
+        gmb += -0.25 * m.KP * m.GAMMA * m.LAMBDA * m.W * a * a / (m.L * s1);
+        gmb += +0.5 * m.KP * m.GAMMA * m.W *
+               (m.LAMBDA * (m.GAMMA * (s2 + s1) + vds - vgs + m.VTO) + 1.0) *
+               (-m.GAMMA * (s2 + s1) + vgs - m.VTO) / (m.L * s1);
+      }
+    }
+  }
+  double MN = m.M / m.N;
+  double Ids = m.NP * MN * ids;
+  gmd = (1 + skp) * gmd * MN;
+  gm = (1 + skp) * gm * MN;
+  gmb = m.NP * (1 + skp) * gmb * MN;
+  if (gmd == 0) gmd = gmin * 2;  // mosq.py:370-375
+  if (gm == 0) gm = gmin * 2;
+  if (gmb == 0) gmb = -2 * gmin;
+  out[0] = CS * Ids;
+  if (CS == 1) {
+    out[1] = gmd; out[2] = gm; out[3] = -gmd - gmb - gm; out[4] = gmb;
+    out[5] = -gmd; out[6] = -gm; out[7] = gmd + gm + gmb; out[8] = -gmb;
+  } else {
+    out[1] = 0; out[2] = 0; out[3] = -gmd - gmb - gm; out[4] = 0;
+    out[5] = -gmd; out[6] = 0; out[7] = 0; out[8] = 0;
+  }
+}
+
+// ---- voltage-controlled switch -------------------------------------------------
+struct SwP { double VT, VH, RON, ROFF; };
+
+// out[0] = i, out[1] = go, out[2] = gm; *is_on is the hysteresis state, updated on
+// every evaluation like the reference's _update_status (switch.py:342-360; the
+// three calls per iteration see the same vin, so one update is equivalent).
+AHK_DEV void switch_eval(const SwP& m, double vout, double vin, double gmin,
+                         double* is_on, double* out) {
+  double A = (m.RON - m.ROFF) / 2, B = (m.RON + m.ROFF) / 2.;
+  for (int rep = 0; rep < 2; rep++) {  // 2nd pass: status after a flip (idempotent)
+    int on = *is_on != 0;
+    double V = m.VT + m.VH * 2 * (!on) - m.VH;
+    double V2 = m.VT + m.VH * 2 * (on) - m.VH;
+    double R1 = A * tanh((vin - V) * 1e2) + B;
+    double R2 = A * tanh((vin - V2) * 1e2) + B;
+    if (vin > V && !on && R1 - R2 == 0.0) { on = 1; V = m.VT + m.VH * 2 * (!on) - m.VH; }
+    if (vin < V && on && R1 - R2 == 0.0) { on = 0; }
+    *is_on = on;
+  }
+  int on = *is_on != 0;
+  double V = m.VT + m.VH * 2 * (!on) - m.VH;
+  double R = A * tanh((vin - V) * 1e2) + B;
+  out[0] = vout / R;
+  out[1] = 1. / R;
+  double th = tanh(1e2 * (V - vin));
+  double den = A * th - B;
+  out[2] = A * 1e2 * (th * th - 1) / (den * den) + gmin;  // switch.py:393-399
+}
+
+// ---- source waveforms -------------------------------------------------------------
+AHK_DEV double tf_eval(int kind, const double* q, double time) {
+  const double PI = 3.141592653589793;
+  switch (kind) {
+    case 1: {  // pulse
+      double v1 = q[0], v2 = q[1], td = q[2], tr = q[3], pw = q[4], tf = q[5], per = q[6];
+      time = time - per * (double)(long long)(time / per);
+      if (time < td) return v1;
+      if (time < td + tr) return v1 + ((v2 - v1) / tr) * (time - td);
+      if (time < td + tr + pw) return v2;
+      if (time < td + tr + pw + tf) return v2 + ((v1 - v2) / tf) * (time - (td + tr + pw));
+      return v1;
+    }
+    case 2: {  // sin
+      double vo = q[0], va = q[1], fr = q[2], td = q[3], th = q[4], phi = q[5];
+      if (time < td) return vo + va * sin(PI * phi / 180.);
+      return vo + va * exp((td - time) * th) * sin(2 * PI * fr * (time - td) + PI * phi / 180.);
+    }
+    case 3: {  // exp
+      double v1 = q[0], v2 = q[1], td1 = q[2], tau1 = q[3], td2 = q[4], tau2 = q[5];
+      if (time < td1) return v1;
+      if (time < td2) return v1 + (v2 - v1) * (1 - exp(-1 * (time - td1) / tau1));
+      return v1 + (v2 - v1) * (1 - exp(-1 * (time - td1) / tau1)) +
+             (v1 - v2) * (1 - exp(-1 * (time - td2) / tau2));
+    }
+    case 4: {  // sffm
+      double vo = q[0], va = q[1], fc = q[2], mdi = q[3], fs = q[4], td = q[5];
+      if (time <= td) return vo;
+      return vo + va * sin(2 * PI * fc * (time - td) + mdi * sin(2 * PI * fs * (time - td)));
+    }
+    case 5: {  // am
+      double sa = q[0], fc = q[1], fm = q[2], oc = q[3], td = q[4];
+      if (time <= td) return 0.;
+      return sa * (oc + sin(2 * PI * fm * (time - td))) * sin(2 * PI * fc * (time - td));
+    }
+  }
+  return 0;
+}
+
+}  // namespace ahk

@@ -1,0 +1,77 @@
+// program.h — the compiled, topology-only "stamp program" shared by every
+// instance of a batch, plus the shared-memory layout of one instance.
+// Built on the host from the ahk_circuit element table (program.cpp); read
+// on the device through pointers into one read-only global allocation.
+#pragma once
+#include "../../include/ahkab_b200.h"
+
+namespace ahk {
+
+#define AHK_SMALL_NMAX 64   // shared-memory engine: pivot mask is one 64-bit word
+
+enum { K_R = 1, K_G, K_VDE, K_E, K_H, K_F, K_C, K_L, K_K };
+
+struct LinOp {      // one linear element's contribution to MNA (Mv) or D (Dv)
+  int kind, pbase, aux0, aux1;
+  int pos[6];       // indices into the merged position list, -1 = ground
+};
+
+struct SrcOp {      // independent source: N, Tt(t), Nac
+  int is_v, elem, pbase, tf, has_ac;
+  int row0, row1;   // V: row0 = KVL row; I: rows of n1, n2 (-1 = ground)
+};
+
+struct DevOp {      // non-linear device
+  int type, pbase, mbase, flags;
+  int node[4];      // reduced indices (-1 ground): D n1,n2; MOS d,g,s,b; SW n1,n2,sn1,sn2
+  int dout;         // first slot of this device's outputs
+  int active;       // 0: both output nodes grounded -> never evaluated (dc_analysis.py:863)
+};
+
+struct Opts {
+  double vea, ver, iea, ier, gmin, cmin, hmin;
+  double nl_voltages_lock_factor, transient_aposteriori_step_threshold;
+  int nl_voltages_lock, nr_damp_first_iters, dc_max_nr_iter, transient_max_nr_iter,
+      ac_max_nr_iter, use_standard_solve_method, use_gmin_stepping, use_source_stepping,
+      transient_prediction_as_x0, transient_use_aposteriori_step_control,
+      transient_max_time_iter, reserved;
+};
+
+struct Prog {
+  int n, nv1, npos, nlin, nsrc, ntd, ndev, ndout, nlock, nguess, nparams, nac;
+  const int* row_ptr;             // [n+1] positions are sorted by (row, col)
+  const unsigned short* pcol;     // [npos]
+  const unsigned short* prowi;    // [npos] row of each position
+  const unsigned char* pdiag;     // [npos] node-row diagonal: gets Gmin / cmin
+  const int* nl_ptr;              // [npos+1] CSR of device contributions per position
+  const short* nl_src;            //   index into dout
+  const signed char* nl_sgn;
+  const int* tx_ptr;              // [n+1] CSR of device currents per row
+  const short* tx_src;
+  const signed char* tx_sgn;
+  // deterministic gather form of the linear MNA stamps (used by the large-n path):
+  // value(pos) = sum over terms of  kind 1: sgn/P(slot)  kind 2: sgn*P(slot)  kind 3: sgn
+  const int* term_ptr;            // [npos+1]
+  const int* term_slot;
+  const signed char* term_kind;   // +-1, +-2, +-3
+  const LinOp* lin;
+  const SrcOp* src;
+  const DevOp* dev;
+  const int* lock;                // [nlock][2] raw node numbers (0 = ground)
+  const double* guessG;           // [n][nguess]
+  const int* gslot;
+  const double* gscale;
+  const double* gconst;
+  const double* nominal;          // [nparams]
+  const int* slot_vary;           // [nparams] row of vary[] or -1
+};
+
+struct Layout {     // offsets in doubles inside one instance's slice
+  int RS;           // row stride of A (odd, >= n+1)
+  int A, x, dx, T, res, Bv, Mv, Dv, Nd, Nc, Ntr, dout, dst, x1, xs, xacc;
+  int hx, hdx, ht, C0, pred, bytes;
+  int buflen;
+  int stride;       // doubles per instance (padded: stride % 16 == (G*RS) % 16)
+};
+
+}  // namespace ahk

@@ -1,0 +1,216 @@
+"""Engine: one compiled topology on one GPU, called through the C-ABI.
+
+PyTorch is the plumbing only — device buffers, pinned staging, streams; the
+arithmetic happens in libahkab_b200.so (hand-written sm_100a CUDA).  There is
+no CPU path: constructing an Engine without a CUDA device raises."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi, options as _options
+from . import compile as _compile
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine(object):
+    """engine = Engine(circ, batch); engine.op() / .dc_sweep() / .tran() / .ac()
+
+    Results are dicts of torch tensors on the device, batch axis first."""
+
+    def __init__(self, circ, batch=None, opts=None, device=None, flat=None):
+        if not torch.cuda.is_available():
+            raise EngineError("ahkab_b200 needs a CUDA device (B200); there is "
+                              "no CPU fallback")
+        self.lib = _abi.load_library()
+        self.device = torch.device(device if device is not None else
+                                   'cuda:%d' % torch.cuda.current_device())
+        self.flat = flat if flat is not None else _compile.flatten(circ, batch)
+        self.circ = circ
+        self.n = self.flat.n
+        self.B = self.flat.B if self.flat.B is not None else 1
+        self._desc = _abi.CircuitDesc(self.flat)
+        o = _options.snapshot()
+        if opts:
+            o.update(opts)
+        self.opts = o
+        self._opts = _abi.make_options(o)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_create(C.byref(self._desc.c), C.byref(self._opts),
+                                     C.byref(h))
+        if rc != 0:
+            raise EngineError(self._err())
+        self._h = h
+        self._slots = np.ascontiguousarray(self.flat.vary_slots, np.int32)
+        self._vary_host = None
+        self.vary = None
+        self.set_vary(self.flat.vary)
+
+    # -- plumbing ---------------------------------------------------------------
+    def _err(self):
+        return (self.lib.ahk_last_error() or b'').decode()
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            try:
+                self.lib.ahk_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def set_vary(self, vary, non_blocking=True):
+        """Upload per-instance values [n_vary][B] (numpy, or a pinned / device
+        torch tensor).  This is the H2D copy of an end-to-end step."""
+        if isinstance(vary, np.ndarray):
+            if self._vary_host is None or tuple(self._vary_host.shape) != vary.shape:
+                self._vary_host = torch.empty(vary.shape, dtype=torch.float64,
+                                              pin_memory=True)
+            self._vary_host.numpy()[...] = vary
+            vary = self._vary_host
+        if vary.device.type != 'cuda':
+            if self.vary is None or self.vary.shape != vary.shape:
+                self.vary = torch.empty(vary.shape, dtype=torch.float64,
+                                        device=self.device)
+            self.vary.copy_(vary, non_blocking=non_blocking)
+        else:
+            self.vary = vary.contiguous()
+        if self.vary.numel():
+            self.B = self.vary.shape[1]
+        return self
+
+    def set_options(self, **kw):
+        self.opts.update(kw)
+        self._opts = _abi.make_options(self.opts)
+        if self.lib.ahk_set_options(self._h, C.byref(self._opts)) != 0:
+            raise EngineError(self._err())
+
+    def set_group(self, lanes):
+        if self.lib.ahk_set_group(self._h, int(lanes)) != 0:
+            raise EngineError(self._err())
+
+    def _batch(self):
+        b = _abi.ahk_batch()
+        b.B = self.B
+        b.n_vary = len(self._slots)
+        b.vary_slots = self._slots.ctypes.data_as(C.POINTER(C.c_int32))
+        b.vary = self.vary.data_ptr() if self.vary.numel() else None
+        return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new(self, shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _x0(self, x0):
+        if x0 is None:
+            return None
+        x0 = torch.as_tensor(x0, dtype=torch.float64, device=self.device)
+        if x0.dim() == 1 or (x0.dim() == 2 and x0.shape[0] != self.B and
+                             x0.shape[-1] == 1):
+            x0 = x0.reshape(1, -1).expand(self.B, self.n)
+        x0 = x0.reshape(self.B, self.n).contiguous()
+        return x0
+
+    def elem_index(self, part_id):
+        for i, e in enumerate(self.circ):
+            if e.part_id.lower() == part_id.lower():
+                return i
+        raise ValueError("element %s not found" % part_id)
+
+    # -- analyses -----------------------------------------------------------------
+    def op(self, x0=None, use_guess=True, want_resid=True):
+        x0 = self._x0(x0)
+        x = self._new((self.B, self.n))
+        resid = self._new((self.B, self.n)) if want_resid else None
+        iters = self._new((self.B,), torch.int32)
+        status = self._new((self.B,), torch.int32)
+        b = self._batch()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_op(self._h, C.byref(b), _ptr(x0),
+                                 int(bool(use_guess)), _ptr(x), _ptr(resid),
+                                 _ptr(iters), _ptr(status), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(x=x, resid=resid, iters=iters, status=status)
+
+    def dc_sweep(self, source, sweep_values, x0=None, use_guess=True):
+        src = source if isinstance(source, int) else self.elem_index(source)
+        sweep = np.ascontiguousarray(sweep_values, np.float64)
+        P = len(sweep)
+        x0 = self._x0(x0)
+        x = self._new((self.B, P, self.n))
+        iters = self._new((self.B, P), torch.int32)
+        status = self._new((self.B, P), torch.int32)
+        b = self._batch()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_dc_sweep(
+                self._h, C.byref(b), src,
+                sweep.ctypes.data_as(C.POINTER(C.c_double)), P, _ptr(x0),
+                int(bool(use_guess)), _ptr(x), _ptr(iters), _ptr(status),
+                self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(x=x, iters=iters, status=status, sweep=sweep)
+
+    def tran(self, x0, tstart, tstep, tstop, method='TRAP',
+             use_step_control=True, max_rows=None):
+        method = method.upper()
+        if method not in _abi.METHODS:
+            raise ValueError("unknown method %s" % method)
+        if max_rows is None:
+            max_rows = self.default_max_rows(tstart, tstep, tstop,
+                                             use_step_control)
+        x0 = self._x0(x0)
+        t = self._new((self.B, max_rows))
+        x = self._new((self.B, max_rows, self.n))
+        rows = self._new((self.B,), torch.int32)
+        counters = self._new((self.B, 4), torch.int32)
+        status = self._new((self.B,), torch.int32)
+        b = self._batch()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_tran(
+                self._h, C.byref(b), _ptr(x0), float(tstart), float(tstep),
+                float(tstop), _abi.METHODS[method], int(bool(use_step_control)),
+                int(max_rows), _ptr(t), _ptr(x), _ptr(rows), _ptr(counters),
+                _ptr(status), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(t=t, x=x, rows=rows, counters=counters, status=status)
+
+    @staticmethod
+    def default_max_rows(tstart, tstep, tstop, use_step_control):
+        nominal = int(np.ceil((tstop - tstart) / tstep)) + 2 if tstep > 0 else 16
+        if not use_step_control:
+            return nominal + 2
+        # LTE control starts at (tstop-tstart)/9999 and may at most double per
+        # step; 64x the nominal count (min 4096) covers stiff oscillators, the
+        # ROWS_FULL status bit reports the rare overflow.
+        return max(4096, 64 * nominal)
+
+    def ac(self, omegas, x_op=None):
+        om = np.ascontiguousarray(omegas, np.float64)
+        P = len(om)
+        x_op = self._x0(x_op)
+        xo = self._new((self.B, P, self.n, 2))
+        status = self._new((self.B,), torch.int32)
+        b = self._batch()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_ac(self._h, C.byref(b), _ptr(x_op),
+                                 om.ctypes.data_as(C.POINTER(C.c_double)), P,
+                                 _ptr(xo), _ptr(status), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(x=torch.view_as_complex(xo), status=status, omegas=om)
+
+    def launch_count(self):
+        return int(self.lib.ahk_launch_count())

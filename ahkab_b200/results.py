@@ -1,0 +1,242 @@
+"""Results objects with a leading batch axis.
+
+Same variable names, ordering and dict-like access as the reference's
+`op_solution`, `dc_solution`, `tran_solution`, `ac_solution`
+(ahkab/results.py:245-853): `V<node>` for the internal nodes 1..nv-1 in creation
+order, then `I(<PART_ID>)` for the voltage-defined elements in circuit order;
+OP/TRAN names are upper-cased, DC/AC keep the node's case; lookups are
+case-insensitive.  The reference streams every row to a tab-separated text
+file and re-parses it on each access (results.py:121-124,178-186); here the
+data stays in tensors (device until first host access) — no per-row file I/O.
+
+Shapes:  op[var] -> (B,)   dc[var] -> (B, npts)   tran[var] -> (B, max_rows)
+(rows beyond `rows[b]` are NaN)   ac[var] -> (B, npts) complex128."""
+import numpy as np
+
+from . import circuit as _c
+from . import _abi
+
+
+def _varnames(circ, upper):
+    nv_1 = circ.get_nodes_number() - 1
+    names, units = [], {}
+    for index in range(nv_1):
+        v = "V%s" % (str(circ.nodes_dict[index + 1]),)
+        v = v.upper() if upper else v
+        names.append(v)
+        units[v] = "V"
+    for elem in circ:
+        if _c.is_elem_voltage_defined(elem):
+            v = "I(%s)" % (elem.part_id.upper(),)
+            v = v.upper() if upper else v
+            names.append(v)
+            units[v] = "A"
+    return names, units
+
+
+def _host(t):
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t
+    return t.detach().cpu().numpy()
+
+
+class solution(object):
+    """Base: dict-like access by variable name (results.py:127-243)."""
+    sol_type = None
+
+    def __init__(self, circ, raw):
+        self.netlist_title = circ.title
+        self.raw = raw          # dict of (device) tensors from the engine
+        self._np = {}
+        self.variables = []
+        self.units = {}
+
+    def _get(self, key):
+        if key not in self._np:
+            self._np[key] = _host(self.raw[key])
+        return self._np[key]
+
+    def _index(self, name):
+        up = [v.upper() for v in self.variables]
+        try:
+            return up.index(name.upper())
+        except ValueError:
+            raise KeyError(name)
+
+    def __len__(self):
+        return len(self.variables)
+
+    def __contains__(self, name):
+        return name.upper() in [v.upper() for v in self.variables]
+
+    has_key = __contains__
+
+    def keys(self):
+        return list(self.variables)
+
+    def values(self):
+        return [self[v] for v in self.variables]
+
+    def items(self):
+        return list(zip(self.keys(), self.values()))
+
+    def __iter__(self):
+        return iter(self.items())
+
+    def get(self, name, default=None):
+        try:
+            return self[name]
+        except KeyError:
+            return default
+
+    @property
+    def status(self):
+        return self._get('status')
+
+    @property
+    def ok(self):
+        return (self.status & _abi.ST_OK) != 0
+
+
+class op_solution(solution):
+    """results.py:245-551 with a batch axis: sol['VN1'] -> (B,)."""
+    sol_type = "OP"
+
+    def __init__(self, circ, raw):
+        solution.__init__(self, circ, raw)
+        self.variables, self.units = _varnames(circ, upper=True)
+
+    @property
+    def iterations(self):
+        return self._get('iters')
+
+    @property
+    def x(self):
+        return self._get('x')
+
+    @property
+    def errors(self):
+        return self._get('resid')
+
+    def asarray(self):
+        """(B, n) — the reference returns (n, 1) for its single instance."""
+        return self.x
+
+    def __getitem__(self, name):
+        return self.x[:, self._index(name)]
+
+    @property
+    def gmin_check_failed(self):
+        return (self.status & _abi.ST_GMIN_CHECK) != 0
+
+
+class dc_solution(solution):
+    """results.py:714-782: variables[0] is the sweep variable."""
+    sol_type = "DC"
+
+    def __init__(self, circ, raw, sweepvar, stype):
+        solution.__init__(self, circ, raw)
+        names, units = _varnames(circ, upper=False)
+        self.variables = [sweepvar] + names
+        self.units = dict(units)
+        self.units[sweepvar] = 'V' if sweepvar[0] == 'V' else 'A'
+        self.stype = stype
+
+    def asarray(self):
+        """(B, 1 + n, npts): sweep axis first, like the reference's rows."""
+        x = self._get('x')
+        sw = np.broadcast_to(self.raw['sweep'][None, None, :],
+                             (x.shape[0], 1, x.shape[1]))
+        return np.concatenate((sw, np.transpose(x, (0, 2, 1))), axis=1)
+
+    def __getitem__(self, name):
+        i = self._index(name)
+        if i == 0:
+            return self.raw['sweep']
+        return self._get('x')[:, :, i - 1]
+
+    def get_x(self):
+        return self.raw['sweep']
+
+    def get_xlabel(self):
+        return self.variables[0]
+
+
+class tran_solution(solution):
+    """results.py:784-853: 'T' then the unknowns; no row for tstart."""
+    sol_type = "TRAN"
+
+    def __init__(self, circ, raw, tstart, tstop, method):
+        solution.__init__(self, circ, raw)
+        names, units = _varnames(circ, upper=True)
+        self.variables = ["T"] + names
+        self.units = dict(units)
+        self.units["T"] = "s"
+        self.tstart, self.tstop, self.method = tstart, tstop, method
+
+    @property
+    def rows(self):
+        return self._get('rows')
+
+    @property
+    def counters(self):
+        """(B, 4): dc_solve calls, NR iterations, LTE rejections, NR step cuts."""
+        return self._get('counters')
+
+    def _masked(self, a):
+        rows = self.rows
+        m = np.arange(a.shape[1])[None, :] >= rows[:, None]
+        a = np.array(a, copy=True)
+        a[m] = np.nan
+        return a
+
+    def __getitem__(self, name):
+        i = self._index(name)
+        if i == 0:
+            return self._masked(self._get('t'))
+        return self._masked(self._get('x')[:, :, i - 1])
+
+    def instance(self, b):
+        """(1 + n, rows[b]) array of instance b — the reference's asarray()."""
+        r = int(self.rows[b])
+        return np.concatenate((self._get('t')[b, None, :r],
+                               self._get('x')[b, :r, :].T), axis=0)
+
+    def get_x(self):
+        return self['T']
+
+    def get_xlabel(self):
+        return "T"
+
+
+class ac_solution(solution):
+    """results.py:554-712: 'f' [Hz] then complex unknowns."""
+    sol_type = "AC"
+
+    def __init__(self, circ, raw, stype):
+        solution.__init__(self, circ, raw)
+        names, units = _varnames(circ, upper=False)
+        self.variables = ["f"] + names
+        self.units = dict(units)
+        self.units["f"] = "Hz"
+        self.stype = stype
+
+    def __getitem__(self, name):
+        i = self._index(name)
+        if i == 0:
+            return self.raw['omegas'] / np.pi / 2
+        return self._get('x')[:, :, i - 1]
+
+    def asarray(self):
+        x = self._get('x')
+        f = np.broadcast_to((self.raw['omegas'] / np.pi / 2)[None, None, :],
+                            (x.shape[0], 1, x.shape[1])).astype(np.complex128)
+        return np.concatenate((f, np.transpose(x, (0, 2, 1))), axis=1)
+
+    def get_x(self):
+        return self['f']
+
+    def get_xlabel(self):
+        return "f"
