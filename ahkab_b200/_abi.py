@@ -62,7 +62,7 @@ METHODS = {'IMPLICIT_EULER': 0, 'TRAP': 1, 'GEAR1': 11, 'GEAR2': 12,
 
 EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_group', 'ahk_last_error', 'ahk_launch_count', 'ahk_op',
-           'ahk_dc_sweep', 'ahk_tran', 'ahk_ac')
+           'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64')
 
 
 def _dp(a):
@@ -151,6 +151,8 @@ def load_library(path=None):
     lib.ahk_tran.restype = C.c_int
     lib.ahk_ac.argtypes = [vp, bp, vp, C.POINTER(dbl), C.c_int, vp, vp, vp]
     lib.ahk_ac.restype = C.c_int
+    lib.ahk_probe_fp64.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.ahk_probe_fp64.restype = C.c_int
     if path == LIB_PATH:
         _lib = lib
     return lib

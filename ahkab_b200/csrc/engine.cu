@@ -98,6 +98,21 @@ __global__ void __launch_bounds__(128) k_ac(const __grid_constant__ KAc k) {
   run_ac<G>(c, k.AL, a);
 }
 
+// FP64 pipe probe: 8 independent DFMA chains per thread, no memory traffic in the
+// loop.  bench.py times it to get the measured FP64 roofline denominator
+// (MEASURED_PEAKS.json has no FP64 figure).
+__global__ void __launch_bounds__(256) k_probe_fp64(int iters, double seed, double* out) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+         a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.999999 + 1e-9 * threadIdx.x, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) out[0] = s;   // keeps the chains live, (almost) never writes
+}
+
 __global__ void k_fill_i32(int* p, long long n, int v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -365,6 +380,14 @@ int ahk_set_group(ahk_engine* e, int lanes) {
   if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
     return fail("group must be 0,1,2,4,8,16,32");
   e->group = lanes;
+  return 0;
+}
+
+int ahk_probe_fp64(int blocks, int threads, int iters, double* out, void* stream) {
+  if (blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0 || !out)
+    return fail("ahk_probe_fp64: bad argument");
+  k_probe_fp64<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, 1.0, out);
+  CK(cudaGetLastError());
   return 0;
 }
 

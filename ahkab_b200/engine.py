@@ -212,5 +212,36 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(x=torch.view_as_complex(xo), status=status, omegas=om)
 
+    def to_host(self, raw, keys=None):
+        """Device->host read of a result dict into cached PINNED buffers
+        (asynchronous on the current stream; synchronise before reading).
+        This is the D2H copy of an end-to-end step."""
+        if not hasattr(self, '_pinned'):
+            self._pinned = {}
+        out = {}
+        for k, v in raw.items():
+            if not torch.is_tensor(v) or (keys is not None and k not in keys):
+                continue
+            src = torch.view_as_real(v) if v.is_complex() else v
+            key = (k, tuple(src.shape), src.dtype)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                self._pinned[key] = buf
+            buf.copy_(src, non_blocking=True)
+            out[k] = buf
+        return out
+
+    def probe_fp64(self, iters=4096, blocks=None, threads=256):
+        """Launch the FP64-FMA probe kernel (diagnostics); returns its flop count."""
+        blocks = blocks or 148 * 8
+        if not hasattr(self, '_probe_out'):
+            self._probe_out = self._new((8,))
+        rc = self.lib.ahk_probe_fp64(int(blocks), int(threads), int(iters),
+                                     _ptr(self._probe_out), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return float(blocks) * threads * iters * 16.0
+
     def launch_count(self):
         return int(self.lib.ahk_launch_count())

@@ -1,0 +1,498 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the batched Newton/MNA hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2] [--only] [--no-cpu]
+
+One JSON line on stdout (rank 0).  A *step* is one pass of an analysis over one
+synthetic batch:
+
+  headline  c2  tests/diode_op operating point, 65536 instances  (BASELINE configs[1])
+  also      c1  Butterworth AC 4096 x 100 freq        -> instance-solves/s
+            c3  Colpitts OP + TRAP fixed step 16384   -> instance-timesteps/s
+            c4  ring3 GEAR2 + LTE 16384               -> instance-timesteps/s
+            c5  R-2R n=257 DC sweep 4096 x 10         -> instance-solves/s
+  (reported under "configs" in the same line; --only skips them)
+
+`value`   kernel path with the per-instance parameters already resident in HBM,
+          CUDA events on the launching stream, L2 flushed between timed steps.
+`e2e`     the same step through the Engine API with HOST buffers: pinned
+          H2D of the parameters, the analysis, pinned D2H of every result.
+N > 1     one process per GPU (torchrun), weak scaling: every rank runs its own
+          full-size batch (seed + rank), no data-path collective; the e2e step
+          ends with the NCCL gather of the per-instance iters/status words.
+--impl reference   the reference's algorithm on the host cores: the C
+          restatement in oracle/ (the reference itself is pure Python and does
+          not travel to the GPU box), OpenMP over all cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+UNITS = dict(c1='instance-solves/s', c2='instance-solves/s',
+             c3='instance-timesteps/s', c4='instance-timesteps/s',
+             c5='instance-solves/s')
+NAMES = dict(
+    c1='README Butterworth band-pass AC sweep, 100 log points, B=4096 (n=14 complex128)',
+    c2='tests/diode_op operating point, B=65536 (n=3)',
+    c3='tests/colpitts OP + TRAP fixed-step transient 250 steps, B=16384 (n=9, 1 EKV)',
+    c4='tests/ring3 GEAR2 + LTE step control transient to 50 ns, B=16384 (n=5, 6 EKV)',
+    c5='tests/r2r 256-node ladder DC sweep 10 points, B=4096 (n=257)')
+FULL_B = dict(c1=4096, c2=65536, c3=16384, c4=16384, c5=4096)
+# bounded samples for the CPU arm (instances), sized for a few seconds per step
+CPU_SAMPLE = dict(c1=4096, c2=65536, c3=2048, c4=256, c5=64)
+C4_MAX_ROWS = 3072
+
+
+def LU(n):
+    return 2.0 / 3.0 * n ** 3 + 2.0 * n ** 2
+
+
+# algorithmic flop per NR iteration: dense LU+solve, residual
+# mat-vec, device evaluations (diode ~120, EKV ~400 flop incl. transcendentals)
+NR_FLOP = dict(c2=LU(3) + 2 * 9 + 120, c3=LU(9) + 2 * 81 + 400,
+               c4=LU(5) + 2 * 25 + 6 * 400)
+AC_FLOP = 4 * LU(14) + 8 * 14 ** 2            # per (instance, frequency)
+# c5: two dense factorisations per instance amortised over the 10-point sweep +
+# per point two (residual mat-vec + forward/backward substitution)
+C5_FLOP = (2 * LU(257) - 2 * 2 * 257 ** 2) / 10.0 + 2 * (2 * 257 ** 2 + 2 * 257 ** 2)
+
+
+# ---------------------------------------------------------------------------------
+class Runner(object):
+    """One workload on one GPU: `step()` with inputs resident, `e2e()` from host."""
+
+    def __init__(self, name, seed_off=0, B=None):
+        import torch
+        import common
+        from ahkab_b200 import workloads as W
+        from ahkab_b200.circuit import Circuit
+        from ahkab_b200.engine import Engine
+        self.torch, self.common, self.W = torch, common, W
+        self.name = name
+        B = B or FULL_B[name]
+        seeds = dict(c1=0, c2=1, c3=2, c4=3, c5=4)
+        self.w = W.ALL[name](B=B, seed=seeds[name] + 1000 * seed_off)
+        self.circ = self.w.circuit(Circuit)
+        self.eng = Engine(self.circ, self.w.batch(), opts=self.w.opts)
+        self.B = B
+        self.vary_host = torch.empty(self.eng.vary.shape, dtype=torch.float64,
+                                     pin_memory=True)
+        self.vary_host.copy_(self.eng.vary)
+        torch.cuda.synchronize()
+        self.h2d = self.vary_host.numel() * 8
+        if name == 'c1':
+            self.om = common.c1_omegas()
+        if name == 'c5':
+            self.sw = common.c5_sweep()
+        if name == 'c4':
+            self.x0_host = torch.as_tensor(common.c4_x0(self.circ, B)).pin_memory()
+            self.x0 = self.x0_host.cuda()
+            self.h2d += self.x0_host.numel() * 8
+
+    def step(self):
+        e, W, n = self.eng, self.W, self.name
+        if n == 'c2':
+            return e.op()
+        if n == 'c1':
+            return e.ac(self.om)
+        if n == 'c3':
+            op = e.op(want_resid=False)
+            x0 = op['x'].clone()             # icmodified_x0 (dc_analysis.py:1143-1190)
+            x0[:, 1] = x0[:, 2] + 2.5        # c1 (nd, ns) ic = 2.5
+            x0[:, 6] = -1e-9                 # l1 ic = -1n
+            r = e.tran(x0, max_rows=256, **W.C3_TRAN)
+            r['op_iters'] = op['iters']
+            return r
+        if n == 'c4':
+            return e.tran(self.x0, max_rows=C4_MAX_ROWS, **W.C4_TRAN)
+        if n == 'c5':
+            return e.dc_sweep('V1', self.sw)
+
+    def e2e(self):
+        """host params -> device, analysis, every result tensor -> pinned host."""
+        self.eng.set_vary(self.vary_host)
+        if self.name == 'c4':
+            self.x0.copy_(self.x0_host, non_blocking=True)
+        raw = self.step()
+        host = self.eng.to_host(raw)
+        return raw, host
+
+    def d2h_bytes(self, host):
+        return int(sum(v.numel() * v.element_size() for v in host.values()))
+
+    def units(self, raw):
+        n = self.name
+        if n == 'c2':
+            return self.B
+        if n == 'c1':
+            return self.B * len(self.om)
+        if n == 'c5':
+            return self.B * len(self.sw)
+        return int(raw['rows'].sum().item())
+
+    def algo(self, raw):
+        """(flop, bytes) one step needs algorithmically."""
+        n, B, N = self.name, self.B, self.eng.n
+        nv = self.vary_host.shape[0]
+        if n == 'c2':
+            it = float(raw['iters'].sum().item())
+            return it * NR_FLOP['c2'], B * (8 * nv + 8 * N * 2 + 8)
+        if n == 'c1':
+            u = B * len(self.om)
+            return u * AC_FLOP, B * 8 * nv + u * 16 * N + 4 * B
+        if n == 'c5':
+            u = B * len(self.sw)
+            return u * C5_FLOP, B * 8 * nv + u * (8 * N + 8)
+        rows = float(raw['rows'].sum().item())
+        nr = float(raw['counters'][:, 1].sum().item())
+        if n == 'c3':
+            nr += float(raw['op_iters'].sum().item())
+        return nr * NR_FLOP[n], B * (8 * nv + 8 * N + 28) + rows * 8 * (N + 1)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while `active` is set."""
+
+    def __init__(self, torch_index):
+        threading.Thread.__init__(self, daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
+        self.stop = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(torch_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                idx = int(vis.split(',')[torch_index]) if vis else torch_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as ex:          # noqa
+            self.err = repr(ex)
+            self.h = None
+
+    def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        names = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown',
+                 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown'}
+        while not self.stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            else:
+                time.sleep(0.001)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [],
+                    "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class Timer(object):
+    def __init__(self, dist_on, device):
+        import torch
+        self.torch, self.dist_on = torch, dist_on
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist_on:
+            import torch.distributed as dist
+            dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, sampler=None):
+        """W untimed + K timed steps; L2 flushed before every timed step; returns
+        (sum of the K device durations in ms, max over ranks; last result)."""
+        torch = self.torch
+        r = None
+        for _ in range(warmup):
+            r = fn()
+        self.barrier()
+        if sampler is not None:
+            sampler.active.set()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        for a, b in ev:
+            self.flush.zero_()
+            a.record()
+            r = fn()
+            b.record()
+        self.barrier()
+        if sampler is not None:
+            sampler.active.clear()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if self.dist_on:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=self.flush.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, r
+
+
+def all_sum(v, dist_on, device):
+    if not dist_on:
+        return v
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def measure_fp64_peak(eng, timer):
+    """Measured FP64-FMA throughput of this GPU (TFLOP/s): best of 5 launches of
+    the library's probe kernel, CUDA events."""
+    import torch
+    best = 0.0
+    eng.probe_fp64(iters=1024)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        fl = eng.probe_fp64(iters=16384)
+        b.record()
+        torch.cuda.synchronize()
+        best = max(best, fl / (a.elapsed_time(b) * 1e-3) / 1e12)
+    return best
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---- CPU arm: the oracle (C restatement of the reference), OpenMP ---------------------
+def cpu_step_fn(name, B):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import oracle
+    import common
+    from ahkab_b200 import workloads as W
+    from ahkab_b200.circuit import Circuit
+    seeds = dict(c1=0, c2=1, c3=2, c4=3, c5=4)
+    w = W.ALL[name](B=B, seed=seeds[name])
+    circ = w.circuit(Circuit)
+    o = oracle.Oracle(circ, w.batch(), opts=w.opts)
+    if name == 'c2':
+        return (lambda: B), (lambda: o.op()), oracle.max_threads()
+    if name == 'c1':
+        om = common.c1_omegas()
+        return (lambda: B * len(om)), (lambda: o.ac(om)), oracle.max_threads()
+    if name == 'c5':
+        sw = common.c5_sweep()
+        return (lambda: B * len(sw)), (lambda: o.dc_sweep(0, sw)), oracle.max_threads()
+    box = {}
+    if name == 'c3':
+        def f():
+            x0 = common.c3_x0(o.op()['x'])
+            box['r'] = o.tran(x0, 0., W.C3_TRAN['tstep'], W.C3_TRAN['tstop'], 'TRAP',
+                              False, 256)
+    else:
+        x0 = common.c4_x0(circ, B)
+
+        def f():
+            box['r'] = o.tran(x0, 0., W.C4_TRAN['tstep'], W.C4_TRAN['tstop'], 'GEAR2',
+                              True, C4_MAX_ROWS)
+    return (lambda: int(box['r']['rows'].sum())), f, oracle.max_threads()
+
+
+def cpu_measure(name, steps, warmup):
+    B = CPU_SAMPLE[name]
+    units, f, cores = cpu_step_fn(name, B)
+    for _ in range(warmup):
+        f()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f()
+    dt = time.perf_counter() - t0
+    return dict(value=units() * steps / dt, unit=UNITS[name], cores=cores, kind='port',
+                sample='%d of %d instances of the same seeded batch, %d step(s), OpenMP '
+                       'over %d threads (oracle/ahk_oracle.c)' % (B, FULL_B[name], steps, cores)), \
+        dt / steps * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    names = [args.workload] + ([] if args.only else
+                               [c for c in ('c1', 'c3', 'c4', 'c5', 'c2') if c != args.workload])
+    out = None
+    cfgs = {}
+    for i, name in enumerate(names):
+        steps = args.steps if i == 0 else min(args.steps, 3)
+        warm = args.warmup if i == 0 else 1
+        if name in ('c3', 'c4', 'c5'):
+            steps, warm = min(steps, 5), min(warm, 1)
+        cb, ms = cpu_measure(name, steps, warm)
+        line = {"metric": UNITS[name].replace('/s', '/sec'), "value": cb['value'],
+                "unit": UNITS[name], "ms_per_step": ms, "steps": steps, "warmup": warm,
+                "cpu_baseline": cb,
+                "e2e": {"value": cb['value'], "unit": UNITS[name], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "config": {"workload": NAMES[name], "sample": cb['sample']}}
+        if i == 0:
+            out = line
+        else:
+            cfgs[name] = line
+    out.update({"impl": "reference", "n_gpus": args.gpus, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "gpu_launches": 0})
+    if cfgs:
+        out["configs"] = cfgs
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------
+def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_src, fp64_peak,
+              dist_on, device, want_cpu):
+    import torch
+    r = Runner(name, seed_off=rank)
+    eng = r.eng
+    # kernel path, inputs resident
+    l0 = eng.launch_count()
+    ms, raw = timer.timed(r.step, steps, warmup, sampler)
+    launches = (eng.launch_count() - l0) // (steps + warmup) * steps
+    units = all_sum(r.units(raw), dist_on, device)
+    flop, byts = r.algo(raw)
+    value = units * steps / (ms * 1e-3)
+    # end to end, host buffers
+    e2e_fn = r.e2e
+    if dist_on:
+        # the single result collective: gather the per-instance words to rank 0
+        from ahkab_b200 import dist as ahk_dist
+
+        def e2e_fn():
+            rr, hh = r.e2e()
+            ahk_dist.gather_rows(rr['status'].reshape(r.B, -1), r.B * world)
+            return rr, hh
+    ms_e, (raw_e, host) = timer.timed(e2e_fn, steps, warmup)
+    units_e = all_sum(r.units(raw_e), dist_on, device)
+    e2e_value = units_e * steps / (ms_e * 1e-3)
+    ok = int((raw['status'] & 1).sum().item()) if 'status' in raw else None
+    step_s = ms * 1e-3 / steps
+    line = {
+        "metric": UNITS[name].replace('/s', '/sec'), "value": value,
+        "unit": UNITS[name], "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if name != 'c1' else "complex128",
+        "data": "synthetic",
+        "config": {"workload": NAMES[name], "instances_per_gpu": r.B,
+                   "units_per_step_rank0": r.units(raw), "n_unknowns": eng.n,
+                   "l2": "flushed (512 MiB write) before every timed step",
+                   "parallelism": "batch sharded, %d rank(s), no data-path collective" % world,
+                   "status_ok_rank0": ok},
+        "e2e": {"value": e2e_value, "unit": UNITS[name], "ms_per_step": ms_e / steps,
+                "h2d_bytes_per_step": r.h2d, "d2h_bytes_per_step": r.d2h_bytes(host)},
+        "gpu_launches": int(launches),
+        "roofline": {
+            "bound": "fp64", "achieved": flop / step_s / 1e12, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": flop / step_s / 1e12 / fp64_peak if fp64_peak else None,
+            "peak_source": "measured in this run: DFMA probe kernel (ahk_probe_fp64), best of 5",
+            "algorithmic_flop_per_step": flop, "traffic": None,
+            "hbm": {"bound": "hbm", "achieved": byts / step_s / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
+                    "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},
+    }
+    if want_cpu and rank == 0 and world == 1:
+        cb, _ms = cpu_measure(name, 2 if name in ('c3', 'c4') else 3, 1)
+        line["cpu_baseline"] = cb
+    del r
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(UNITS))
+    ap.add_argument('--only', action='store_true', help='headline workload only')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback. "
+                         "Use --impl reference for the host-CPU arm.")
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    warmup = max(3, args.warmup)
+    timer = Timer(dist_on, device)
+    sampler = ClockSampler(local)
+    sampler.start()
+    hbm_peak, hbm_src = peaks()
+    probe = Runner('c2', B=1024)
+    fp64_peak = measure_fp64_peak(probe.eng, timer)
+    del probe
+    head = bench_one(args.workload, rank, world, timer, sampler, args.steps, warmup, hbm_peak,
+                     hbm_src, fp64_peak, dist_on, device, not args.no_cpu)
+    head["clocks"] = sampler.summary()
+    cfgs = {}
+    if not args.only:
+        for name in ('c1', 'c3', 'c4', 'c5', 'c2'):
+            if name == args.workload:
+                continue
+            heavy = name in ('c3', 'c4', 'c5')
+            cfgs[name] = bench_one(name, rank, world, timer, None,
+                                   min(args.steps, 3 if heavy else 10), 3, hbm_peak, hbm_src,
+                                   fp64_peak, dist_on, device, not args.no_cpu)
+        head["configs"] = cfgs
+    sampler.stop.set()
+    head["gpu"] = torch.cuda.get_device_name(local)
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(head), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -174,6 +174,14 @@ const char* ahk_last_error(void);
 /* Number of kernel launches issued by this library so far (all engines). */
 int64_t ahk_launch_count(void);
 
+/* Diagnostics (no reference counterpart): launches an FP64-FMA-only kernel,
+ * blocks x threads (<= 256) threads each running 8 independent chains of
+ * `iters` DFMAs = blocks*threads*iters*16 flop.  bench.py times it with CUDA
+ * events to obtain the measured FP64 roofline denominator.  `out` is a device
+ * pointer to at least one double.  Not counted by ahk_launch_count(). */
+int ahk_probe_fp64(int blocks, int threads, int iters, double* out,
+                   void* stream);
+
 /* Operating point — replaces dc_analysis.op_analysis
  * (ahkab/dc_analysis.py:598-687): guess -> dc_solve with Gmin -> dc_solve
  * without Gmin from x1 -> gmin_check; iterations = n1 + n2.
