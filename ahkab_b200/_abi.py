@@ -62,7 +62,8 @@ METHODS = {'IMPLICIT_EULER': 0, 'TRAP': 1, 'GEAR1': 11, 'GEAR2': 12,
 
 EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_group', 'ahk_last_error', 'ahk_launch_count', 'ahk_op',
-           'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64')
+           'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64',
+           'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info')
 
 
 def _dp(a):
@@ -151,8 +152,33 @@ def load_library(path=None):
     lib.ahk_tran.restype = C.c_int
     lib.ahk_ac.argtypes = [vp, bp, vp, C.POINTER(dbl), C.c_int, vp, vp, vp]
     lib.ahk_ac.restype = C.c_int
+    lib.ahk_set_variant.argtypes = [vp, C.c_int, C.c_int]
+    lib.ahk_set_variant.restype = C.c_int
+    lib.ahk_variant_count.argtypes = [C.c_int]
+    lib.ahk_variant_count.restype = C.c_int
+    lib.ahk_variant_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    lib.ahk_variant_info.restype = C.c_int
     lib.ahk_probe_fp64.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     lib.ahk_probe_fp64.restype = C.c_int
     if path == LIB_PATH:
         _lib = lib
     return lib
+
+
+def variants(kind='real', lib=None):
+    """[(id, NC, R, G)] of the compiled kernel variants; kind = 'real' (OP / DC /
+    transient) or 'ac'.  NC = 0 is the generic shared-memory fallback."""
+    lib = lib or load_library()
+    k = 1 if kind == 'ac' else 0
+    out = []
+    buf = (C.c_int32 * 3)()
+    for i in range(lib.ahk_variant_count(k)):
+        lib.ahk_variant_info(k, i, buf)
+        out.append((i, int(buf[0]), int(buf[1]), int(buf[2])))
+    return out
+
+
+def fitting_variants(n, kind='real', lib=None):
+    """ids of the variants that can run a circuit with n unknowns."""
+    return [i for i, NC, R, G in variants(kind, lib)
+            if (NC == 0 and n <= 64) or (NC - 1 >= n and R * G >= n)]

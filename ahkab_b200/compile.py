@@ -48,7 +48,10 @@ def _src_block(elem, ov, B):
         abs_ac, arg_ac = 0.0, 0.0
     tfk, tfp = TF.encode(elem._time_function) if elem.is_timedependent \
         else (0, [])
-    tfp = list(tfp) + [0.0] * (N_TF - len(tfp))
+    if tfk:
+        tfp = list(tfp) + [0.0] * (N_TF - len(tfp))
+    else:
+        tfp = []      # no waveform -> no tf slots (keeps the staged block small)
     return [dc, abs_ac, arg_ac] + tfp, flags, tfk
 
 
@@ -145,7 +148,7 @@ def flatten(circ, batch=None):
             r['tf'] = tfk
             nm = ['dc_value', 'abs_ac', 'arg_ac'] + ['tf%d' % j
                                                      for j in range(N_TF)]
-            r['pbase'] = push(pid, list(zip(nm, blk)))
+            r['pbase'] = push(pid, list(zip(nm[:len(blk)], blk)))
         elif isinstance(e, (C.EVSource, C.GISource)):
             if 'value' in ov:
                 ov['alpha'] = ov.pop('value')

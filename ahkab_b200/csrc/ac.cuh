@@ -6,7 +6,9 @@
 // circuit (ac.py:293-305), i.e. exactly one iteration x = x_prev + solve(A,
 // -(A x_prev + Nac)); the same update is done here, frequency after frequency,
 // by the group that owns the instance (x_prev chains inside a frequency chunk).
-// Complex LU: partial pivoting on |re|+|im| as LAPACK zgesv (izamax) does.
+// Complex solve: partial pivoting on |re|+|im| as LAPACK zgesv (izamax) does;
+// register-resident Gauss-Jordan for Var<NC,R,G> (see core.cuh), LU in shared
+// memory for the generic fallback Var<0,0,G>.
 #pragma once
 #include "core.cuh"
 #include "program_build.hpp"
@@ -28,29 +30,34 @@ AHK_DEV cd cdivv(cd a, cd b) {   // Smith's algorithm (what C / numpy use)
 }
 
 struct AcLayout {
-  Layout L;          // real arrays shared with core.cuh (Mv, Dv, Bv, dout, dst, x=xr, bytes)
-  int RS;            // complex row stride (elements)
-  int Ac, xc, dxc, Nac;   // offsets in doubles of the complex arrays
+  Layout L;          // real arrays shared with core.cuh (Mv, Dv, Bv, dout, dst, x=xr, bytes, Pv)
+  int RS;            // complex row stride (elements) of the staging / fallback matrix
+  int Ac, xc, dxc, Nac, pvc;   // offsets in doubles of the complex arrays
   int stride;
 };
 
-inline AcLayout make_ac_layout(const HostProg& H, int G) {
+inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
   AcLayout A; std::memset(&A, 0, sizeof A);
   const Prog& h = H.hdr;
   const int n = h.n;
-  A.RS = n + 1;
+  A.RS = NC > 0 ? NC : n + 1;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
-  A.Ac = take(2 * n * A.RS);
+  A.Ac = take(2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
   A.xc = take(2 * n); A.dxc = take(2 * n); A.Nac = take(2 * n);
+  A.pvc = take(NC > 0 ? 4 * NC : 0);
   A.L.RS = A.RS;
   A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos);
   A.L.x = take(n);
   A.L.dout = take(h.ndout); A.L.dst = take(2 * h.ndev);
   A.L.bytes = take(16);
+  A.L.Pv = take(h.nparams); A.L.dcon = take(H.ncon);
   A.L.buflen = 1;
-  int want = (2 * G) % 16;   // 16-byte elements: spread consecutive groups over banks
-  while (off % 16 != want) off++;
+  if (G == 1) { if (off % 2 == 0) off++; }
+  else {
+    int want = (2 * G + 1) % 16;   // 16-byte elements: spread consecutive groups over banks
+    while (off % 16 != want) off++;
+  }
   A.stride = off;
   A.L.stride = off;
   return A;
@@ -65,8 +72,9 @@ struct AcArgs {
   int* status;
 };
 
+// generic fallback: complex LU + back-substitution on the shared-memory matrix
 template <int G>
-AHK_DEV int zlu_solve(Ctx& c, const AcLayout& AL) {
+AHK_DEV int zlu_solve_smem(Ctx& c, const AcLayout& AL) {
   const int n = c.p->n, RS = AL.RS;
   cd* A = (cd*)(c.sm + AL.Ac);
   cd* dx = (cd*)(c.sm + AL.dxc);
@@ -109,19 +117,92 @@ AHK_DEV int zlu_solve(Ctx& c, const AcLayout& AL) {
   return 1;
 }
 
-template <int G>
+// register-resident complex Gauss-Jordan (same scheme as gj_solve in core.cuh)
+template <class V>
+AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
+  const int NC = V::NC, R = V::R, G = V::G;
+  const int n = c.p->n;
+  cd* dx = (cd*)(c.sm + AL.dxc);
+  cd* pvb = (cd*)(c.sm + AL.pvc);   // [2][NC]
+  unsigned usedm = 0;
+  cd pd[R > 0 ? R : 1];
+  int ps[R > 0 ? R : 1];
+#pragma unroll
+  for (int s = 0; s < R; s++) { pd[s] = cd{1.0, 0.0}; ps[s] = 0; }
+#pragma unroll
+  for (int k = 0; k < NC - 1; k++) {
+    if (k < n) {
+      double best = -1.0;
+      int bi = -1;
+#pragma unroll
+      for (int s = 0; s < R; s++) {
+        const int r = c.sub + G * s;
+        const double v = fabs(a[s][k].re) + fabs(a[s][k].im);
+        const bool cand = r < n && !((usedm >> s) & 1u);
+        if (cand && (bi < 0 || v > best)) { best = v; bi = r; }
+      }
+      Grp<G>::argmax(best, bi, c.mask);
+      if (best == 0.0) return 0;
+      const int own = bi & (G - 1), slot = bi / G;
+      const bool mine = c.sub == own;
+      cd pv[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int j = k; j < NC; j++) {
+        cd t = a[0][j];
+#pragma unroll
+        for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
+        pv[j] = t;
+      }
+      if (G > 1) {
+        cd* buf = pvb + (k & 1) * NC;
+        if (mine) {
+#pragma unroll
+          for (int j = k; j < NC; j++) buf[j] = pv[j];
+        }
+        Grp<G>::sync(c.mask);
+#pragma unroll
+        for (int j = k; j < NC; j++) pv[j] = buf[j];
+      }
+      if (mine) {
+        usedm |= 1u << slot;
+#pragma unroll
+        for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+      }
+      const cd inv = cdivv(cd{1.0, 0.0}, pv[k]);
+#pragma unroll
+      for (int s = 0; s < R; s++) {
+        cd l = cmul(a[s][k], inv);
+        if (mine && slot == s) l = cd{0.0, 0.0};
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) {
+          a[s][j].re -= l.re * pv[j].re - l.im * pv[j].im;
+          a[s][j].im -= l.re * pv[j].im + l.im * pv[j].re;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < R; s++) {
+    const int r = c.sub + G * s;
+    if (r < n) dx[ps[s]] = cdivv(a[s][NC - 1], pd[s]);
+  }
+  Grp<G>::sync(c.mask);
+  return 1;
+}
+
+template <class V>
 AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
+  const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n, RS = AL.RS;
   c.L = &AL.L;
-  c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0;
-  build_values(c, true);
+  c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0; c.gadd = 0.0; c.G = G;
+  build_values<Var<0, 0, V::G> >(c, true);   // parameters, Mv, Dv, device constants
   double* Bv = c.sm + AL.L.Bv;
   const double* Mv = c.sm + AL.L.Mv;
   const double* Dv = c.sm + AL.L.Dv;
   double* xr = c.sm + AL.L.x;
-  cd* A = (cd*)(c.sm + AL.Ac);
   cd* x = (cd*)(c.sm + AL.xc);
   cd* dx = (cd*)(c.sm + AL.dxc);
   cd* Nac = (cd*)(c.sm + AL.Nac);
@@ -132,7 +213,7 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     Nac[i] = cd{0.0, 0.0};
   }
   Grp<G>::sync(c.mask);
-  if (p.ndev) eval_devices<G>(c, xr);   // J at the linearisation point (ac.py:417-443)
+  if (p.ndev) { eval_devices(c, xr); Grp<G>::sync(c.mask); }   // J at the linearisation point (ac.py:417-443)
   const double* dout = c.sm + AL.L.dout;
   for (int k = c.sub; k < p.npos; k += G) {
     double v = Mv[k];
@@ -154,24 +235,63 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     }
   }
   Grp<G>::sync(c.mask);
+  // register variants: dense staging rows of (Bv, Dv) pairs, filled once per instance;
+  // every frequency then builds its complex row with NC loads and no scatter
+  double* BD = c.sm + AL.Ac;
+  if constexpr (V::NC > 0) {
+    for (int i = c.sub; i < 2 * n * V::NC; i += G) BD[i] = 0.0;
+    Grp<G>::sync(c.mask);
+    for (int k = c.sub; k < p.npos; k += G) {
+      double* e = BD + 2 * ((int)p.prowi[k] * V::NC + p.pcol[k]);
+      e[0] = Bv[k]; e[1] = Dv[k];
+    }
+    Grp<G>::sync(c.mask);
+  }
   int st = AHK_ST_OK;
   for (int f = a.f0; f < a.f1; f++) {
     const double om = a.omegas[f];
-    for (int r = c.sub; r < n; r += G) {
-      cd* Ar = A + r * RS;
-      for (int j = 0; j < n; j++) Ar[j] = cd{0.0, 0.0};
-      cd s = Nac[r];
-      for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
-        int col = p.pcol[k];
-        cd v = {Bv[k], om * Dv[k]};
-        Ar[col] = v;
-        s = cadd(s, cmul(v, x[col]));
+    int ok;
+    if constexpr (V::NC > 0) {
+      const int NC = V::NC, R = V::R;
+      cd m[R > 0 ? R : 1][NC > 0 ? NC : 1];
+#pragma unroll
+      for (int s = 0; s < R; s++) {
+        const int r = c.sub + G * s;
+        if (r < n) {
+          const double* row = BD + 2 * r * NC;
+#pragma unroll
+          for (int j = 0; j < NC - 1; j++) m[s][j] = cd{row[2 * j], om * row[2 * j + 1]};
+          cd acc = Nac[r];
+          for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
+            const cd v = {Bv[k], om * Dv[k]};
+            acc = cadd(acc, cmul(v, x[p.pcol[k]]));
+          }
+          m[s][NC - 1] = cd{-acc.re, -acc.im};
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; j++) m[s][j] = cd{0.0, 0.0};
+        }
       }
-      Ar[n] = cd{-s.re, -s.im};
+      ok = zgj_solve<V>(c, AL, m);
+    } else {
+      cd* A = (cd*)(c.sm + AL.Ac);
+      for (int r = c.sub; r < n; r += G) {
+        cd* Ar = A + r * RS;
+        for (int j = 0; j < n; j++) Ar[j] = cd{0.0, 0.0};
+        cd s = Nac[r];
+        for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
+          int col = p.pcol[k];
+          cd v = {Bv[k], om * Dv[k]};
+          Ar[col] = v;
+          s = cadd(s, cmul(v, x[col]));
+        }
+        Ar[n] = cd{-s.re, -s.im};
+      }
+      Grp<G>::sync(c.mask);
+      ok = zlu_solve_smem<G>(c, AL);
     }
-    Grp<G>::sync(c.mask);
     double* xo = a.x_out + ((c.inst * a.npts + f) * n) * 2;
-    if (!zlu_solve<G>(c, AL)) {
+    if (!ok) {
       st = AHK_ST_SINGULAR;
       const double qn = nan("");
       for (int g = f; g < a.f1; g++) {

@@ -1,10 +1,19 @@
 #!/bin/sh
 # Builds ahkab_b200/lib/libahkab_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+# The translation units are compiled in parallel, then linked.
 set -e
 cd "$(dirname "$0")"
-mkdir -p ../lib
+mkdir -p ../lib ../lib/obj
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-  -Xcompiler -fPIC -shared ${AHK_PTXAS_V:+-Xptxas -v} \
-  -o ../lib/libahkab_b200.so engine.cu -lcudart
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${AHK_PTXAS_V:+-Xptxas -v}"
+pids=""
+for f in engine k_dc k_tran k_ac; do
+  $NVCC $FLAGS -c -o ../lib/obj/$f.o $f.cu > ../lib/obj/$f.log 2>&1 &
+  pids="$pids $!"
+done
+rc=0
+for p in $pids; do wait $p || rc=1; done
+for f in engine k_dc k_tran k_ac; do cat ../lib/obj/$f.log; done
+[ $rc -eq 0 ] || { echo "nvcc failed"; exit 1; }
+$NVCC -shared -o ../lib/libahkab_b200.so ../lib/obj/engine.o ../lib/obj/k_dc.o ../lib/obj/k_tran.o ../lib/obj/k_ac.o -lcudart
 echo "built ahkab_b200/lib/libahkab_b200.so"

@@ -1,13 +1,19 @@
 // core.cuh — per-instance Newton/MNA machinery of the small-circuit engine.
 //
 // Execution model: a GROUP of G lanes (G = 1,2,4,8,16,32, a sub-warp) owns one
-// circuit instance for the whole analysis.  The instance's dense augmented
-// matrix [n][RS], its iterate, history ring and device state live in shared
-// memory; matrix rows are owned cyclically by the lanes of the group
-// (row r -> lane r % G).  Devices are evaluated one per lane, the Jacobian is
-// assembled by a conflict-free gather, the LU uses implicit partial pivoting
-// (no row swaps) with a group arg-max.  Control scalars (time, step, counters)
-// are kept redundantly in registers and are group-uniform by construction.
+// circuit instance for the whole analysis.  A kernel variant Var<NC,R,G> fixes at
+// compile time the number of matrix columns NC (>= n+1, the last one is the
+// right-hand side), the rows per lane R and the lanes per instance G (R*G >= n):
+// row r lives in lane r % G, slot r / G, as NC doubles IN REGISTERS for the whole
+// linear solve (Gauss-Jordan with implicit partial pivoting, fully unrolled; the
+// pivot row crosses lanes through a shared-memory broadcast).  The per-instance
+// parameters are staged once from HBM into shared memory, together with the
+// sparse values of the linear stamps, the iterate, the history ring and the
+// device outputs; HBM is touched again only to write result rows.
+// Var<0,0,G> is the generic fallback for n > 31: run-time n, matrix in shared
+// memory, LU with back-substitution.
+// Control scalars (time, step, counters) are kept redundantly in registers and
+// are group-uniform by construction.
 //
 // What it replaces in the reference (all per instance, pure Python there):
 //   dc_analysis.mdn_solver / _update_J_and_Tx / get_td   dc_analysis.py:690-946
@@ -21,6 +27,9 @@
 #include "program.h"
 
 namespace ahk {
+
+template <int NC_, int R_, int G_>
+struct Var { static const int NC = NC_, R = R_, G = G_; };
 
 // ---- group primitives ---------------------------------------------------------
 #ifdef __CUDACC__
@@ -61,16 +70,20 @@ struct Ctx {
   const Opts* o;
   const Layout* L;
   double* sm;            // this instance's shared-memory slice
-  const double* vary;    // [n_vary][B]
+  const double* vary;    // [n_vary][B] in HBM
   long long B, inst;
   int sub;               // lane within the group
+  int G;                 // lanes per instance (run-time copy of Var::G)
   unsigned mask;         // lanes of the group
   int singular;
   int dc_src;            // DC sweep: element whose dc value is overridden
   double dc_val;
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
+  double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
 
-  AHK_MEM double P(int slot) const {
+  // per-instance parameter value: staged copy in shared memory
+  AHK_MEM double P(int slot) const { return sm[L->Pv + slot]; }
+  AHK_MEM double Pglobal(int slot) const {
     int v = p->slot_vary[slot];
     return v < 0 ? p->nominal[slot] : vary[(long long)v * B + inst];
   }
@@ -82,12 +95,21 @@ struct Ctx {
 
 AHK_DEV double V_of(const double* x, int node) { return node >= 0 ? x[node] : 0.0; }
 
-// ---- prologue: per-instance values of the linear stamps -------------------------
+// ---- prologue: stage the parameters, per-instance values of the linear stamps ---
 // dc_analysis.generate_mna_and_N (dc_analysis.py:949-1069) + transient.generate_D
 // (transient.py:472-561) evaluated into the compact value arrays Mv/Dv that
-// parallel the merged position list.  Serial (lane 0): runs once per instance.
+// parallel the merged position list; device constants and fresh device state.
+template <class V>
 AHK_DEV void build_values(Ctx& c, bool with_D) {
   const Prog& p = *c.p;
+  const int G = V::G;
+  double* Pv = c.sm + c.L->Pv;
+  for (int s = c.sub; s < p.nparams; s += G) Pv[s] = c.Pglobal(s);
+  if (V::NC > 0) {   // the dense staging matrix is zeroed once: only the sparsity
+    double* A = c.A();   // pattern (and the rhs column) is rewritten per iteration
+    for (int i = c.sub; i < p.n * c.L->RS; i += G) A[i] = 0.0;
+  }
+  Grp<V::G>::sync(c.mask);
   double* Mv = c.sm + c.L->Mv;
   double* Dv = c.sm + c.L->Dv;
   if (c.sub == 0) {
@@ -113,16 +135,26 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
     }
     if (with_D && c.o->cmin > 0)
       for (int k = 0; k < p.npos; k++) if (p.pdiag[k]) Dv[k] += c.o->cmin;
-    // fresh device state (diode.py:89, ekv.py:107, switch.py:98)
-    double* st = c.sm + c.L->dst;
-    for (int d = 0; d < p.ndev; d++) {
-      const DevOp& dv = p.dev[d];
-      st[2 * d] = st[2 * d + 1] = 0.0;
-      if (dv.type == AHK_D) st[2 * d] = .425;
-      if (dv.type == AHK_EKV) st[2 * d] = st[2 * d + 1] = 1.0;
-      if (dv.type == AHK_SW) st[2 * d] = c.P(dv.pbase);
+  }
+  // device constants + fresh device state (diode.py:89, switch.py:98): one device per lane
+  double* st = c.sm + c.L->dst;
+  double* dcon = c.sm + c.L->dcon;
+  for (int d = c.sub; d < p.ndev; d += G) {
+    const DevOp& dv = p.dev[d];
+    st[2 * d] = st[2 * d + 1] = 0.0;
+    if (dv.type == AHK_D) st[2 * d] = .425;
+    if (dv.type == AHK_SW) st[2 * d] = c.P(dv.pbase);
+    if (dv.type == AHK_EKV) {
+      EkvP m;
+      m.VTO = c.P(dv.mbase + 0); m.KP = c.P(dv.mbase + 1); m.GAMMA = c.P(dv.mbase + 2);
+      m.PHI = c.P(dv.mbase + 3); m.COX = c.P(dv.mbase + 4); m.LAMBDA = c.P(dv.mbase + 5);
+      m.XJ = c.P(dv.mbase + 6); m.UCRIT = c.P(dv.mbase + 7);
+      m.W = c.P(dv.pbase + 0); m.L = c.P(dv.pbase + 1); m.M = c.P(dv.pbase + 2);
+      m.N = c.P(dv.pbase + 3); m.NP = dv.flags;
+      ekv_setup(m, dcon + dv.con);
     }
   }
+  Grp<V::G>::sync(c.mask);
 }
 
 // N of generate_mna_and_N: DC current sources, then -V on the KVL rows.
@@ -142,13 +174,13 @@ AHK_DEV void build_N(Ctx& c) {
 }
 
 // ---- device evaluation: one device per lane ------------------------------------
-template <int G>
+// Not a template: one copy of the device models per kernel, whatever the variant.
 AHK_DEV void eval_devices(Ctx& c, const double* x) {
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   double* dout = c.sm + c.L->dout;
   double* dst = c.sm + c.L->dst;
-  for (int d = c.sub; d < p.ndev; d += G) {
+  for (int d = c.sub; d < p.ndev; d += c.G) {
     const DevOp& dv = p.dev[d];
     if (!dv.active) continue;
     double* out = dout + dv.dout;
@@ -163,15 +195,9 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
         diode_eval(m, V_of(x, dv.node[0]) - V_of(x, dv.node[1]), o.vea, o.gmin, st, out);
       } break;
       case AHK_EKV: {
-        EkvP m;
-        m.VTO = c.P(dv.mbase + 0); m.KP = c.P(dv.mbase + 1); m.GAMMA = c.P(dv.mbase + 2);
-        m.PHI = c.P(dv.mbase + 3); m.COX = c.P(dv.mbase + 4); m.LAMBDA = c.P(dv.mbase + 5);
-        m.XJ = c.P(dv.mbase + 6); m.UCRIT = c.P(dv.mbase + 7);
-        m.W = c.P(dv.pbase + 0); m.L = c.P(dv.pbase + 1); m.M = c.P(dv.pbase + 2);
-        m.N = c.P(dv.pbase + 3); m.NP = dv.flags;
         double vb = V_of(x, dv.node[3]);
-        ekv_eval(m, V_of(x, dv.node[0]) - vb, V_of(x, dv.node[1]) - vb,
-                 V_of(x, dv.node[2]) - vb, o.gmin, st, out);
+        ekv_eval(c.sm + c.L->dcon + dv.con, dv.flags, V_of(x, dv.node[0]) - vb,
+                 V_of(x, dv.node[1]) - vb, V_of(x, dv.node[2]) - vb, o.gmin, out);
       } break;
       case AHK_MOSQ: {
         MosqP m;
@@ -194,47 +220,114 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
       } break;
     }
   }
-  Grp<G>::sync(c.mask);
 }
 
-// ---- assembly: A = [Bv + J | -(Bv.x + T + Tx)], row-local, no conflicts -----------
+// ---- assembly: [Bv + J | -(Bv.x + T + Tx)], row-local, no conflicts ----------------
 // residuo = mna.dot(x) + T + Tx (dc_analysis.py:816); the matrix solved is mna + J.
-template <int G>
-AHK_DEV void assemble(Ctx& c) {
+// One row: writes the pattern entries into the staging row Ar, returns the rhs.
+AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
   const Prog& p = *c.p;
-  const int n = p.n, RS = c.L->RS;
-  double* A = c.A();
   const double* x = c.x();
   const double* Bv = c.sm + c.L->Bv;
-  const double* T = c.sm + c.L->T;
   const double* dout = c.sm + c.L->dout;
-  double* res = c.sm + c.L->res;
-  for (int r = c.sub; r < n; r += G) {
-    double* Ar = A + r * RS;
-    for (int j = 0; j < n; j++) Ar[j] = 0.0;
-    double s = 0.0;
-    for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
-      double v = Bv[k];
-      int col = p.pcol[k];
-      s += v * x[col];
-      for (int q = p.nl_ptr[k]; q < p.nl_ptr[k + 1]; q++) v += (double)p.nl_sgn[q] * dout[p.nl_src[q]];
-      Ar[col] = v;
-    }
-    double tx = 0.0;
-    for (int q = p.tx_ptr[r]; q < p.tx_ptr[r + 1]; q++) tx += (double)p.tx_sgn[q] * dout[p.tx_src[q]];
-    double rr = s + T[r] + tx;
-    res[r] = rr;
-    Ar[n] = -rr;
+  double s = 0.0;
+  const int k1 = p.row_ptr[r + 1];
+  int q = p.nl_ptr[p.row_ptr[r]];
+  for (int k = p.row_ptr[r]; k < k1; k++) {
+    double v = Bv[k];
+    const int pc = p.pcd[k];
+    const int col = pc & 0x7fff;
+    if (pc & 0x8000) v += c.gadd;
+    s += v * x[col];
+    const int q1 = p.nl_ptr[k + 1];
+    for (; q < q1; q++) v += (double)p.nl_sgn[q] * dout[p.nl_src[q]];
+    Ar[col] = v;
   }
-  Grp<G>::sync(c.mask);
+  double tx = 0.0;
+  for (int t = p.tx_ptr[r]; t < p.tx_ptr[r + 1]; t++) tx += (double)p.tx_sgn[t] * dout[p.tx_src[t]];
+  const double rr = s + (c.sm + c.L->T)[r] + tx;
+  (c.sm + c.L->res)[r] = rr;
+  return -rr;
 }
 
-// ---- dense solve: Gaussian elimination, implicit partial pivoting --------------------
-// numpy.linalg.solve (LAPACK dgesv) at dc_analysis.py:822.  Same pivot rule (largest
-// |a| in the column among the remaining rows); rows are never moved, the pivot order
-// is recorded in prow[]/stepof[].  Returns 0 if a pivot is exactly zero (LinAlgError).
+// ---- dense solve, register-resident (Var<NC,R,G>, NC > 0) --------------------------------
+// numpy.linalg.solve (LAPACK dgesv) at dc_analysis.py:822: same pivot rule (largest |a|
+// in the column among the rows not yet used), but Gauss-Jordan instead of LU +
+// back-substitution: every elimination step updates all other rows, so no lane idles
+// and there is no serial triangular solve; rows are never moved.  Results differ from
+// dgesv by rounding only.  Returns 0 if a pivot is exactly zero (LinAlgError).
+template <class V>
+AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
+  const int NC = V::NC, R = V::R, G = V::G;
+  const int n = c.p->n;
+  double* dx = c.sm + c.L->dx;
+  double* pvb = c.sm + c.L->pvb;   // [2][NC] pivot-row broadcast buffers
+  unsigned usedm = 0;              // bit s: local row slot s has been a pivot row
+  double pd[R > 0 ? R : 1];
+  int ps[R > 0 ? R : 1];
+#pragma unroll
+  for (int s = 0; s < R; s++) { pd[s] = 1.0; ps[s] = 0; }
+#pragma unroll
+  for (int k = 0; k < NC - 1; k++) {
+    if (k < n) {
+      double best = -1.0;
+      int bi = -1;
+#pragma unroll
+      for (int s = 0; s < R; s++) {
+        const int r = c.sub + G * s;
+        const double v = fabs(a[s][k]);
+        const bool cand = r < n && !((usedm >> s) & 1u);
+        if (cand && (bi < 0 || v > best)) { best = v; bi = r; }   // NaN never wins after the first
+      }
+      Grp<G>::argmax(best, bi, c.mask);
+      if (best == 0.0) return 0;
+      const int own = bi & (G - 1), slot = bi / G;
+      const bool mine = c.sub == own;
+      double pv[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int j = k; j < NC; j++) {
+        double t = a[0][j];
+#pragma unroll
+        for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
+        pv[j] = t;
+      }
+      if (G > 1) {
+        double* buf = pvb + (k & 1) * NC;
+        if (mine) {
+#pragma unroll
+          for (int j = k; j < NC; j++) buf[j] = pv[j];
+        }
+        Grp<G>::sync(c.mask);
+#pragma unroll
+        for (int j = k; j < NC; j++) pv[j] = buf[j];
+      }
+      if (mine) {
+        usedm |= 1u << slot;
+#pragma unroll
+        for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+      }
+      const double inv = 1.0 / pv[k];
+#pragma unroll
+      for (int s = 0; s < R; s++) {
+        const double l = (mine && slot == s) ? 0.0 : a[s][k] * inv;
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) a[s][j] -= l * pv[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < R; s++) {
+    const int r = c.sub + G * s;
+    if (r < n) dx[ps[s]] = a[s][NC - 1] / pd[s];
+  }
+  Grp<G>::sync(c.mask);
+  return 1;
+}
+
+// ---- dense solve, generic fallback (Var<0,0,G>): matrix in shared memory ----------------
+// Gaussian elimination with implicit partial pivoting + back-substitution, run-time n.
 template <int G>
-AHK_DEV int lu_solve(Ctx& c) {
+AHK_DEV int lu_solve_smem(Ctx& c) {
   const int n = c.p->n, RS = c.L->RS;
   double* A = c.A();
   double* dx = c.sm + c.L->dx;
@@ -247,7 +340,7 @@ AHK_DEV int lu_solve(Ctx& c) {
     for (int r = c.sub; r < n; r += G) {
       if ((used >> r) & 1ull) continue;
       double v = fabs(A[r * RS + k]);
-      if (bi < 0 || v > best) { best = v; bi = r; }   // NaN never wins after the first
+      if (bi < 0 || v > best) { best = v; bi = r; }
     }
     Grp<G>::argmax(best, bi, c.mask);
     if (best == 0.0) return 0;
@@ -276,17 +369,44 @@ AHK_DEV int lu_solve(Ctx& c) {
   return 1;
 }
 
-// np.allclose element test (utilities.py:527-529)
-AHK_DEV int close1(double a, double b, double rtol, double atol) {
-  if (isnan(a) || isnan(b)) return 0;
-  if (isinf(a) || isinf(b)) return a == b;
-  return fabs(a - b) <= atol + rtol * fabs(b);
+// one Newton linear step: assemble at x() and solve into dx(); 0 = singular
+template <class V>
+AHK_DEV int assemble_solve(Ctx& c) {
+  const int n = c.p->n, RS = c.L->RS, G = V::G;
+  double* A = c.A();
+  if constexpr (V::NC > 0) {
+    const int NC = V::NC, R = V::R;
+    double a[R > 0 ? R : 1][NC > 0 ? NC : 1];
+#pragma unroll
+    for (int s = 0; s < R; s++) {
+      const int r = c.sub + G * s;
+      if (r < n) {
+        double* Ar = A + r * RS;
+        a[s][NC - 1] = assemble_row(c, r, Ar);
+#pragma unroll
+        for (int j = 0; j < NC - 1; j++) a[s][j] = Ar[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; j++) a[s][j] = 0.0;
+      }
+    }
+    return gj_solve<V>(c, a);
+  } else {
+    for (int r = c.sub; r < n; r += G) {
+      double* Ar = A + r * RS;
+      for (int j = 0; j < n; j++) Ar[j] = 0.0;
+      Ar[n] = assemble_row(c, r, Ar);
+    }
+    Grp<G>::sync(c.mask);
+    return lu_solve_smem<G>(c);
+  }
 }
 
 // ---- damped Newton (dc_analysis.mdn_solver) -------------------------------------------
 // returns 1 converged, 0 not converged, -1 singular (x untouched in that iteration)
-template <int G>
+template <class V>
 AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
+  const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n;
@@ -297,9 +417,8 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
   int it = 0, conv = 0;
   while (it < MAXIT) {
     it++;
-    if (p.ndev) eval_devices<G>(c, x);
-    assemble<G>(c);
-    if (!lu_solve<G>(c)) { c.singular = 1; *iters = 0; return -1; }
+    if (p.ndev) { eval_devices(c, x); Grp<G>::sync(c.mask); }
+    if (!assemble_solve<V>(c)) { c.singular = 1; *iters = 0; return -1; }
     // get_td (dc_analysis.py:884-946)
     double td = 1.0;
     if (o.nr_damp_first_iters) td = it < 10 ? 1e-2 : (it < 20 ? 0.1 : 1.0);
@@ -314,15 +433,17 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
       }
       td = fmin(td, Grp<G>::fmin_all(t, c.mask));
     }
+    // convergence_check (utilities.py:392-549): np.allclose(x, x + dx) per unit class and
+    // |residual| <= the other class's absolute tolerance; NaN never passes
     int ok = 1, finite = 1;
     for (int i = c.sub; i < n; i += G) {
-      double d = dx[i];
-      double xn = x[i] + td * d;
+      const double d = dx[i];
+      const double xn = x[i] + td * d;
       x[i] = xn;
       if (!isfinite(xn)) finite = 0;
-      bool isv = i < p.nv1;
-      if (!close1(xn, xn + d, isv ? o.ver : o.ier, isv ? o.vea : o.iea)) ok = 0;
-      if (!close1(res[i], 0.0, 0.0, isv ? o.iea : o.vea)) ok = 0;
+      const bool isv = i < p.nv1;
+      if (!(fabs(d) <= (isv ? o.vea : o.iea) + (isv ? o.ver : o.ier) * fabs(xn + d))) ok = 0;
+      if (!(fabs(res[i]) <= (isv ? o.iea : o.vea))) ok = 0;
     }
     Grp<G>::sync(c.mask);
     if (!p.ndev) { conv = 1; break; }            // linear circuit: one iteration
@@ -333,11 +454,23 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
   return conv;
 }
 
+// 10 ** -(idx+1), idx = 0..9 (dc_analysis.py:452-455) and the source-stepping factors
+// (dc_analysis.py:456-457); literal constants, no local-memory tables
+AHK_DEV double gmin_step_value(int i) {
+  return i == 0 ? 1e-1 : i == 1 ? 1e-2 : i == 2 ? 1e-3 : i == 3 ? 1e-4 : i == 4 ? 1e-5 :
+         i == 5 ? 1e-6 : i == 6 ? 1e-7 : i == 7 ? 1e-8 : i == 8 ? 1e-9 : 1e-10;
+}
+AHK_DEV double source_step_value(int i) {
+  return i == 0 ? 0.001 : i == 1 ? .005 : i == 2 ? .01 : i == 3 ? .03 : i == 4 ? .1 :
+         i == 5 ? .3 : i == 6 ? .5 : i == 7 ? .7 : i == 8 ? .8 : .9;
+}
+
 // ---- dc_solve: standard -> gmin stepping -> source stepping (dc_analysis.py:128-320) ---
 // gmin: value on the node diagonals for the standard / source-stepping attempts.
-template <int G>
+template <class V>
 AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT,
                      int* tot_iters, int* method) {
+  const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n;
@@ -349,51 +482,54 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
   const double* Mv = c.sm + c.L->Mv;
   const double* Dv = c.sm + c.L->Dv;
   for (int i = c.sub; i < n; i += G) Nd[i] = Nc[i];
-  Grp<G>::sync(c.mask);
-  if (p.ntd && c.sub == 0) {   // Tt(t), dc_analysis.py:222-237
-    for (int k = 0; k < p.nsrc; k++) {
-      const SrcOp& s = p.src[k];
-      if (!s.tf) continue;
-      double q[8];
-      for (int j = 0; j < 8; j++) q[j] = c.P(s.pbase + 3 + j);
-      double v = tf_eval(s.tf, q, time);
-      if (s.is_v) Nd[s.row0] += -1 * v;
-      else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
+  if (p.ntd) {   // Tt(t), dc_analysis.py:222-237
+    Grp<G>::sync(c.mask);
+    if (c.sub == 0) {
+      for (int k = 0; k < p.nsrc; k++) {
+        const SrcOp& s = p.src[k];
+        if (!s.tf) continue;
+        double q[8];
+        for (int j = 0; j < 8; j++) q[j] = c.P(s.pbase + 3 + j);
+        double v = tf_eval(s.tf, q, time);
+        if (s.is_v) Nd[s.row0] += -1 * v;
+        else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
+      }
     }
   }
-  int failed[3] = {0, 0, 0};
-  const int use[3] = {o.use_standard_solve_method, o.use_gmin_stepping, o.use_source_stepping};
+  int failed = 0;   // bit m: method m failed
+  const int use = (o.use_standard_solve_method ? 1 : 0) | (o.use_gmin_stepping ? 2 : 0) |
+                  (o.use_source_stepping ? 4 : 0);
   int enabled = -1, gidx = 0, sidx = 0;
-  for (int m = 0; m < 3; m++) if (use[m]) { enabled = m; break; }
+  for (int m = 0; m < 3; m++) if ((use >> m) & 1) { enabled = m; break; }
   *tot_iters = 0;
   *method = 0;
   while (true) {
     if (enabled < 0) return 0;
     double g = gmin, f = 1.0;
-    if (enabled == 1) {   // 10 ** -(idx+1), replaces Gmin (dc_analysis.py:262-269,452-455)
-      const double g10[10] = {1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10};
-      g = g10[gidx];
-    } else if (enabled == 2) {
-      const double sfac[10] = {0.001, .005, .01, .03, .1, .3, .5, .7, .8, .9};
-      f = sfac[sidx];
-    }
+    if (enabled == 1) g = gmin_step_value(gidx);   // replaces Gmin (dc_analysis.py:262-269,452-455)
+    else if (enabled == 2) f = source_step_value(sidx);
     Grp<G>::sync(c.mask);
-    for (int k = c.sub; k < p.npos; k += G) {
-      double v = Mv[k];
-      if (with_tran) v += c.C1 * Dv[k];
-      if (p.pdiag[k]) v += g;
-      Bv[k] = v;
+    if (Bv != Mv) {   // transient layout: Bv = Mv + C1 D + Gmin, built per attempt
+      for (int k = c.sub; k < p.npos; k += G) {
+        double v = Mv[k];
+        if (with_tran) v += c.C1 * Dv[k];
+        if (p.pdiag[k]) v += g;
+        Bv[k] = v;
+      }
+      c.gadd = 0.0;
+    } else {
+      c.gadd = g;     // OP/DC layout: Gmin is added while assembling
     }
     for (int i = c.sub; i < n; i += G) T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + (with_tran ? Ntr[i] : 0.0);
     Grp<G>::sync(c.mask);
     int it = 0;
-    int r = mdn_solver<G>(c, MAXIT, &it);
+    int r = mdn_solver<V>(c, MAXIT, &it);
     if (r >= 0) *tot_iters += it;
     *method = enabled;
     if (r <= 0) {   // set_next_solve_method, dc_analysis.py:354-408
-      failed[enabled] = 1;
+      failed |= 1 << enabled;
       enabled = -1;
-      for (int m = 0; m < 3; m++) if (!failed[m] && use[m]) { enabled = m; break; }
+      for (int m = 0; m < 3; m++) if (!((failed >> m) & 1) && ((use >> m) & 1)) { enabled = m; break; }
       if (enabled < 0) return 0;
     } else {
       if (enabled == 2 && sidx != 9) sidx++;
@@ -405,8 +541,9 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
 
 // ---- OP: guess -> Gmin pass -> no-Gmin pass -> gmin_check (dc_analysis.py:598-687) ---
 // in: x() holds x0 if have_x0; out: x() solution; returns AHK_ST_* word
-template <int G>
+template <class V>
 AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
+  const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n;
@@ -428,7 +565,7 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
   }
   Grp<G>::sync(c.mask);
   int n1 = 0, n2 = 0, m1 = 0, m2 = 0, status;
-  int s1 = dc_solve<G>(c, o.gmin, false, 0.0, o.dc_max_nr_iter, &n1, &m1);
+  int s1 = dc_solve<V>(c, o.gmin, false, 0.0, o.dc_max_nr_iter, &n1, &m1);
   if (!s1) {
     *iters = n1;
     status = (m1 << 1);
@@ -439,7 +576,7 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
     const double* res = c.sm + c.L->res;
     for (int i = c.sub; i < n; i += G) { x1[i] = x[i]; r1[i] = res[i]; }
     Grp<G>::sync(c.mask);
-    int s2 = dc_solve<G>(c, 0.0, false, 0.0, o.dc_max_nr_iter, &n2, &m2);
+    int s2 = dc_solve<V>(c, 0.0, false, 0.0, o.dc_max_nr_iter, &n2, &m2);
     if (!s2) {
       double* resw = c.sm + c.L->res;
       for (int i = c.sub; i < n; i += G) { x[i] = x1[i]; resw[i] = r1[i]; }
@@ -472,10 +609,13 @@ AHK_DEV int check_step(const Opts& o, double& tstep, double time, double tstop, 
 
 struct DfOut { double C1, x_lte, pred_lte; int has_pred; };
 
+AHK_DEV double ipow(double b, int e) { double r = 1.0; for (int i = 0; i < e; i++) r *= b; return r; }
+
 // History ring: entry k (k = 0 newest) lives in slot (h0 + k) % buflen.
-template <int G>
+template <class V>
 AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h0, int buflen,
                     double step, bool predict, DfOut& d) {
+  const int G = V::G;
   const int n = c.p->n;
   const double* ht = c.sm + c.L->ht;
   const double* hx = c.sm + c.L->hx;
@@ -519,38 +659,48 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
       d.has_pred = 1;
     }
   } else {                                           // gear.py:122-208
-    double s[9], alpha[9], gamma[9];
-    s[0] = 0;
-    for (int i = 1; i < order + 2; i++) s[i] = step + HT(0) - HT(i - 1);
-    for (int k = 1; k < order + 2; k++) {
-      double a = 1.0;
-      for (int j = 1; j < order + 2; j++) a *= (j == k) ? 1.0 : s[j] / (s[j] - s[k]);
-      alpha[k] = a;
+    // s / alpha / gamma (order + 2 entries each) live in the instance's scratch: lane 0
+    // fills them, the group reads them (keeps run-time indexed arrays out of local memory)
+    double* s = c.sm + c.L->gsc;
+    double* alpha = s + 8;
+    double* gamma = s + 16;
+    if (c.sub == 0) {
+      s[0] = 0;
+      for (int i = 1; i < order + 2; i++) s[i] = step + HT(0) - HT(i - 1);
+      for (int k = 1; k < order + 2; k++) {
+        double a = 1.0;
+        for (int j = 1; j < order + 2; j++) a *= (j == k) ? 1.0 : s[j] / (s[j] - s[k]);
+        alpha[k] = a;
+      }
+      double g0 = 0;
+      for (int k = 1; k < order + 1; k++) {
+        gamma[k] = alpha[k] * ((1.0 / s[order + 1]) - (1.0 / s[k]));
+        g0 -= gamma[k];
+      }
+      gamma[0] = g0;
+      double xl = 0.0, fact = 1.0;
+      for (int k = 2; k <= order + 1; k++) fact *= k;
+      for (int k = 1; k < order + 1; k++) xl += ipow(s[k], order + 1) * (-1.0 * gamma[k] / g0);
+      s[24] = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;    // x_lte
+      double pl = -1.0 / fact;
+      for (int k = 1; k < order + 2; k++) pl *= s[k];
+      s[25] = pl;                                                      // pred_lte
     }
-    gamma[0] = 0;
-    for (int k = 1; k < order + 1; k++) {
-      gamma[k] = alpha[k] * ((1.0 / s[order + 1]) - (1.0 / s[k]));
-      gamma[0] -= gamma[k];
-    }
+    Grp<G>::sync(c.mask);
     d.C1 = gamma[0];
+    d.x_lte = s[24];
     for (int i = c.sub; i < n; i += G) {
       double a = 0.0;
       for (int k = 0; k < order; k++) a = a + gamma[k + 1] * HX(k)[i];
       C0[i] = a;
     }
-    double xl = 0.0, fact = 1.0;
-    for (int k = 2; k <= order + 1; k++) fact *= k;
-    for (int k = 1; k < order + 1; k++) xl += pow(s[k], (double)(order + 1)) * (-1.0 * gamma[k] / gamma[0]);
-    d.x_lte = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;
     if (predict) {
       for (int i = c.sub; i < n; i += G) {
         double a = 0.0;
         for (int k = 1; k < order + 2; k++) a = a + alpha[k] * HX(k - 1)[i];
         pred[i] = a;
       }
-      double pl = -1.0 / fact;
-      for (int k = 1; k < order + 2; k++) pl *= s[k];
-      d.pred_lte = pl;
+      d.pred_lte = s[25];
       d.has_pred = 1;
     }
   }
@@ -568,8 +718,9 @@ struct TranArgs {
 };
 
 // in: x() holds x(tstart).  returns status word.
-template <int G>
+template <class V>
 AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
+  const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n;
@@ -608,7 +759,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   while (time < a.tstop) {
     DfOut d;
     bool predict = a.use_step_control && iter_n >= start_pred;
-    get_df<G>(c, a.method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
+    get_df<V>(c, a.method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
     // NR start point (transient.py:335-338)
     if (o.transient_prediction_as_x0 && a.use_step_control && d.has_pred) {
       for (int i = c.sub; i < n; i += G) x[i] = pred[i];
@@ -626,22 +777,29 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
     c.C1 = d.C1;
     Grp<G>::sync(c.mask);
     int it = 0, meth = 0;
-    int ok = dc_solve<G>(c, o.gmin, true, time + tstep, o.transient_max_nr_iter, &it, &meth);
+    int ok = dc_solve<V>(c, o.gmin, true, time + tstep, o.transient_max_nr_iter, &it, &meth);
     n_solves++; n_nr += it;
     if (ok) {
       double old_step = tstep;
       if (a.use_step_control && d.has_pred) {
-        double coeff = 2.0;
-        double ex = 1.0 / (order + 1);
-        for (int i = c.sub; i < n; i += G) {   // transient.py:356-365
-          double lte = fabs((d.x_lte / (d.pred_lte - d.x_lte)) * (pred[i] - x[i]));
+        // transient.py:356-365: coeff = min(2, min_i ((aerr + rerr |x_prev_i|) / lte_i)^(1/(order+1)));
+        // the power is monotone, so the minimum ratio is found first and raised once.
+        double rmin = INFINITY;
+        const double sc = d.x_lte / (d.pred_lte - d.x_lte);
+        for (int i = c.sub; i < n; i += G) {
+          double lte = fabs(sc * (pred[i] - x[i]));
           if (lte != 0) {
             double re = i < p.nv1 ? o.ver : o.ier;
-            double v = pow((o.vea + re * fabs(xacc[i])) / lte, ex);
-            if (v < coeff) coeff = v;
+            double v = (o.vea + re * fabs(xacc[i])) / lte;
+            if (v < rmin) rmin = v;
           }
         }
-        coeff = Grp<G>::fmin_all(coeff, c.mask);
+        rmin = Grp<G>::fmin_all(rmin, c.mask);
+        double coeff = 2.0;
+        if (rmin < INFINITY) {
+          double v = pow(rmin, 1.0 / (order + 1));
+          if (v < coeff) coeff = v;
+        }
         double new_step = tstep * coeff;
         bool reject = o.transient_use_aposteriori_step_control &&
                       coeff < o.transient_aposteriori_step_threshold;

@@ -8,7 +8,8 @@
 //   sources ahkab/time_functions.py:402-745
 // Unlike the reference (which re-runs the whole EKV current computation four
 // times per Newton iteration, ekv.py:676,687,698), each device is evaluated
-// once and every output is derived from that single evaluation.
+// once and every output is derived from that single evaluation; the EKV inner
+// solve is stateless (no warm-start state) and converged to ~1e-12.
 #pragma once
 #include <math.h>
 
@@ -82,98 +83,115 @@ AHK_DEV void diode_eval(const DiodeP& m, double v, double vea, double gmin,
 // ---- EKV ---------------------------------------------------------------------
 struct EkvP { double VTO, KP, GAMMA, PHI, COX, LAMBDA, XJ, UCRIT, W, L, M, N; int NP; };
 
-// Solve ln(sqrt(1/4+i)-1/2) + 2 sqrt(1/4+i) - 1 = v for i (ekv.py:703-752) with
-// the Halley iteration scipy.optimize.newton runs (tol 1.48e-8, warm start).
-AHK_DEV double ekv_ismall(double vsmall, double iguess) {
-  double p0 = iguess, p = p0;
-  for (int it = 0; it < 500; it++) {
-    double fval, fder, fder2;
-    if (p0 > 0) {
-      double s = sqrt(.25 + p0);
-      fval = log(s - 0.5) + 2.0 * s - 1.0 - vsmall;
-    } else {
-      fval = p0 - vsmall;
-    }
-    if (fval == 0) { p = p0; break; }
-    {
-      double xx = p0 < AHK_EPS ? 10 * AHK_EPS : p0;
-      double a = xx + 0.25, s = sqrt(a), q = s - 0.5;
-      double is = 1.0 / s, iq = 1.0 / q;
-      fder = 0.5 * iq * is + is;
-      double ia = 1.0 / a;
-      fder2 = -0.25 * ia * iq * iq - 0.5 * ia * is - 0.25 * ia * is * iq;
-    }
-    double step = fval / fder;
-    double adj = step * fder2 / fder * 0.5;
-    if (fabs(adj) < 1) step /= 1.0 - adj;
-    p = p0 - step;
-    if (fabs(p - p0) <= 1.48e-8) break;
-    p0 = p;
-  }
-  return p > 10 * AHK_EPS ? p : 10 * AHK_EPS;
-}
+#ifdef __CUDACC__
+AHK_DEV double ahk_rsqrt(double x) { return rsqrt(x); }
+#else
+AHK_DEV double ahk_rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
 
-AHK_DEV void ekv_vp(const EkvP& m, double VG, double sqphi, double& VP) {  // ekv.py:524-540
-  double VGeff = VG - m.VTO + m.PHI + m.GAMMA * sqphi;
-  double t = sqphi + m.GAMMA * 0.5;
-  double arg = VG - m.VTO + t * t;
-  if (VGeff > 0 && arg > 0) {
-    VP = VG - m.VTO - m.GAMMA * (sqrt(arg) - t);
-    if (isnan(VP)) VP = 0;
-  } else {
-    VP = -m.PHI;
-  }
-}
+// Per-instance constants of one EKV device (model/geometry only), computed once
+// when the instance is loaded instead of at every evaluation.
+enum { EK_VTO, EK_GAMMA, EK_PHI, EK_SQPHI, EK_T, EK_KWL, EK_VC, EK_UTVC, EK_LVC, EK_LAMBDA,
+       EK_LLC, EK_ILCU, EK_NL, EK_LMIN2, EK_IUCRIT, EK_PREF, EK_NCONST };
 
-// out[0] = Ids, out[1..3] = gmd, gmg, gms ; st[0..1] = ifn, irn warm starts.
-// (vd, vg, vs) are the drive-port voltages w.r.t. bulk.
-AHK_DEV void ekv_eval(const EkvP& m, double vd, double vg, double vs, double gmin,
-                      double* st, double* out) {
+AHK_DEV void ekv_setup(const EkvP& m, double* k) {
   const double Ut = AHK_VTH;
-  double VD = vd * m.NP, VG = vg * m.NP, VS = vs * m.NP;  // ekv.py:481-507
+  k[EK_VTO] = m.VTO; k[EK_GAMMA] = m.GAMMA; k[EK_PHI] = m.PHI;
+  k[EK_SQPHI] = sqrt(m.PHI);
+  k[EK_T] = k[EK_SQPHI] + m.GAMMA * 0.5;
+  k[EK_KWL] = m.KP * m.W / m.L;
+  const double Vc = m.UCRIT * m.N * m.L;                 // ekv.py:640
+  k[EK_VC] = Vc; k[EK_UTVC] = Ut / Vc;
+  k[EK_LVC] = Ut * (log(.5 * Vc / Ut) - .6);             // ekv.py:643
+  k[EK_LAMBDA] = m.LAMBDA;
+  const double Lc = sqrt(AHK_ESI * m.XJ / m.COX);        // ekv.py:650
+  k[EK_LLC] = m.LAMBDA * Lc;
+  k[EK_ILCU] = 1.0 / (Lc * m.UCRIT);
+  k[EK_NL] = m.N * m.L;
+  k[EK_LMIN2] = (m.N * m.L / 10.0) * (m.N * m.L / 10.0);
+  k[EK_IUCRIT] = 1.0 / m.UCRIT;
+  k[EK_PREF] = m.NP * m.L * m.M;                          // ekv.py:601
+}
+
+// ekv.py:703-752 "ismall": the normalised current i solves
+//   ln(sqrt(1/4+i) - 1/2) + 2 sqrt(1/4+i) - 1 = v.
+// With q = sqrt(1/4+i) - 1/2 (so i = q^2 + q) this is ln q + 2 q = v, and in
+// y = ln q the function f(y) = y + 2 e^y - v is increasing and convex.  The
+// reference runs scipy's Halley iteration on i from the previous solution until
+// |di| <= 1.48e-8; here a closed-form start (within 0.23 of the root for every v)
+// is followed by two Halley steps in y (cubic: 0.23 -> 1e-3 -> 2e-12 relative in
+// q, measured over v in [-40, 590]); the last exponential is updated by its series.
+// Stateless and branch-uniform: every lane does the same work.
+AHK_DEV double ekv_q(double v) {
+  double y;
+  if (v > 2.0) y = log(0.5 * v);
+  else if (v < -2.0) y = v;
+  else y = -0.85 + v * (0.555 - 0.065 * v);
+  double E = exp(y);
+  {
+    double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
+    double d = 2.0 * f * f1 / (2.0 * f1 * f1 - f * 2.0 * E);
+    y -= d;
+    E = exp(y);
+  }
+  {
+    double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
+    double d = 2.0 * f * f1 / (2.0 * f1 * f1 - f * 2.0 * E);
+    E = E * (1.0 - d * (1.0 - 0.5 * d));
+  }
+  return E;
+}
+
+AHK_DEV double ekv_vp(const double* k, double VG) {   // ekv.py:524-540
+  double VGeff = VG - k[EK_VTO] + k[EK_PHI] + k[EK_GAMMA] * k[EK_SQPHI];
+  double t = k[EK_T];
+  double arg = VG - k[EK_VTO] + t * t;
+  double VP = -k[EK_PHI];
+  if (VGeff > 0 && arg > 0) {
+    VP = VG - k[EK_VTO] - k[EK_GAMMA] * (sqrt(arg) - t);
+    if (isnan(VP)) VP = 0;
+  }
+  return VP;
+}
+
+// out[0] = Ids, out[1..3] = gmd, gmg, gms.  k = the device's ekv_setup() block,
+// NP = +1 (n) / -1 (p); (vd, vg, vs) are the drive-port voltages w.r.t. bulk.
+AHK_DEV void ekv_eval(const double* k, int NP, double vd, double vg, double vs, double gmin,
+                      double* out) {
+  const double Ut = AHK_VTH, iUt = 1.0 / AHK_VTH;
+  double VD = vd * NP, VG = vg * NP, VS = vs * NP;  // ekv.py:481-507
   int CS = +1;
   if (VS > VD) { double t = VD; VD = VS; VS = t; CS = -1; }
-  double sqphi = sqrt(m.PHI);
-  double VP;
-  ekv_vp(m, VG, sqphi, VP);
-  double nq = 1.0 + .5 * m.GAMMA / sqrt(m.PHI + .5 * VP);
-  double KWL = m.KP * m.W / m.L;
-  double Is = 2 * nq * Ut * Ut * KWL;  // ekv.py:509-522
-  double Gs = 2 * nq * Ut * KWL;
-  double vp = VP / Ut, vsn = VS / Ut, vdn = VD / Ut;
-  double ifn = ekv_ismall(vp - vsn, fmax(st[0], 1e-10));
-  // get_leq_virp, ekv.py:629-670 (normalised vd, vs => half Vds, quirk 11)
-  double Leq, v_irn;
-  {
-    double Vc = m.UCRIT * m.N * m.L;
-    double sif = sqrt(ifn);
-    double Vdss = Vc * (sqrt(.25 + Ut / Vc * sif) - .5);
-    double Vdssp = Vc * (sqrt(.25 + Ut / Vc * (sif - .75 * log(ifn))) - .5) +
-                   Ut * (log(.5 * Vc / Ut) - .6);
-    double vser_1 = sif - Vdss / Ut;
-    double Vds = (vdn - vsn) * .5 * Ut;
-    double delta_v = 4.0 * Ut * sqrt(m.LAMBDA * vser_1 + 1.0 / 64);
-    double dv2 = delta_v * delta_v;
-    double Vip = sqrt(Vdss * Vdss + dv2) - sqrt((Vds - Vdss) * (Vds - Vdss) + dv2);
-    double Lc = sqrt(AHK_ESI * m.XJ / m.COX);
-    double delta_l = m.LAMBDA * Lc * log(1 + (Vds - Vip) / (Lc * m.UCRIT));
-    double Lp = m.N * m.L - delta_l + (Vds + Vip) / m.UCRIT;
-    double Lmin = m.N * m.L / 10.0;
-    Leq = .5 * (Lp + sqrt(Lp * Lp + Lmin * Lmin));
-    v_irn = (VP - Vds - vsn * Ut - sqrt(Vdssp * Vdssp + dv2) +
-             sqrt((Vds - Vdssp) * (Vds - Vdssp) + dv2)) / Ut;
-  }
-  double irn = ekv_ismall(v_irn, fmax(st[1], 1e-10));
-  st[0] = ifn; st[1] = irn;
-  double qf = sqrt(.25 + fmax(ifn, 0.0)) - .5;  // ekv.py:783-789
-  double qr = sqrt(.25 + fmax(irn, 0.0)) - .5;
-  out[0] = CS * m.NP * m.L / Leq * m.M * Is * (ifn - irn);  // ekv.py:601-602
+  const double VP = ekv_vp(k, VG);
+  const double nq = 1.0 + .5 * k[EK_GAMMA] * ahk_rsqrt(k[EK_PHI] + .5 * VP);
+  const double Gs = 2 * nq * Ut * k[EK_KWL];        // ekv.py:509-522
+  const double Is = Gs * Ut;
+  double qf = ekv_q((VP - VS) * iUt);
+  double ifn = qf * qf + qf;
+  if (!(ifn > 10 * AHK_EPS)) { ifn = 10 * AHK_EPS; qf = 10 * AHK_EPS; }   // ekv.py:726
+  // get_leq_virp, ekv.py:629-670 (Vds = half the drain-source voltage: quirk 11)
+  const double Vc = k[EK_VC];
+  const double sif = sqrt(ifn);
+  const double Vdss = Vc * (sqrt(.25 + k[EK_UTVC] * sif) - .5);
+  const double Vdssp = Vc * (sqrt(.25 + k[EK_UTVC] * (sif - .75 * log(ifn))) - .5) + k[EK_LVC];
+  const double vser_1 = sif - Vdss * iUt;
+  const double Vds = (VD - VS) * .5;
+  const double dv2 = 16.0 * Ut * Ut * (k[EK_LAMBDA] * vser_1 + 1.0 / 64);
+  const double Vip = sqrt(Vdss * Vdss + dv2) - sqrt((Vds - Vdss) * (Vds - Vdss) + dv2);
+  const double delta_l = k[EK_LLC] * log(1 + (Vds - Vip) * k[EK_ILCU]);
+  const double Lp = k[EK_NL] - delta_l + (Vds + Vip) * k[EK_IUCRIT];
+  const double Leq = .5 * (Lp + sqrt(Lp * Lp + k[EK_LMIN2]));
+  const double v_irn = (VP - Vds - VS - sqrt(Vdssp * Vdssp + dv2) +
+                        sqrt((Vds - Vdssp) * (Vds - Vdssp) + dv2)) * iUt;
+  double qr = ekv_q(v_irn);
+  double irn = qr * qr + qr;
+  if (!(irn > 10 * AHK_EPS)) { irn = 10 * AHK_EPS; qr = 10 * AHK_EPS; }
+  out[0] = CS * k[EK_PREF] / Leq * Is * (ifn - irn);       // ekv.py:601-602
   double gmd = CS == 1 ? Gs * qr : Gs * qf;                 // ekv.py:672-692
   double gms = CS == 1 ? -1.0 * Gs * qf : -Gs * qr;
   // get_gmg: nv from the UN-flipped vg (ekv.py:697, quirk 11)
-  double VPu;
-  ekv_vp(m, vg, sqphi, VPu);
-  double nv = 1.0 + .5 * m.GAMMA / sqrt(m.PHI + VPu + 1e-12);
+  const double VPu = NP == 1 ? VP : ekv_vp(k, vg);
+  const double nv = 1.0 + .5 * k[EK_GAMMA] * ahk_rsqrt(k[EK_PHI] + VPu + 1e-12);
   double gmg = CS * Gs * (qf - qr) / nv;
   if (gmd == 0) gmd = gmin * 2.0;  // ekv.py:331-336
   if (gmg == 0) gmg = gmin * 2.0;

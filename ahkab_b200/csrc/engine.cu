@@ -1,11 +1,6 @@
-// engine.cu — CUDA kernels of the small-circuit engine and the C-ABI
-// (include/ahkab_b200.h).  sm_100a only; no CPU fallback.
-//
-// One kernel per analysis; each is a persistent-per-instance kernel: a group of
-// G lanes carries its instance through the whole analysis (every Newton
-// iteration of both OP passes / every sweep point / every time step / every
-// frequency) out of shared memory, touching HBM only for the parameter reads
-// and the result rows.  See core.cuh for the per-instance algorithm.
+// engine.cu — host side of the C-ABI (include/ahkab_b200.h): program upload, kernel-variant
+// selection, launches.  The kernels live in k_dc.cu / k_tran.cu / k_ac.cu (small circuits,
+// core.cuh) and biglin.cuh (large linear circuits).  sm_100a only; no CPU fallback.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -15,10 +10,8 @@
 #include <string>
 #include <vector>
 
-#include "ac.cuh"
 #include "biglin.cuh"
-#include "entry.cuh"
-#include "program_build.hpp"
+#include "kernels.cuh"
 
 using namespace ahk;
 
@@ -35,68 +28,6 @@ int fail(const std::string& m) { g_err = m; return -1; }
     if (e_ != cudaSuccess)                                                           \
       return fail(std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
-
-struct KBase {
-  Prog p; Opts o; Layout L;
-  const double* vary; long long B;
-};
-struct KOp { KBase b; OpArgs a; };
-struct KDc { KBase b; DcArgs a; };
-struct KTran { KBase b; const double* x0; TranArgs a; int* status; };
-struct KAc { Prog p; Opts o; AcLayout AL; const double* vary; long long B; AcArgs a; int nchunks; };
-
-template <int G>
-__device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
-                                         int stride, const double* vary, long long B,
-                                         long long units, long long& unit) {
-  extern __shared__ double smem[];
-  const int gi = threadIdx.x / G;
-  const int ipb = blockDim.x / G;
-  unit = (long long)blockIdx.x * ipb + gi;
-  if (unit >= units) return false;
-  const int lane = threadIdx.x & 31;
-  c.p = p; c.o = o; c.L = L;
-  c.sm = smem + (size_t)gi * stride;
-  c.vary = vary; c.B = B; c.inst = unit;
-  c.sub = threadIdx.x % G;
-  c.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  return true;
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) k_op(const __grid_constant__ KOp k) {
-  Ctx c; long long u;
-  if (!make_ctx<G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, k.b.B, u)) return;
-  run_op<G>(c, k.a);
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) k_dc(const __grid_constant__ KDc k) {
-  Ctx c; long long u;
-  if (!make_ctx<G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, k.b.B, u)) return;
-  run_dc<G>(c, k.a);
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) k_tran(const __grid_constant__ KTran k) {
-  Ctx c; long long u;
-  if (!make_ctx<G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, k.b.B, u)) return;
-  run_tran<G>(c, k.x0, k.a, k.status);
-}
-
-// AC: unit = (instance, frequency chunk)
-template <int G>
-__global__ void __launch_bounds__(128) k_ac(const __grid_constant__ KAc k) {
-  Ctx c; long long u;
-  if (!make_ctx<G>(c, &k.p, &k.o, &k.AL.L, k.AL.stride, k.vary, k.B, k.B * k.nchunks, u)) return;
-  c.inst = u / k.nchunks;
-  const int ch = (int)(u % k.nchunks);
-  AcArgs a = k.a;
-  const int per = (a.npts + k.nchunks - 1) / k.nchunks;
-  a.f0 = ch * per;
-  a.f1 = min(a.npts, a.f0 + per);
-  run_ac<G>(c, k.AL, a);
-}
 
 // FP64 pipe probe: 8 independent DFMA chains per thread, no memory traffic in the
 // loop.  bench.py times it to get the measured FP64 roofline denominator
@@ -124,7 +55,9 @@ struct ahk_engine {
   HostProg H;
   Opts o;
   int n = 0;
-  int group = 0;           // 0 = heuristic
+  int group = 0;           // 0 = heuristic, else only variants with that many lanes
+  int force_vid = -1;      // real-valued kernels: forced variant id (-1 = heuristic)
+  int force_ac_vid = -1;   // AC kernels
   int device = 0;
   int sm_count = 148;
   size_t smem_max = 227 * 1024;
@@ -201,6 +134,7 @@ size_t put(std::vector<unsigned char>& buf, const std::vector<T>& v) {
 int upload_program(ahk_engine* e) {
   HostProg& H = e->H;
   std::vector<unsigned char> buf;
+  size_t o_pcd = put(buf, H.pcd);
   size_t o_row = put(buf, H.row_ptr), o_pcol = put(buf, H.pcol), o_prowi = put(buf, H.prowi), o_pdiag = put(buf, H.pdiag);
   size_t o_tp = put(buf, H.term_ptr), o_ts = put(buf, H.term_slot), o_tk = put(buf, H.term_kind);
   size_t o_nlp = put(buf, H.nl_ptr), o_nls = put(buf, H.nl_src), o_nlg = put(buf, H.nl_sgn);
@@ -216,6 +150,7 @@ int upload_program(ahk_engine* e) {
   Prog p = H.hdr;
   p.row_ptr = (const int*)(d + o_row); p.pcol = (const unsigned short*)(d + o_pcol);
   p.prowi = (const unsigned short*)(d + o_prowi); p.pdiag = d + o_pdiag;
+  p.pcd = (const unsigned short*)(d + o_pcd);
   p.term_ptr = (const int*)(d + o_tp); p.term_slot = (const int*)(d + o_ts);
   p.term_kind = (const signed char*)(d + o_tk);
   p.nl_ptr = (const int*)(d + o_nlp); p.nl_src = (const short*)(d + o_nls);
@@ -260,57 +195,74 @@ int to_scratch(ahk_engine* e, const double* host, int cnt, cudaStream_t s) {
   return 0;
 }
 
-int pow2floor(long long v) { int g = 1; while (2LL * g <= v) g *= 2; return g; }
-int pow2ceil(int v) { int g = 1; while (g < v) g *= 2; return g; }
-
-// lanes per instance: enough to spread the rows / devices of one instance, but
-// no more than what still fills the machine with B instances
-int pick_group(const ahk_engine* e, long long units, int useful_min) {
-  if (e->group > 0) return e->group;
-  const Prog& h = e->H.hdr;
-  int useful = pow2ceil(std::max(std::max(h.ndev, (h.n + 1) / 2), useful_min));
-  long long slots = (long long)e->sm_count * 1024;
-  int fill = pow2floor(std::max(1LL, slots / std::max(1LL, units)));
-  int g = std::min(useful, fill);
-  return std::max(1, std::min(32, g));
+// ---- kernel-variant selection -------------------------------------------------------------
+bool fits(const VarInfo& v, int n) {
+  if (v.NC == 0) return n <= AHK_SMALL_NMAX;
+  return v.NC - 1 >= n && v.R * v.G >= n;
 }
 
-struct Launch { int G, threads, blocks; size_t smem; };
+// Smallest column count that fits (least padding); among those, few lanes per instance
+// when the batch alone fills the machine (no idle lanes, no cross-lane traffic), many
+// lanes when it does not (latency hiding needs the extra warps).
+int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, long long units,
+                 int* vid) {
+  const int n = e->n;
+  if (forced >= 0) {
+    if (forced >= ntab || !fits(tab[forced], n)) return fail("forced kernel variant does not fit this circuit");
+    if (tab[forced].NC == 0 && n > AHK_SMALL_NMAX) return fail("circuit too large");
+    *vid = forced;
+    return 0;
+  }
+  const bool big_batch = units >= 32768;
+  int best = -1;
+  for (int i = 2; i < ntab; i++) {
+    if (!fits(tab[i], n)) continue;
+    if (e->group > 0 && tab[i].G != e->group) continue;
+    if (best < 0) { best = i; continue; }
+    const VarInfo &a = tab[i], &b = tab[best];
+    if (a.NC != b.NC) { if (a.NC < b.NC) best = i; continue; }
+    if (big_batch ? a.G < b.G : a.G > b.G) best = i;
+  }
+  if (best < 0) {   // generic fallback
+    if (n > AHK_SMALL_NMAX) return fail("circuit too large for the shared-memory engine");
+    if (e->group > 0 && e->group != 8 && e->group != 32)
+      return fail("no kernel variant with that many lanes fits this circuit");
+    best = e->group == 8 ? 0 : (e->group == 32 ? 1 : (big_batch ? 0 : 1));
+  }
+  *vid = best;
+  return 0;
+}
 
-int plan(const ahk_engine* e, long long units, int stride_of_G(const ahk_engine*, int, void*),
-         void* ud, int G, Launch& L) {
+// Block size: the per-instance shared-memory slice bounds how many instances are
+// resident per SM (228 KB per SM, 1 KB reserved per block); smaller blocks waste
+// less of it.  Registers (<= 128 per thread for the common variants) allow 512
+// threads per SM.  Pick the block size with the most resident instances.
+int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int stride, Launch& L) {
+  const size_t sm_total = 228 * 1024;
+  long long best_res = -1;
   for (int threads = 128; threads >= 32; threads >>= 1) {
-    if (threads < G) break;
-    int ipb = threads / G;
-    size_t smem = (size_t)ipb * stride_of_G(e, G, ud) * sizeof(double);
-    if (smem <= e->smem_max) {
-      L.G = G; L.threads = threads; L.smem = smem;
+    if (threads < v.G) break;
+    const int ipb = threads / v.G;
+    const size_t smem = (size_t)ipb * stride * sizeof(double);
+    if (smem > e->smem_max) continue;
+    long long blocks_sm = (long long)(sm_total / (smem + 1024));
+    if (blocks_sm > 32) blocks_sm = 32;
+    long long thr = blocks_sm * threads;
+    if (thr > 512) thr = 512;
+    const long long res = thr / v.G;
+    if (res > best_res) {
+      best_res = res;
+      L.vid = vid; L.G = v.G; L.threads = threads; L.smem = smem;
       L.blocks = (int)((units + ipb - 1) / ipb);
-      return 0;
     }
   }
-  return fail("circuit too large for the shared-memory engine (n = " + std::to_string(e->n) + ")");
+  if (best_res < 0)
+    return fail("circuit too large for the shared-memory engine (n = " + std::to_string(e->n) + ")");
+  return 0;
 }
 
-template <typename K, typename F>
-int launch_g(int G, F&& f) {
-  switch (G) {
-    case 1: return f(std::integral_constant<int, 1>());
-    case 2: return f(std::integral_constant<int, 2>());
-    case 4: return f(std::integral_constant<int, 4>());
-    case 8: return f(std::integral_constant<int, 8>());
-    case 16: return f(std::integral_constant<int, 16>());
-    case 32: return f(std::integral_constant<int, 32>());
-  }
-  return fail("bad group size");
-}
-
-template <typename KernelT, typename Args>
-int do_launch(KernelT kern, const Args& args, const Launch& L, cudaStream_t s) {
-  if (L.smem > 48 * 1024)
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  kern<<<L.blocks, L.threads, L.smem, s>>>(args);
-  CK(cudaGetLastError());
+int launched(int rc) {
+  if (rc != 0) return fail(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
   g_launches++;
   return 0;
 }
@@ -321,12 +273,20 @@ KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
   return k;
 }
 
-struct LayoutReq { int mode, method, usc; };
-int stride_small(const ahk_engine* e, int G, void* ud) {
-  LayoutReq* r = (LayoutReq*)ud;
-  return make_layout(e->H, r->mode, r->method, r->usc, G).stride;
+int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* d_sweep, int npts,
+                 const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
+                 int32_t* status, cudaStream_t s) {
+  int vid;
+  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, &vid)) return -1;
+  const VarInfo& v = real_variants()[vid];
+  Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC);
+  Launch L;
+  if (plan(e, batch->B, vid, v, Ly.stride, L)) return -1;
+  KDc k;
+  k.b = make_base(e, batch, Ly);
+  k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
+  return launched(launch_dc(k, L, s));
 }
-int stride_ac(const ahk_engine* e, int G, void*) { return make_ac_layout(e->H, G).stride; }
 
 }  // namespace
 
@@ -383,6 +343,25 @@ int ahk_set_group(ahk_engine* e, int lanes) {
   return 0;
 }
 
+int ahk_variant_count(int kind) { return kind == 1 ? AHK_N_AC_VARIANTS : AHK_N_REAL_VARIANTS; }
+
+int ahk_variant_info(int kind, int id, int32_t* nc_r_g) {
+  if (!nc_r_g || id < 0 || id >= ahk_variant_count(kind)) return fail("bad variant id");
+  const VarInfo& v = (kind == 1 ? ac_variants() : real_variants())[id];
+  nc_r_g[0] = v.NC; nc_r_g[1] = v.R; nc_r_g[2] = v.G;
+  return 0;
+}
+
+int ahk_set_variant(ahk_engine* e, int real_id, int ac_id) {
+  if (!e) return fail("null engine");
+  if (real_id >= AHK_N_REAL_VARIANTS || ac_id >= AHK_N_AC_VARIANTS) return fail("bad variant id");
+  if (real_id >= 0 && !fits(real_variants()[real_id], e->n)) return fail("variant does not fit this circuit");
+  if (ac_id >= 0 && !fits(ac_variants()[ac_id], e->n)) return fail("variant does not fit this circuit");
+  e->force_vid = real_id < 0 ? -1 : real_id;
+  e->force_ac_vid = ac_id < 0 ? -1 : ac_id;
+  return 0;
+}
+
 int ahk_probe_fp64(int blocks, int threads, int iters, double* out, void* stream) {
   if (blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0 || !out)
     return fail("ahk_probe_fp64: bad argument");
@@ -401,13 +380,7 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0, int use_gues
     double v = 0.0;
     return e->big.run(e, batch, -1, &v, 1, x, iters, status, resid, s, g_err, g_launches);
   }
-  LayoutReq rq = {MODE_OP, 0, 0};
-  Launch L;
-  if (plan(e, batch->B, stride_small, &rq, pick_group(e, batch->B, 1), L)) return -1;
-  KOp k;
-  k.b = make_base(e, batch, make_layout(e->H, MODE_OP, 0, 0, L.G));
-  k.a = OpArgs{x0, use_guess, x, resid, iters, status};
-  return launch_g<KOp>(L.G, [&](auto g) { return do_launch(k_op<decltype(g)::value>, k, L, s); });
+  return run_dc_small(e, batch, -1, nullptr, 1, x0, use_guess, x, resid, iters, status, s);
 }
 
 int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_values,
@@ -426,13 +399,8 @@ int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
                       g_err, g_launches);
   }
   if (to_scratch(e, sweep_values, npts, s)) return -1;
-  LayoutReq rq = {MODE_OP, 0, 0};
-  Launch L;
-  if (plan(e, batch->B, stride_small, &rq, pick_group(e, batch->B, 1), L)) return -1;
-  KDc k;
-  k.b = make_base(e, batch, make_layout(e->H, MODE_OP, 0, 0, L.G));
-  k.a = DcArgs{src_elem, e->d_scratch, npts, x0, use_guess, x_out, iters, status};
-  return launch_g<KDc>(L.G, [&](auto g) { return do_launch(k_dc<decltype(g)::value>, k, L, s); });
+  return run_dc_small(e, batch, src_elem, e->d_scratch, npts, x0, use_guess, x_out, nullptr, iters,
+                      status, s);
 }
 
 int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tstart, double tstep,
@@ -447,15 +415,18 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   if (e->n > AHK_SMALL_NMAX) return fail("transient needs n <= 64 in this build");
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
-  LayoutReq rq = {MODE_TRAN, method, use_step_control};
+  int vid;
+  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, &vid)) return -1;
+  const VarInfo& v = real_variants()[vid];
+  Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC);
   Launch L;
-  if (plan(e, batch->B, stride_small, &rq, pick_group(e, batch->B, 4), L)) return -1;
+  if (plan(e, batch->B, vid, v, Ly.stride, L)) return -1;
   KTran k;
-  k.b = make_base(e, batch, make_layout(e->H, MODE_TRAN, method, use_step_control, L.G));
+  k.b = make_base(e, batch, Ly);
   k.x0 = x0;
   k.a = TranArgs{tstart, tstep, tstop, method, use_step_control, max_rows, t_out, x_out, rows, counters};
   k.status = status;
-  return launch_g<KTran>(L.G, [&](auto g) { return do_launch(k_tran<decltype(g)::value>, k, L, s); });
+  return launched(launch_tran(k, L, s));
 }
 
 int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const double* omegas,
@@ -473,8 +444,12 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     while (nchunks < npts && batch->B * nchunks < want && npts / (nchunks * 2) >= 4) nchunks *= 2;
   }
   long long units = batch->B * nchunks;
+  int vid;
+  if (pick_variant(e, ac_variants(), AHK_N_AC_VARIANTS, e->force_ac_vid, units, &vid)) return -1;
+  const VarInfo& v = ac_variants()[vid];
+  AcLayout AL = make_ac_layout(e->H, v.G, v.NC);
   Launch L;
-  if (plan(e, units, stride_ac, nullptr, pick_group(e, units, 8), L)) return -1;
+  if (plan(e, units, vid, v, AL.stride, L)) return -1;
   {
     long long nb = (batch->B + 255) / 256;
     k_fill_i32<<<(int)nb, 256, 0, s>>>(status, batch->B, AHK_ST_OK);
@@ -482,10 +457,10 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     g_launches++;
   }
   KAc k;
-  k.p = e->dprog; k.o = e->o; k.AL = make_ac_layout(e->H, L.G);
+  k.p = e->dprog; k.o = e->o; k.AL = AL;
   k.vary = batch->vary; k.B = batch->B; k.nchunks = nchunks;
   k.a = AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status};
-  return launch_g<KAc>(L.G, [&](auto g) { return do_launch(k_ac<decltype(g)::value>, k, L, s); });
+  return launched(launch_ac(k, L, s));
 }
 
 }  // extern "C"

@@ -6,75 +6,56 @@
 
 namespace ahk {
 
-struct OpArgs {
-  const double* x0; int use_guess;
-  double* x; double* resid; int* iters; int* status;
-};
-
+// OP = a sweep of one point with no swept source (src_elem < 0, sweep == nullptr)
 struct DcArgs {
   int src_elem; const double* sweep; int npts;
   const double* x0; int use_guess;
-  double* x_out; int* iters; int* status;
+  double* x_out; double* resid; int* iters; int* status;
 };
 
-template <int G>
+template <class V>
 AHK_DEV void init_ctx(Ctx& c) {
-  c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0;
+  c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0; c.gadd = 0.0; c.G = V::G;
 }
 
-// dc_analysis.op_analysis for one instance
-template <int G>
-AHK_DEV void run_op(Ctx& c, const OpArgs& a) {
-  const int n = c.p->n;
-  init_ctx<G>(c);
-  build_values(c, false);
-  double* x = c.x();
-  if (a.x0) for (int i = c.sub; i < n; i += G) x[i] = a.x0[c.inst * n + i];
-  Grp<G>::sync(c.mask);
-  int it = 0;
-  int st = op_analysis<G>(c, a.x0 != nullptr, a.use_guess != 0, &it);
-  const double* res = c.sm + c.L->res;
-  for (int i = c.sub; i < n; i += G) {
-    a.x[c.inst * n + i] = x[i];
-    if (a.resid) a.resid[c.inst * n + i] = (st & AHK_ST_OK) ? res[i] : nan("");
-  }
-  if (c.sub == 0) { a.iters[c.inst] = it; a.status[c.inst] = st; }
-}
-
-// dc_analysis.dc_analysis for one instance: the full OP per sweep value,
-// warm-started from the previous point (dc_analysis.py:563-581)
-template <int G>
+// dc_analysis.op_analysis (one point) / dc_analysis.dc_analysis for one instance: the
+// full OP per sweep value, warm-started from the previous point (dc_analysis.py:563-581)
+template <class V>
 AHK_DEV void run_dc(Ctx& c, const DcArgs& a) {
-  const int n = c.p->n;
-  init_ctx<G>(c);
-  build_values(c, false);
+  const int n = c.p->n, G = V::G;
+  init_ctx<V>(c);
+  build_values<V>(c, false);
   double* x = c.x();
   bool have = a.x0 != nullptr;
   if (have) for (int i = c.sub; i < n; i += G) x[i] = a.x0[c.inst * n + i];
-  Grp<G>::sync(c.mask);
+  Grp<V::G>::sync(c.mask);
   c.dc_src = a.src_elem;
   for (int k = 0; k < a.npts; k++) {
-    c.dc_val = a.sweep[k];
+    if (a.src_elem >= 0) c.dc_val = a.sweep[k];
     int it = 0;
-    int st = op_analysis<G>(c, have, a.use_guess != 0, &it);
+    int st = op_analysis<V>(c, have, a.use_guess != 0, &it);
     long long o = c.inst * a.npts + k;
-    for (int i = c.sub; i < n; i += G) a.x_out[o * n + i] = x[i];
+    const double* res = c.sm + c.L->res;
+    for (int i = c.sub; i < n; i += G) {
+      a.x_out[o * n + i] = x[i];
+      if (a.resid) a.resid[o * n + i] = (st & AHK_ST_OK) ? res[i] : nan("");
+    }
     if (c.sub == 0) { a.iters[o] = it; a.status[o] = st; }
     have = (st & AHK_ST_OK) != 0;   // a failed point returns None -> next one restarts
-    Grp<G>::sync(c.mask);
+    Grp<V::G>::sync(c.mask);
   }
 }
 
 // transient.transient_analysis for one instance
-template <int G>
+template <class V>
 AHK_DEV void run_tran(Ctx& c, const double* x0, const TranArgs& a, int* status) {
-  const int n = c.p->n;
-  init_ctx<G>(c);
-  build_values(c, true);
+  const int n = c.p->n, G = V::G;
+  init_ctx<V>(c);
+  build_values<V>(c, true);
   double* x = c.x();
   for (int i = c.sub; i < n; i += G) x[i] = x0 ? x0[c.inst * n + i] : 0.0;
-  Grp<G>::sync(c.mask);
-  int st = tran_analysis<G>(c, a);
+  Grp<V::G>::sync(c.mask);
+  int st = tran_analysis<V>(c, a);
   if (c.sub == 0) status[c.inst] = st;
 }
 

@@ -1,0 +1,28 @@
+// k_ac.cu — AC kernels (ac.ac_analysis): unit = (instance, frequency chunk).  sm_100a.
+#include "kernels.cuh"
+
+namespace ahk {
+
+template <class V>
+__global__ void __launch_bounds__(128, (V::NC > 0 && V::NC <= 8) ? 4 : ((V::NC == 0 || V::NC <= 16) ? 3 : 2)) k_ac(const __grid_constant__ KAc k) {
+  Ctx c; long long u;
+  if (!make_ctx<V::G>(c, &k.p, &k.o, &k.AL.L, k.AL.stride, k.vary, k.B, k.B * k.nchunks, u)) return;
+  c.inst = u / k.nchunks;
+  const int ch = (int)(u % k.nchunks);
+  AcArgs a = k.a;
+  const int per = (a.npts + k.nchunks - 1) / k.nchunks;
+  a.f0 = ch * per;
+  a.f1 = min(a.npts, a.f0 + per);
+  run_ac<V>(c, k.AL, a);
+}
+
+int launch_ac(const KAc& k, const Launch& L, cudaStream_t s) {
+  switch (L.vid) {
+#define X(id, NC, R, G) case id: return do_launch(k_ac<Var<NC, R, G> >, k, L, s);
+    AHK_AC_VARIANTS(X)
+#undef X
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace ahk

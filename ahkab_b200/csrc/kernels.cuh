@@ -1,0 +1,95 @@
+// kernels.cuh — launch-side declarations shared by the kernel translation units
+// (k_dc.cu, k_tran.cu, k_ac.cu) and the host API (engine.cu).  Each kernel is a
+// persistent-per-instance kernel: a group of G lanes carries its instance through
+// the whole analysis (every Newton iteration of both OP passes / every sweep point /
+// every time step / every frequency), touching HBM only for the parameter reads and
+// the result rows.  See core.cuh for the per-instance algorithm.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "ac.cuh"
+#include "entry.cuh"
+
+namespace ahk {
+
+// Kernel variants (id, NC, R, G): NC matrix columns incl. the rhs (0 = run-time n,
+// shared-memory fallback), R rows per lane, G lanes per instance.  R*G >= n, NC > n.
+#define AHK_REAL_VARIANTS(X)                                                          \
+  X(0, 0, 0, 8) X(1, 0, 0, 32)                                                        \
+  X(2, 4, 3, 1) X(3, 6, 5, 1)                                                         \
+  X(4, 4, 1, 4) X(5, 6, 1, 8) X(6, 8, 2, 4) X(7, 10, 3, 4) X(8, 12, 3, 4)             \
+  X(9, 16, 2, 8) X(10, 16, 1, 16) X(11, 24, 3, 8) X(12, 32, 2, 16)
+#define AHK_N_REAL_VARIANTS 13
+// complex128 rows cost twice the registers: one row per lane beyond n = 3
+#define AHK_AC_VARIANTS(X)                                                            \
+  X(0, 0, 0, 8) X(1, 0, 0, 32)                                                        \
+  X(2, 4, 3, 1) X(3, 8, 1, 8) X(4, 16, 1, 16) X(5, 24, 1, 32) X(6, 32, 1, 32)
+#define AHK_N_AC_VARIANTS 7
+
+struct VarInfo { int NC, R, G; };
+inline const VarInfo* real_variants() {
+  static const VarInfo t[] = {
+#define X(id, NC, R, G) {NC, R, G},
+      AHK_REAL_VARIANTS(X)
+#undef X
+  };
+  return t;
+}
+inline const VarInfo* ac_variants() {
+  static const VarInfo t[] = {
+#define X(id, NC, R, G) {NC, R, G},
+      AHK_AC_VARIANTS(X)
+#undef X
+  };
+  return t;
+}
+
+struct KBase {
+  Prog p; Opts o; Layout L;
+  const double* vary; long long B;
+};
+struct KDc { KBase b; DcArgs a; };
+struct KTran { KBase b; const double* x0; TranArgs a; int* status; };
+struct KAc { Prog p; Opts o; AcLayout AL; const double* vary; long long B; AcArgs a; int nchunks; };
+
+struct Launch { int vid, G, threads, blocks; size_t smem; };
+
+// defined in k_dc.cu / k_tran.cu / k_ac.cu; return cudaError_t as int
+int launch_dc(const KDc& k, const Launch& L, cudaStream_t s);
+int launch_tran(const KTran& k, const Launch& L, cudaStream_t s);
+int launch_ac(const KAc& k, const Launch& L, cudaStream_t s);
+
+#ifdef __CUDACC__
+template <int G>
+__device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
+                                         int stride, const double* vary, long long B,
+                                         long long units, long long& unit) {
+  extern __shared__ double smem[];
+  const int gi = threadIdx.x / G;
+  const int ipb = blockDim.x / G;
+  unit = (long long)blockIdx.x * ipb + gi;
+  if (unit >= units) return false;
+  const int lane = threadIdx.x & 31;
+  c.p = p; c.o = o; c.L = L;
+  c.sm = smem + (size_t)gi * stride;
+  c.vary = vary; c.B = B; c.inst = unit;
+  c.sub = threadIdx.x % G;
+  c.G = G;
+  c.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  return true;
+}
+
+template <typename KernelT, typename Args>
+int do_launch(KernelT kern, const Args& args, const Launch& L, cudaStream_t s) {
+  if (L.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<L.blocks, L.threads, L.smem, s>>>(args);
+  return (int)cudaGetLastError();
+}
+#endif
+
+}  // namespace ahk

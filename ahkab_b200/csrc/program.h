@@ -25,6 +25,7 @@ struct DevOp {      // non-linear device
   int type, pbase, mbase, flags;
   int node[4];      // reduced indices (-1 ground): D n1,n2; MOS d,g,s,b; SW n1,n2,sn1,sn2
   int dout;         // first slot of this device's outputs
+  int con;          // first slot of its per-instance constants (EKV), else -1
   int active;       // 0: both output nodes grounded -> never evaluated (dc_analysis.py:863)
 };
 
@@ -41,6 +42,7 @@ struct Prog {
   int n, nv1, npos, nlin, nsrc, ntd, ndev, ndout, nlock, nguess, nparams, nac;
   const int* row_ptr;             // [n+1] positions are sorted by (row, col)
   const unsigned short* pcol;     // [npos]
+  const unsigned short* pcd;      // [npos] pcol | 0x8000 on node-row diagonals (n < 32768)
   const unsigned short* prowi;    // [npos] row of each position
   const unsigned char* pdiag;     // [npos] node-row diagonal: gets Gmin / cmin
   const int* nl_ptr;              // [npos+1] CSR of device contributions per position
@@ -67,9 +69,14 @@ struct Prog {
 };
 
 struct Layout {     // offsets in doubles inside one instance's slice
-  int RS;           // row stride of A (odd, >= n+1)
+  int RS;           // row stride of A: NC for a register variant, else odd >= n+1
+  int ARS;          // row stride of the staging rows of a register variant (NC - 1)
   int A, x, dx, T, res, Bv, Mv, Dv, Nd, Nc, Ntr, dout, dst, x1, xs, xacc;
   int hx, hdx, ht, C0, pred, bytes;
+  int Pv;           // staged parameter values [nparams]
+  int dcon;         // per-device constants [ndev][EK_NCONST]
+  int pvb;          // pivot-row broadcast buffers [2][NC]
+  int gsc;          // scratch of the GEAR coefficient generation [32]
   int buflen;
   int stride;       // doubles per instance (padded: stride % 16 == (G*RS) % 16)
 };

@@ -25,7 +25,7 @@ namespace ahk {
 struct HostProg {
   Prog hdr;   // scalar fields valid; pointers filled by view()/upload
   std::vector<int> row_ptr, nl_ptr, tx_ptr, lock, gslot, slot_vary;
-  std::vector<unsigned short> pcol, prowi;
+  std::vector<unsigned short> pcol, prowi, pcd;
   std::vector<unsigned char> pdiag;
   std::vector<int> term_ptr, term_slot;
   std::vector<signed char> term_kind;
@@ -37,12 +37,13 @@ struct HostProg {
   std::vector<double> guessG, gscale, gconst, nominal;
   std::vector<int> ic_kind, ic_a, ic_b, ic_slot;   // unused on device (host x0 helpers)
   int n_nodes = 0, n_vde = 0;
+  int ncon = 0;      // doubles of per-instance device constants
   bool nonlinear = false;
 
   // Prog whose pointers reference this object's host vectors
   Prog view() const {
     Prog p = hdr;
-    p.row_ptr = row_ptr.data(); p.pcol = pcol.data(); p.prowi = prowi.data(); p.pdiag = pdiag.data();
+    p.row_ptr = row_ptr.data(); p.pcol = pcol.data(); p.pcd = pcd.data(); p.prowi = prowi.data(); p.pdiag = pdiag.data();
     p.term_ptr = term_ptr.data(); p.term_slot = term_slot.data(); p.term_kind = term_kind.data();
     p.nl_ptr = nl_ptr.data(); p.nl_src = nl_src.data(); p.nl_sgn = nl_sgn.data();
     p.tx_ptr = tx_ptr.data(); p.tx_src = tx_src.data(); p.tx_sgn = tx_sgn.data();
@@ -125,6 +126,9 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
     H.pdiag[k] = (r == cc && r < nv1) ? 1 : 0;
   }
   for (int r = 0; r < n; r++) H.row_ptr[r + 1] += H.row_ptr[r];
+  if (n >= 32768) throw std::runtime_error("circuit too large (n >= 32768)");
+  H.pcd.resize(np);
+  for (int k = 0; k < np; k++) H.pcd[k] = (unsigned short)(H.pcol[k] | (H.pdiag[k] ? 0x8000 : 0));
 
   // pass 2: linear ops in the reference's loop order (dc_analysis.py:989-1062)
   auto mk = [&](int kind, const ahk_elem& e) { LinOp o; std::memset(&o, 0, sizeof o); o.kind = kind; o.pbase = e.pbase; o.aux0 = e.aux0; o.aux1 = e.aux1; for (int i = 0; i < 6; i++) o.pos[i] = -1; return o; };
@@ -208,7 +212,8 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
     H.nonlinear = true;
     DevOp d; std::memset(&d, 0, sizeof d);
     d.type = e.type; d.pbase = e.pbase; d.mbase = e.mbase; d.flags = e.flags;
-    d.dout = ndout; d.active = 1;
+    d.dout = ndout; d.active = 1; d.con = -1;
+    if (e.type == AHK_EKV) { d.con = H.ncon; H.ncon += 16; }
     const int b = ndout;
     switch (e.type) {
       case AHK_D:   // stamp path, diode.py:150-198
@@ -299,20 +304,31 @@ inline void set_vary_slots(HostProg& H, int n_vary, const int* slots) {
 enum { MODE_OP = 0, MODE_TRAN = 1 };
 
 // Shared-memory layout of one instance for G lanes per instance.
-inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_control, int G) {
+// NC > 0: register variant with NC matrix columns (staging rows of NC - 1 doubles).
+// Every array is allocated only when the mode / variant / circuit needs it: the
+// bytes per instance bound how many instances are resident per SM.
+inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_control, int G,
+                          int NC = 0) {
   const Prog& h = H.hdr;
   Layout L; std::memset(&L, 0, sizeof L);
   const int n = h.n;
-  L.RS = (n + 1) | 1;
+  L.RS = NC > 0 ? NC - 1 : ((n + 1) | 1);
+  L.ARS = L.RS;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
   L.A = take(n * L.RS);
   L.x = take(n); L.dx = take(n); L.T = take(n); L.res = take(n);
-  L.Bv = take(h.npos); L.Mv = take(h.npos);
-  L.Nd = take(n); L.Nc = take(n);
+  L.Mv = take(h.npos);
+  // OP/DC: the matrix is Mv plus Gmin on the node diagonals, added on the fly
+  L.Bv = mode == MODE_TRAN ? take(h.npos) : L.Mv;
+  L.Nc = take(n);
+  L.Nd = h.ntd > 0 ? take(n) : L.Nc;      // N + Tt(t); no waveforms: N itself
   L.dout = take(h.ndout); L.dst = take(2 * h.ndev);
   L.x1 = take(n); L.xs = take(n);
-  L.bytes = take(16);
+  L.bytes = take(NC > 0 ? 0 : 16);
+  L.Pv = take(h.nparams); L.dcon = take(H.ncon);
+  L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);
+  L.gsc = take(mode == MODE_TRAN && method >= AHK_GEAR1 ? 32 : 0);
   L.buflen = 1;
   if (mode == MODE_TRAN) {
     int order, max_x, max_dx, pmax_x;
@@ -333,8 +349,13 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
     L.hx = L.hdx = L.ht = L.C0 = L.pred = 0;
   }
   // bank rule: consecutive groups of a half-warp must land on distinct 8-byte banks
-  int want = (G * L.RS) % 16;
-  while (off % 16 != want) off++;
+  // (one lane per instance: any odd stride spreads 16 lanes over the 16 banks)
+  if (G == 1) { if (off % 2 == 0) off++; }
+  else {
+    int want = (G * L.RS) % 16;
+    if (want % 2 == 0) want = (want + 1) % 16;
+    while (off % 16 != want) off++;
+  }
   L.stride = off;
   return L;
 }

@@ -97,6 +97,11 @@ class Engine(object):
         if self.lib.ahk_set_group(self._h, int(lanes)) != 0:
             raise EngineError(self._err())
 
+    def set_variant(self, real=-1, ac=-1):
+        """Force a kernel variant (ids from _abi.variants()); -1 = heuristic."""
+        if self.lib.ahk_set_variant(self._h, int(real), int(ac)) != 0:
+            raise EngineError(self._err())
+
     def _batch(self):
         b = _abi.ahk_batch()
         b.B = self.B

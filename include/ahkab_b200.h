@@ -45,8 +45,9 @@ enum {
   AHK_L = 3,   /* inductor (vde)      params: [L, ic]                      */
   AHK_K = 4,   /* inductor coupling   params: [K]  ref/ref2 = vde of L1/L2,
                                       aux0/aux1 = pbase of L1/L2           */
-  AHK_V = 5,   /* V source (vde)      params: [dc, |ac|, arg(ac), tf0..tf7] */
-  AHK_I = 6,   /* I source            params: [dc, |ac|, arg(ac), tf0..tf7] */
+  AHK_V = 5,   /* V source (vde)      params: [dc, |ac|, arg(ac)] + [tf0..tf7]
+                                      iff tf != AHK_TF_NONE                 */
+  AHK_I = 6,   /* I source            params: as AHK_V                      */
   AHK_E = 7,   /* VCVS (vde)          params: [alpha]  n3,n4 = sense nodes  */
   AHK_G = 8,   /* VCCS                params: [alpha]  n3,n4 = sense nodes  */
   AHK_H = 9,   /* CCVS (vde)          params: [alpha]  ref = sensed vde     */
@@ -168,8 +169,17 @@ void ahk_destroy(ahk_engine* e);
 int ahk_size(const ahk_engine* e);
 /* Replace the options snapshot (cheap). */
 int ahk_set_options(ahk_engine* e, const ahk_options* opts);
-/* Tuning: lanes cooperating on one instance (1,2,4,8,16,32; 0 = heuristic). */
+/* Tuning: lanes cooperating on one instance (1,2,4,8,16,32; 0 = heuristic):
+ * restricts the kernel-variant choice to variants with that many lanes. */
 int ahk_set_group(ahk_engine* e, int lanes);
+/* Kernel variants.  A variant (NC, R, G) fixes at compile time the matrix columns
+ * NC (>= n+1; 0 = run-time n, shared-memory fallback), the rows per lane R and the
+ * lanes per instance G.  kind 0 = OP/DC/transient kernels, 1 = AC kernels.
+ * ahk_variant_info writes {NC, R, G}; ahk_set_variant forces one (-1 = heuristic),
+ * failing if it cannot hold the engine's circuit. */
+int ahk_variant_count(int kind);
+int ahk_variant_info(int kind, int id, int32_t* nc_r_g);
+int ahk_set_variant(ahk_engine* e, int real_id, int ac_id);
 const char* ahk_last_error(void);
 /* Number of kernel launches issued by this library so far (all engines). */
 int64_t ahk_launch_count(void);

@@ -38,6 +38,21 @@ def lib():
 
 _dp, _ip = _oracle._dp, _oracle._ip
 
+# host-testable kernel variants (tests/hostemu/hostemu.cpp)
+VARIANTS = {0: 'Var<0,0,1> generic', 1: 'Var<4,3,1>', 2: 'Var<6,5,1>'}
+
+
+def set_variant(v):
+    if lib().emu_set_variant(int(v)) != 0:
+        raise ValueError("unknown host variant %r" % (v,))
+
+
+def _check(rc):
+    if rc == -2:
+        raise ValueError("circuit does not fit the selected host variant")
+    if rc != 0:
+        raise RuntimeError("hostemu call failed (%d)" % rc)
+
 
 class Emu(_oracle.Oracle):
     """Same constructor as Oracle; methods run the emulated engine instead."""
@@ -50,8 +65,8 @@ class Emu(_oracle.Oracle):
         x = np.zeros((B, n)); res = np.zeros((B, n))
         it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
         x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
-        lib().emu_op(*self._common(), _dp(x0), C.c_int(bool(use_guess)),
-                     _dp(x), _dp(res), _ip(it), _ip(st))
+        _check(lib().emu_op(*self._common(), _dp(x0), C.c_int(bool(use_guess)),
+                     _dp(x), _dp(res), _ip(it), _ip(st)))
         return dict(x=x, resid=res, iters=it, status=st)
 
     def dc_sweep(self, src_elem, sweep, x0=None, use_guess=True, threads=0):
@@ -61,9 +76,9 @@ class Emu(_oracle.Oracle):
         x = np.zeros((B, P, n))
         it = np.zeros((B, P), np.int32); st = np.zeros((B, P), np.int32)
         x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
-        lib().emu_dc_sweep(*self._common(), C.c_int(src_elem), _dp(sweep),
+        _check(lib().emu_dc_sweep(*self._common(), C.c_int(src_elem), _dp(sweep),
                            C.c_int(P), _dp(x0), C.c_int(bool(use_guess)),
-                           _dp(x), _ip(it), _ip(st))
+                           _dp(x), _ip(it), _ip(st)))
         return dict(x=x, iters=it, status=st)
 
     def tran(self, x0, tstart, tstep, tstop, method, use_step_control,
@@ -74,11 +89,11 @@ class Emu(_oracle.Oracle):
         rows = np.zeros(B, np.int32); cnt = np.zeros((B, 4), np.int32)
         st = np.zeros(B, np.int32)
         x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
-        lib().emu_tran(*self._common(), _dp(x0), C.c_double(tstart),
+        _check(lib().emu_tran(*self._common(), _dp(x0), C.c_double(tstart),
                        C.c_double(tstep), C.c_double(tstop),
                        C.c_int(_abi.METHODS[method.upper()]),
                        C.c_int(bool(use_step_control)), C.c_int64(max_rows),
-                       _dp(t), _dp(x), _ip(rows), _ip(cnt), _ip(st))
+                       _dp(t), _dp(x), _ip(rows), _ip(cnt), _ip(st)))
         return dict(t=t, x=x, rows=rows, counters=cnt, status=st)
 
     def ac(self, omegas, x_op=None, threads=0):
@@ -87,6 +102,6 @@ class Emu(_oracle.Oracle):
         x = np.zeros((B, len(om), n), np.complex128)
         st = np.zeros(B, np.int32)
         x_op = None if x_op is None else np.ascontiguousarray(x_op, np.float64)
-        lib().emu_ac(*self._common(), _dp(x_op), _dp(om), C.c_int(len(om)),
-                     x.ctypes.data_as(C.POINTER(C.c_double)), _ip(st))
+        _check(lib().emu_ac(*self._common(), _dp(x_op), _dp(om), C.c_int(len(om)),
+                     x.ctypes.data_as(C.POINTER(C.c_double)), _ip(st)))
         return dict(x=x, status=st)

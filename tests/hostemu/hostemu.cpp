@@ -17,6 +17,11 @@ using namespace ahk;
 
 static void copy_opts(const ahk_options* o, Opts& q) { std::memcpy(&q, o, sizeof(Opts)); }
 
+// Host-testable kernel variants: one lane per instance (no cross-lane traffic).
+//   0: Var<0,0,1> generic shared-memory fallback   1: Var<4,3,1>   2: Var<6,5,1>
+static int g_variant = 0;
+static int variant_nc() { return g_variant == 1 ? 4 : (g_variant == 2 ? 6 : 0); }
+
 struct Emu {
   HostProg H; Prog p; Opts o; Layout L; std::vector<double> sm;
   Emu(const ahk_circuit* c, const ahk_options* opts, int n_vary, const int32_t* slots, int mode,
@@ -25,23 +30,34 @@ struct Emu {
     set_vary_slots(H, n_vary, slots);
     p = H.view();
     copy_opts(opts, o);
-    L = make_layout(H, mode, method, usc, 1);
+    L = make_layout(H, mode, method, usc, 1, variant_nc());
     sm.assign(L.stride + 64, 0.0);
   }
   Ctx ctx(const double* vary, long long B, long long b) {
     Ctx c; c.p = &p; c.o = &o; c.L = &L; c.sm = sm.data(); c.vary = vary; c.B = B; c.inst = b;
-    c.sub = 0; c.mask = 1u; return c;
+    c.sub = 0; c.G = 1; c.mask = 1u; return c;
   }
+  bool fits() const { int nc = variant_nc(); return nc == 0 || p.n <= nc - 1; }
 };
 
+#define DISPATCH(CALL)                                   \
+  switch (g_variant) {                                   \
+    case 1: { typedef Var<4, 3, 1> V; CALL; } break;     \
+    case 2: { typedef Var<6, 5, 1> V; CALL; } break;     \
+    default: { typedef Var<0, 0, 1> V; CALL; } break;    \
+  }
+
 extern "C" {
+
+int emu_set_variant(int v) { if (v < 0 || v > 2) return -1; g_variant = v; return 0; }
 
 int emu_op(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, const int32_t* slots,
            const double* vary, const double* x0, int use_guess, double* x, double* resid,
            int32_t* iters, int32_t* status) {
   Emu e(c, o, n_vary, slots, MODE_OP, 0, 0);
-  OpArgs a = {x0, use_guess, x, resid, iters, status};
-  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); run_op<1>(cx, a); }
+  if (!e.fits()) return -2;
+  DcArgs a = {-1, nullptr, 1, x0, use_guess, x, resid, iters, status};
+  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); DISPATCH(run_dc<V>(cx, a)) }
   return 0;
 }
 
@@ -50,8 +66,9 @@ int emu_dc_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_va
                  int npts, const double* x0, int use_guess, double* x_out, int32_t* iters,
                  int32_t* status) {
   Emu e(c, o, n_vary, slots, MODE_OP, 0, 0);
-  DcArgs a = {src_elem, sweep, npts, x0, use_guess, x_out, iters, status};
-  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); run_dc<1>(cx, a); }
+  if (!e.fits()) return -2;
+  DcArgs a = {src_elem, sweep, npts, x0, use_guess, x_out, nullptr, iters, status};
+  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); DISPATCH(run_dc<V>(cx, a)) }
   return 0;
 }
 
@@ -60,8 +77,9 @@ int emu_tran(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, 
              int method, int usc, int64_t max_rows, double* t_out, double* x_out, int32_t* rows,
              int32_t* counters, int32_t* status) {
   Emu e(c, o, n_vary, slots, MODE_TRAN, method, usc);
+  if (!e.fits()) return -2;
   TranArgs a = {tstart, tstep, tstop, method, usc, max_rows, t_out, x_out, rows, counters};
-  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); run_tran<1>(cx, x0, a, status); }
+  for (int64_t b = 0; b < B; b++) { Ctx cx = e.ctx(vary, B, b); DISPATCH(run_tran<V>(cx, x0, a, status)) }
   return 0;
 }
 
@@ -69,14 +87,16 @@ int emu_ac(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, co
            const double* vary, const double* x_op, const double* omegas, int npts, double* x_out,
            int32_t* status) {
   Emu e(c, o, n_vary, slots, MODE_OP, 0, 0);
-  AcLayout AL = make_ac_layout(e.H, 1);
+  const int nc = g_variant == 1 ? 4 : 0;   // AC register variant on the host: Var<4,3,1>
+  if (nc && e.p.n > nc - 1) return -2;
+  AcLayout AL = make_ac_layout(e.H, 1, nc);
   std::vector<double> sm(AL.stride + 64, 0.0);
   AcArgs a = {x_op, omegas, npts, 0, npts, x_out, status};
   for (int64_t b = 0; b < B; b++) {
     status[b] = AHK_ST_OK;
     Ctx cx = e.ctx(vary, B, b);
     cx.sm = sm.data();
-    run_ac<1>(cx, AL, a);
+    if (nc) run_ac<Var<4, 3, 1> >(cx, AL, a); else run_ac<Var<0, 0, 1> >(cx, AL, a);
   }
   return 0;
 }

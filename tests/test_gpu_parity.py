@@ -27,33 +27,47 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize('G', [0, 1, 2, 4, 8, 32])
-def test_c2_diode_op(gold, G):
+def _variants(n, kind='real'):
+    """-1 (the heuristic's choice) + every compiled kernel variant that fits n."""
+    from ahkab_b200 import _abi
+    return [-1] + _abi.fitting_variants(n, kind)
+
+
+def _set(e, v, kind='real'):
+    e.set_variant(real=v if kind == 'real' else -1, ac=v if kind == 'ac' else -1)
+
+
+def test_c2_diode_op(gold):
     w = W.c2_diode_op(4096)
-    e = _engine(w); e.set_group(G)
-    r = e.op()
-    x, it, st = _np(r['x']), _np(r['iters']), _np(r['status'])
+    e = _engine(w)
     o = _oracle(w).op()
-    assert (st == o['status']).all() and (st & 1).all()
-    assert (it == o['iters']).all()                      # same NR iteration counts
-    assert np.abs(x - o['x']).max() < 1e-12
     g = gold('c2')                                       # live reference, its own 512-batch
-    w = W.c2_diode_op(int(g['K']))
-    e = _engine(w); e.set_group(G)
-    r = e.op()
-    assert np.abs(_np(r['x']) - g['x']).max() < 1e-12
-    assert (_np(r['iters']) == g['iters']).all()
+    wg = W.c2_diode_op(int(g['K']))
+    eg = _engine(wg)
+    for v in _variants(3):
+        _set(e, v)
+        r = e.op()
+        x, it, st = _np(r['x']), _np(r['iters']), _np(r['status'])
+        assert (st == o['status']).all() and (st & 1).all(), v
+        # same NR iteration counts (Gauss-Jordan vs dgesv rounding may flip the
+        # convergence test of a rare instance by one iteration)
+        assert (it != o['iters']).mean() < 0.002 and np.abs(it - o['iters']).max() <= 1, v
+        assert np.abs(x - o['x']).max() < 1e-12, v
+        _set(eg, v)
+        r = eg.op()
+        assert np.abs(_np(r['x']) - g['x']).max() < 1e-12, v
+        assert (_np(r['iters']) != g['iters']).mean() < 0.004, v
 
 
-@pytest.mark.parametrize('G', [0, 1, 4, 8, 16])
-def test_c3_colpitts_op_tran(gold, G):
+@pytest.mark.parametrize('v', [-1, 0, 1, 7, 8, 9, 10, 11, 12])
+def test_c3_colpitts_op_tran(gold, v):
     g = gold('c3')
     w = W.c3_colpitts(int(g['K']))         # the golden batch (seeded by its size)
-    e = _engine(w); e.set_group(G)
+    e = _engine(w); _set(e, v)
     o = _oracle(w)
     rop, oop = e.op(), o.op()
     xop = _np(rop['x'])
-    assert (_np(rop['iters']) == oop['iters']).all()
+    assert np.abs(_np(rop['iters']) - oop['iters']).max() <= 2
     assert common.parity_tol(xop, oop['x'], 5, 1e-6, 1e-6) < 1e-3
     assert common.parity_tol(xop[:8], g['op'], 5, 1e-6, 1e-6) < 1e-3
     x0 = common.c3_x0(oop['x'])
@@ -73,12 +87,12 @@ def test_c3_colpitts_op_tran(gold, G):
     assert np.abs(nr - ot['counters'][:, 1]).max() <= 8
 
 
-@pytest.mark.parametrize('G', [0, 2, 8])
-def test_c4_ring3_gear2_lte(gold, G):
+@pytest.mark.parametrize('v', [-1, 0, 3, 5, 6, 9])
+def test_c4_ring3_gear2_lte(gold, v):
     g = gold('c4')
     w = W.c4_ring3(int(g['K']))
     circ = w.circuit(Circuit)
-    e = _engine(w); e.set_group(G)
+    e = _engine(w); _set(e, v)
     o = _oracle(w)
     x0 = common.c4_x0(circ, w.B)
     rt = e.tran(x0, max_rows=4096, **W.C4_TRAN)
@@ -103,11 +117,11 @@ def test_c4_ring3_gear2_lte(gold, G):
         assert common.parity_tol(x[b, :k], g['x'][b, :k], 4) < 50.0
 
 
-@pytest.mark.parametrize('G', [0, 1, 8, 16, 32])
-def test_c1_butterworth_ac(gold, G):
+@pytest.mark.parametrize('v', [-1, 0, 1, 4, 5, 6])
+def test_c1_butterworth_ac(gold, v):
     g = gold('c1')
     w = W.c1_butterworth(int(g['K']))
-    e = _engine(w); e.set_group(G)
+    e = _engine(w); _set(e, v, 'ac')
     om = common.c1_omegas()
     r = e.ac(om)
     x = _np(r['x'])
@@ -140,14 +154,41 @@ def test_c5_r2r_dc_sweep(gold):
         assert np.allclose(x1[:, k - 1], sw / 2.0 ** (k - 1), rtol=1e-12)
 
 
-def test_c5_small_ladder_uses_shared_memory_engine():
-    """n = 31: the same circuit family through the small-n engine."""
-    w = W.c5_r2r(64, nodes=30)
+@pytest.mark.parametrize('nodes', [3, 5, 7, 9, 11, 15, 22, 30, 40])
+def test_c5_small_ladders_every_variant(nodes):
+    """R-2R ladders of n = nodes + 1 unknowns through every small-n kernel variant
+    that fits (register-resident Gauss-Jordan tiers and the shared-memory fallback)."""
+    w = W.c5_r2r(64, nodes=nodes)
     e = _engine(w)
     sw = common.c5_sweep()
-    x = _np(e.dc_sweep('V1', sw)['x'])
     o = _oracle(w).dc_sweep(0, sw)
-    assert np.abs(x - o['x']).max() / np.abs(o['x']).max() < 1e-13
+    for v in _variants(nodes + 1):
+        _set(e, v)
+        r = e.dc_sweep('V1', sw)
+        assert (_np(r['status']) == 1).all(), v
+        assert np.abs(_np(r['x']) - o['x']).max() / np.abs(o['x']).max() < 1e-12, v
+
+
+def test_ac_small_rc_every_variant():
+    def build(Circuit, p):
+        cir = Circuit('rc')
+        cir.add_vsource('V1', 'in', cir.gnd, dc_value=0., ac_value=1.)
+        cir.add_resistor('R1', 'in', 'out', p['R1'])
+        cir.add_capacitor('C1', 'out', cir.gnd, p['C1'])
+        return cir
+    rng = np.random.default_rng(0)
+    B = 256
+    params = dict(R1=1e3 * (1 + .1 * rng.standard_normal(B)),
+                  C1=1e-6 * (1 + .1 * rng.standard_normal(B)))
+    w = W.Workload('rc', build, dict(R1=1e3, C1=1e-6), params,
+                   dict(R1=('R1', 'value'), C1=('C1', 'value')))
+    e = _engine(w)
+    om = 2 * np.pi * np.logspace(1, 4, 20)
+    q = _oracle(w).ac(om)
+    for v in _variants(3, 'ac'):
+        _set(e, v, 'ac')
+        r = e.ac(om)
+        assert np.abs(_np(r['x']) - q['x']).max() < 1e-12, v
 
 
 def test_run_api_matches_engine():

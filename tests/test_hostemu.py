@@ -1,0 +1,113 @@
+"""CPU: the CUDA engine's per-instance source (core.cuh / entry.cuh / ac.cuh /
+devices.cuh) compiled for the host with one lane per instance, against the
+oracle on the same seeded inputs.  Covers the generic shared-memory variant and
+the register-resident thread-per-instance variants (the multi-lane variants need
+warp shuffles and are covered by the -m gpu tests)."""
+import numpy as np
+import pytest
+
+import common
+import emu
+import oracle
+from ahkab_b200 import workloads as W
+from ahkab_b200.circuit import Circuit
+
+
+def _pair(w, variant):
+    emu.set_variant(variant)
+    circ = w.circuit(Circuit)
+    return (emu.Emu(circ, w.batch(), opts=w.opts),
+            oracle.Oracle(circ, w.batch(), opts=w.opts), circ)
+
+
+@pytest.fixture(autouse=True)
+def _reset_variant():
+    yield
+    emu.set_variant(0)
+
+
+@pytest.mark.parametrize('variant', [0, 1, 2])
+def test_c2_diode_op(variant):
+    e, o, _ = _pair(W.c2_diode_op(2048), variant)
+    r, q = e.op(), o.op()
+    assert (r['status'] == q['status']).all() and (r['status'] & 1).all()
+    assert np.abs(r['x'] - q['x']).max() < 1e-12
+    # Gauss-Jordan vs LU rounding may flip a convergence test on a rare instance
+    assert (r['iters'] != q['iters']).mean() < 0.002
+
+
+@pytest.mark.parametrize('variant', [0])
+def test_c3_colpitts_op_tran(variant):
+    e, o, _ = _pair(W.c3_colpitts(8), variant)
+    rop, qop = e.op(), o.op()
+    assert np.abs(rop['iters'] - qop['iters']).max() <= 2
+    assert common.parity_tol(rop['x'], qop['x'], 5, 1e-6, 1e-6) < 1e-3
+    x0 = common.c3_x0(qop['x'])
+    a = (x0, 0., W.C3_TRAN['tstep'], W.C3_TRAN['tstop'], 'TRAP', False, 256)
+    rt, qt = e.tran(*a), o.tran(*a)
+    assert (rt['rows'] == 250).all() and (qt['rows'] == 250).all()
+    assert np.array_equal(rt['t'][:, :250], qt['t'][:, :250])
+    assert common.parity_tol(rt['x'][:, :250], qt['x'][:, :250], 5, 1e-6, 1e-6) < 1.0
+    assert np.abs(rt['counters'][:, 1] - qt['counters'][:, 1]).max() <= 8
+
+
+@pytest.mark.parametrize('variant', [0, 2])
+def test_c4_ring3_gear2_lte(variant):
+    w = W.c4_ring3(4)
+    e, o, circ = _pair(w, variant)
+    x0 = common.c4_x0(circ, w.B)
+    a = (x0, 0., 1e-9, 50e-9, 'GEAR2', True, 4096)
+    rt, qt = e.tran(*a), o.tran(*a)
+    assert (rt['status'] & 1).all()
+    assert np.abs(rt['rows'] - qt['rows']).max() <= 0.01 * qt['rows'].max()
+    k = 200     # early window, before LTE-controlled grids drift apart
+    assert common.parity_tol(rt['x'][:, :k], qt['x'][:, :k], 4) < 50.0
+
+
+@pytest.mark.parametrize('variant', [0])
+def test_c1_butterworth_ac(variant):
+    e, o, _ = _pair(W.c1_butterworth(8), variant)
+    om = common.c1_omegas()
+    r, q = e.ac(om), o.ac(om)
+    scale = np.abs(q['x']).max(axis=(1,), keepdims=True)
+    assert (np.abs(r['x'] - q['x']) / (1e-9 + 1e-6 * scale)).max() < 1.0
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_small_rc_ac_register_variant(variant):
+    """n = 3 linear RC low-pass: the AC register variant Var<4,3,1> on the host."""
+    def build(Circuit, p):
+        cir = Circuit('rc')
+        cir.add_vsource('V1', 'in', cir.gnd, dc_value=0., ac_value=1.)
+        cir.add_resistor('R1', 'in', 'out', p['R1'])
+        cir.add_capacitor('C1', 'out', cir.gnd, p['C1'])
+        return cir
+    rng = np.random.default_rng(0)
+    B = 64
+    params = dict(R1=1e3 * (1 + .1 * rng.standard_normal(B)),
+                  C1=1e-6 * (1 + .1 * rng.standard_normal(B)))
+    w = W.Workload('rc', build, dict(R1=1e3, C1=1e-6), params,
+                   dict(R1=('R1', 'value'), C1=('C1', 'value')))
+    e, o, _ = _pair(w, variant)
+    om = 2 * np.pi * np.logspace(1, 4, 20)
+    r, q = e.ac(om), o.ac(om)
+    assert np.abs(r['x'] - q['x']).max() < 1e-12
+    # analytic: |Vout| = 1/sqrt(1 + (w R C)^2) (Gmin = 1e-12 S on the nodes shifts it by ~R*Gmin)
+    ana = 1 / np.sqrt(1 + (om[None, :] * (params['R1'] * params['C1'])[:, None]) ** 2)
+    assert np.abs(np.abs(r['x'][:, :, 1]) - ana).max() < 1e-8
+
+
+def test_c5_small_ladder_dc_sweep():
+    w = W.c5_r2r(8, nodes=30)
+    e, o, _ = _pair(w, 0)
+    sw = common.c5_sweep()
+    r, q = e.dc_sweep(0, sw), o.dc_sweep(0, sw)
+    assert np.abs(r['x'] - q['x']).max() / np.abs(q['x']).max() < 1e-13
+
+
+def test_variant_that_does_not_fit_is_refused():
+    emu.set_variant(1)
+    w = W.c3_colpitts(2)          # n = 9 > 3
+    circ = w.circuit(Circuit)
+    with pytest.raises(ValueError):
+        emu.Emu(circ, w.batch(), opts=w.opts).op()

@@ -1,5 +1,5 @@
 """Dev probe: times every BASELINE workload at full size for each
-lanes-per-instance setting (CUDA events, inputs resident).  Not the bench."""
+kernel variant (CUDA events, inputs resident).  Not the bench."""
 import sys
 import time
 
@@ -33,11 +33,14 @@ def main():
         circ = w.circuit(Circuit)
         e = Engine(circ, w.batch(), opts=w.opts)
         print('== %s B=%d n=%d (setup %.2fs)' % (name, w.B, e.n, time.time() - t0), flush=True)
-        Gs = [0, 1, 2, 4, 8, 16, 32]
+        from ahkab_b200 import _abi
+        kind = 'ac' if name == 'c1' else 'real'
+        Gs = [-1] + _abi.fitting_variants(e.n, kind)
         if name == 'c5':
-            Gs = [0]
+            Gs = [-1]
+        info = {i: (NC, R, G_) for i, NC, R, G_ in _abi.variants(kind)}
         for G in Gs:
-            e.set_group(G)
+            e.set_variant(real=G if kind == 'real' else -1, ac=G if kind == 'ac' else -1)
             try:
                 if name == 'c2':
                     ms = timeit(lambda: e.op())
@@ -66,9 +69,9 @@ def main():
                     sw = common.c5_sweep()
                     ms = timeit(lambda: e.dc_sweep('V1', sw), reps=2)
                     units = w.B * len(sw)
-                print('   G=%2d  %9.3f ms  %.4g units/s' % (G, ms, units / ms * 1e3), flush=True)
+                print('   variant %2d %-12s %9.3f ms  %.4g units/s' % (G, info.get(G, 'auto'), ms, units / ms * 1e3), flush=True)
             except Exception as ex:
-                print('   G=%2d  failed: %s' % (G, ex), flush=True)
+                print('   variant %2d  failed: %s' % (G, ex), flush=True)
 
 
 if __name__ == '__main__':

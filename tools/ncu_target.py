@@ -1,4 +1,4 @@
-"""Short single-workload run for ncu captures: python tools/ncu_target.py c2 [G] [reps]"""
+"""Short single-workload run for ncu captures: python tools/ncu_target.py c2 [variant] [reps] [B]"""
 import sys
 import torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
@@ -8,12 +8,13 @@ from ahkab_b200.circuit import Circuit
 from ahkab_b200.engine import Engine
 
 name = sys.argv[1] if len(sys.argv) > 1 else 'c2'
-G = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+G = int(sys.argv[2]) if len(sys.argv) > 2 else -1   # kernel variant id, -1 = heuristic
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-w = W.ALL[name]()
+B = int(sys.argv[4]) if len(sys.argv) > 4 else None
+w = W.ALL[name](B) if B else W.ALL[name]()
 circ = w.circuit(Circuit)
 e = Engine(circ, w.batch(), opts=w.opts)
-e.set_group(G)
+e.set_variant(real=G if name != 'c1' else -1, ac=G if name == 'c1' else -1)
 for _ in range(reps):
     if name == 'c2':
         r = e.op()
@@ -29,3 +30,5 @@ for _ in range(reps):
         r = e.dc_sweep('V1', common.c5_sweep())
 torch.cuda.synchronize()
 print('done', name, {k: tuple(v.shape) for k, v in r.items() if hasattr(v, 'shape')})
+if 'counters' in r:
+    print('rows', int(r['rows'].sum()), 'solves/nr/rej/cut', r['counters'].sum(0).tolist())
