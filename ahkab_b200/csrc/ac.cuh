@@ -15,10 +15,20 @@
 
 namespace ahk {
 
-struct cd { double re, im; };
+#ifdef __CUDACC__
+struct __align__(16) cd { double re, im; };
+#else
+struct alignas(16) cd { double re, im; };
+#endif
 AHK_DEV cd cmul(cd a, cd b) { return cd{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 AHK_DEV cd csub(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
 AHK_DEV cd cadd(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
+// reciprocal through the squared modulus: one division (pivots of circuit matrices are
+// far from the over/underflow range of |b|^2)
+AHK_DEV cd crecip(cd b) {
+  const double s = 1.0 / (b.re * b.re + b.im * b.im);
+  return cd{b.re * s, -b.im * s};
+}
 AHK_DEV cd cdivv(cd a, cd b) {   // Smith's algorithm (what C / numpy use)
   if (fabs(b.re) >= fabs(b.im)) {
     double r = b.im / b.re, den = b.re + b.im * r;
@@ -43,9 +53,10 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
   A.RS = NC > 0 ? NC : n + 1;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
-  A.Ac = take(2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
-  A.xc = take(2 * n); A.dxc = take(2 * n); A.Nac = take(2 * n);
-  A.pvc = take(NC > 0 ? 4 * NC : 0);
+  auto take2 = [&](int cnt) { off += off & 1; return take(cnt); };   // 16-byte aligned
+  A.Ac = take2(2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
+  A.xc = take2(2 * n); A.dxc = take2(2 * n); A.Nac = take2(2 * n);
+  A.pvc = take2(NC > 0 && G > 1 ? 4 * NC : 0);
   A.L.RS = A.RS;
   A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos);
   A.L.x = take(n);
@@ -53,11 +64,8 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
   A.L.bytes = take(16);
   A.L.Pv = take(h.nparams); A.L.dcon = take(H.ncon);
   A.L.buflen = 1;
-  if (G == 1) { if (off % 2 == 0) off++; }
-  else {
-    int want = (2 * G + 1) % 16;   // 16-byte elements: spread consecutive groups over banks
-    while (off % 16 != want) off++;
-  }
+  // complex elements are 16-byte aligned: even stride, 2 mod 4 to spread the groups
+  while (off % 4 != 2) off++;
   A.stride = off;
   A.L.stride = off;
   return A;
@@ -132,43 +140,48 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
 #pragma unroll
   for (int k = 0; k < NC - 1; k++) {
     if (k < n) {
-      double best = -1.0;
-      int bi = -1;
+      unsigned long long key = 0ull;
 #pragma unroll
       for (int s = 0; s < R; s++) {
         const int r = c.sub + G * s;
-        const double v = fabs(a[s][k].re) + fabs(a[s][k].im);
+        const unsigned long long kb = pivot_key(fabs(a[s][k].re) + fabs(a[s][k].im), r);
         const bool cand = r < n && !((usedm >> s) & 1u);
-        if (cand && (bi < 0 || v > best)) { best = v; bi = r; }
+        if (cand && kb > key) key = kb;
       }
-      Grp<G>::argmax(best, bi, c.mask);
-      if (best == 0.0) return 0;
+      key = Grp<G>::kmax(key, c.mask);
+      if ((key >> 5) == 0ull) return 0;
+      const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
       cd pv[NC > 0 ? NC : 1];
-#pragma unroll
-      for (int j = k; j < NC; j++) {
-        cd t = a[0][j];
-#pragma unroll
-        for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
-        pv[j] = t;
-      }
       if (G > 1) {
         cd* buf = pvb + (k & 1) * NC;
         if (mine) {
 #pragma unroll
-          for (int j = k; j < NC; j++) buf[j] = pv[j];
+          for (int s = 0; s < R; s++)
+            if (slot == s) {
+#pragma unroll
+              for (int j = k; j < NC; j++) buf[j] = a[s][j];
+            }
         }
         Grp<G>::sync(c.mask);
 #pragma unroll
         for (int j = k; j < NC; j++) pv[j] = buf[j];
+      } else {
+#pragma unroll
+        for (int j = k; j < NC; j++) {
+          cd t = a[0][j];
+#pragma unroll
+          for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
+          pv[j] = t;
+        }
       }
       if (mine) {
         usedm |= 1u << slot;
 #pragma unroll
         for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
       }
-      const cd inv = cdivv(cd{1.0, 0.0}, pv[k]);
+      const cd inv = crecip(pv[k]);
 #pragma unroll
       for (int s = 0; s < R; s++) {
         cd l = cmul(a[s][k], inv);

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p ../lib ../lib/obj
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${AHK_PTXAS_V:+-Xptxas -v}"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${AHK_PTXAS_V:+-Xptxas -v} ${AHK_DEFS}"
 pids=""
 for f in engine k_dc k_tran k_ac; do
   $NVCC $FLAGS -c -o ../lib/obj/$f.o $f.cu > ../lib/obj/$f.log 2>&1 &

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -258,6 +259,10 @@ int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int st
   }
   if (best_res < 0)
     return fail("circuit too large for the shared-memory engine (n = " + std::to_string(e->n) + ")");
+  if (getenv("AHK_DEBUG"))
+    fprintf(stderr, "[ahk] n=%d variant %d (NC=%d R=%d G=%d) stride %d doubles, %d thr/block, %d blocks, "
+            "%zu B smem/block, %lld instances resident/SM\n", e->n, vid, v.NC, v.R, v.G, stride, L.threads,
+            L.blocks, L.smem, best_res);
   return 0;
 }
 

@@ -66,7 +66,7 @@ template <int G>
 __device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
                                          int stride, const double* vary, long long B,
                                          long long units, long long& unit) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int gi = threadIdx.x / G;
   const int ipb = blockDim.x / G;
   unit = (long long)blockIdx.x * ipb + gi;

@@ -324,7 +324,8 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   L.Nc = take(n);
   L.Nd = h.ntd > 0 ? take(n) : L.Nc;      // N + Tt(t); no waveforms: N itself
   L.dout = take(h.ndout); L.dst = take(2 * h.ndev);
-  L.x1 = take(n); L.xs = take(n);
+  L.xs = take(n);
+  L.x1 = mode == MODE_TRAN ? L.xs : take(n);   // x1: pass-1 solution of the OP only
   L.bytes = take(NC > 0 ? 0 : 16);
   L.Pv = take(h.nparams); L.dcon = take(H.ncon);
   L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);

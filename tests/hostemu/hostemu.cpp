@@ -101,4 +101,38 @@ int emu_ac(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, co
   return 0;
 }
 
+// ---- single-device entry points (same device code the kernels inline) -------------------
+void emu_ekv_eval(const double* model8, int np, const double* dev4, double vd, double vg,
+                  double vs, double gmin, double* out4) {
+  EkvP m;
+  m.VTO = model8[0]; m.KP = model8[1]; m.GAMMA = model8[2]; m.PHI = model8[3]; m.COX = model8[4];
+  m.LAMBDA = model8[5]; m.XJ = model8[6]; m.UCRIT = model8[7];
+  m.W = dev4[0]; m.L = dev4[1]; m.M = dev4[2]; m.N = dev4[3]; m.NP = np;
+  double k[EK_NCONST];
+  ekv_setup(m, k);
+  ekv_eval(k, np, vd, vg, vs, gmin, out4);
+}
+double emu_ekv_q(double v) { return ekv_q(v); }
+void emu_mosq_eval(const double* model7, int np, const double* dev6, double vds, double vgs,
+                   double vbs, double iea, double gmin, double* out9) {
+  MosqP m;
+  m.VTO = model7[0]; m.KP = model7[1]; m.GAMMA = model7[2]; m.PHI = model7[3]; m.LAMBDA = model7[4];
+  m.AVT = model7[5]; m.AKP = model7[6];
+  m.W = dev6[0]; m.L = dev6[1]; m.M = dev6[2]; m.N = dev6[3]; m.ZVT = dev6[4]; m.ZKP = dev6[5];
+  m.NP = np;
+  mosq_eval(m, vds, vgs, vbs, iea, gmin, out9);
+}
+void emu_diode_eval(const double* model9, double area, double v, double vea, double gmin,
+                    double* last_vd, double* out2) {
+  DiodeP m;
+  m.IS = model9[0]; m.N = model9[1]; m.NBV = model9[2]; m.ISR = model9[3]; m.NR = model9[4];
+  m.RS = model9[5]; m.BV = model9[6]; m.IKF = model9[7]; m.VT = model9[8]; m.AREA = area;
+  diode_eval(m, v, vea, gmin, last_vd, out2);
+}
+void emu_switch_eval(const double* model4, double vout, double vin, double* is_on, double gmin,
+                     double* out3) {
+  SwP m; m.VT = model4[0]; m.VH = model4[1]; m.RON = model4[2]; m.ROFF = model4[3];
+  switch_eval(m, vout, vin, gmin, is_on, out3);
+}
+
 }  // extern "C"

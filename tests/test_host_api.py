@@ -1,0 +1,132 @@
+"""CPU: host-side mirror of the reference API — Circuit construction, the
+topology compiler (flatten), analysis descriptors, sweep iterators, source
+waveforms, x0 helpers and the results objects (fed with numpy stand-ins for
+the device tensors).  No GPU, no compute through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ahkab_b200 as ahkab
+import oracle
+from ahkab_b200 import compile as cp
+from ahkab_b200 import results, utilities, time_functions as TF
+from ahkab_b200 import workloads as W
+from ahkab_b200.circuit import Circuit
+
+
+def test_new_analysis_descriptors_keep_reference_signatures():
+    op = ahkab.new_op()
+    assert op == {'type': 'op', 'guess': True, 'x0': None, 'outfile': None, 'verbose': 0}
+    dc = ahkab.new_dc(1e3, 10e3, 10, 'V1')
+    assert dc['step'] == (10e3 - 1e3) / 9 and dc['sweep_type'] == 'LINEAR'   # ahkab.py:317
+    tr = ahkab.new_tran(0, 25e-9, .1e-9, method='TRAP', use_step_control=False)
+    assert tr['x0'] == 'op' and tr['tstep'] == .1e-9
+    ac = ahkab.new_ac(.97e3, 1.03e3, 1e2, x0=None)
+    assert ac['sweep_type'] == 'LOG' and ac['points'] == 1e2
+
+
+def test_sweep_iterators_are_cumulative_like_the_reference():
+    """utilities.py:246-378: products / sums, so f[99] = 1029.9999999999918, not 1030."""
+    # the AC sweep iterates over omega = 2 pi f and reports omega / 2 / pi (ac.py:283-309)
+    om = np.array(list(utilities.log_axis_iterator(2 * np.pi * .97e3, 2 * np.pi * 1.03e3, 1e2)))
+    f = om / np.pi / 2
+    assert f[0] == 970 and f[1] == 970.58823353488754 and f[99] == 1029.9999999999918
+    s = np.array(list(utilities.lin_axis_iterator(1e3, 10e3, 10)))
+    assert np.allclose(s, np.arange(1, 11) * 1e3, rtol=1e-15) and len(s) == 10
+
+
+def test_node_numbering_and_variable_names_follow_creation_order():
+    w = W.c4_ring3(2)
+    circ = w.circuit(Circuit)
+    # internal numbering by creation order: '3','1','2','4' 
+    assert [circ.nodes_dict[i] for i in range(1, 5)] == ['3', '1', '2', '4']
+    raw = dict(x=np.zeros((2, 5)), resid=np.zeros((2, 5)), iters=np.zeros(2, np.int32),
+               status=np.ones(2, np.int32))
+    sol = results.op_solution(circ, raw)
+    assert sol.keys() == ['V3', 'V1', 'V2', 'V4', 'I(V2)']
+    assert 'v1' in sol and sol['i(v2)'].shape == (2,)
+    c3 = W.c3_colpitts(2).circuit(Circuit)
+    names = results.tran_solution(c3, dict(t=np.zeros((2, 4)), x=np.zeros((2, 4, 9)),
+                                           rows=np.array([4, 2]), status=np.ones(2, np.int32)),
+                                  0, 1, 'TRAP').keys()
+    assert names == ['T', 'VDD', 'VND', 'VNS', 'VND1', 'VBIAS', 'I(VDD)', 'I(L1)', 'I(VTEST)',
+                     'I(VBIAS)']
+
+
+def test_tran_solution_masks_rows_beyond_the_accepted_count():
+    c3 = W.c3_colpitts(2).circuit(Circuit)
+    t = np.arange(8.).reshape(2, 4)
+    sol = results.tran_solution(c3, dict(t=t, x=np.ones((2, 4, 9)), rows=np.array([4, 2]),
+                                         status=np.ones(2, np.int32)), 0, 1, 'TRAP')
+    T = sol['T']
+    assert np.array_equal(T[0], t[0]) and np.isnan(T[1, 2:]).all() and not np.isnan(T[1, :2]).any()
+    assert sol.instance(1).shape == (10, 2)
+
+
+def test_flatten_builds_the_abi_tables():
+    w = W.c2_diode_op(8)
+    flat = cp.flatten(w.circuit(Circuit), w.batch())
+    assert flat.n == 3 and flat.n_nodes == 3 and flat.n_vde == 1 and flat.B == 8
+    assert flat.vary.shape == (3, 8) and len(flat.vary_slots) == 3
+    # slot-major vary rows hold the batch values of the overridden slots
+    nom = np.array(flat.nominal)
+    for k, slot in enumerate(flat.vary_slots):
+        assert flat.vary[k].shape == (8,) and np.isfinite(nom[slot])
+    types = [int(e['type']) for e in flat.elems]
+    assert types == [5, 1, 11]                       # AHK_V, AHK_R, AHK_D
+    # a V source without a waveform carries 3 slots, not 11
+    assert int(flat.elems[1]['pbase']) - int(flat.elems[0]['pbase']) == 3
+    # the OP-guess operator reproduces dc_guess.get_dc_guess: x0 = [1, 0.425, 0]
+    T = np.array([flat.guess_const[j] + (flat.guess_scale[j] * nom[flat.guess_slot[j]]
+                                         if flat.guess_slot[j] >= 0 else 0.0)
+                  for j in range(flat.n_guess)])
+    x0 = np.asarray(flat.guess_G).reshape(flat.n, flat.n_guess) @ T
+    assert np.allclose(x0, [1.0, 0.425, 0.0], atol=1e-12)
+
+
+def test_unknown_batch_owner_is_rejected():
+    w = W.c2_diode_op(4)
+    pb = w.batch()
+    pb.set('nosuch', 'value', np.ones(4))
+    with pytest.raises((KeyError, ValueError)):
+        cp.flatten(w.circuit(Circuit), pb)
+    with pytest.raises(ValueError):
+        ahkab.ParamBatch(4).set('r1', 'value', np.ones(5))
+
+
+def test_time_functions_match_the_device_encoding():
+    """host __call__ == the C evaluation of the encoded 8-slot block (same code the
+    kernels run, through the oracle's exported tf_eval)."""
+    L = oracle.lib()
+    fns = [TF.pulse(0., 1., 1e-9, 2e-9, 5e-9, 3e-9, 20e-9), TF.sin(0.5, 2., 1e8, 1e-9, 1e7, 30.),
+           TF.exp(0., 1., 1e-9, 2e-9, 8e-9, 3e-9), TF.sffm(0., 1., 1e8, 2., 1e7, 1e-9),
+           TF.am(1., 1e8, 1e7, 0.5, 1e-9)]
+    for fn in fns:
+        kind, prm = TF.encode(fn)
+        q = np.zeros(8)
+        q[:len(prm)] = prm
+        for t in np.linspace(0, 45e-9, 91):
+            c = L.ahko_tf_eval(C.c_int(kind), q.ctypes.data_as(C.POINTER(C.c_double)),
+                               C.c_double(float(t)))
+            assert abs(c - fn(float(t))) <= 1e-12 * max(1.0, abs(c)), (type(fn).__name__, t)
+
+
+def test_x0_helpers():
+    w = W.c4_ring3(3)
+    circ = w.circuit(Circuit)
+    x0 = ahkab.new_x0(circ, W.C4_IC)
+    assert x0.shape == (5,)
+    assert x0[circ.ext_node_to_int('2') - 1] == 2.5 and x0[circ.ext_node_to_int('1') - 1] == 0
+    c3 = W.c3_colpitts(2).circuit(Circuit)
+    xm = ahkab.icmodified_x0(c3, np.zeros((2, 9))).numpy()
+    assert np.allclose(xm[:, 1], 2.5) and np.allclose(xm[:, 6], -1e-9)   # c1 ic, l1 ic
+
+
+def test_running_an_analysis_without_a_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    w = W.c2_diode_op(4)
+    with pytest.raises(ahkab.EngineError):
+        ahkab.run(w.circuit(ahkab.Circuit), ahkab.new_op(), batch=w.batch())
