@@ -287,6 +287,16 @@ def measure_fp64_peak(eng, timer):
     return best
 
 
+def measured_traffic(name):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu
+    capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))[name]
+        return {"bytes": t["bytes"], "launch": t["launch"], "kernel": t["kernel"]}
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -423,7 +433,7 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
             "bound": "fp64", "achieved": flop / step_s / 1e12, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": flop / step_s / 1e12 / fp64_peak if fp64_peak else None,
             "peak_source": "measured in this run: DFMA probe kernel (ahk_probe_fp64), best of 5",
-            "algorithmic_flop_per_step": flop, "traffic": None,
+            "algorithmic_flop_per_step": flop, "traffic": measured_traffic(name),
             "hbm": {"bound": "hbm", "achieved": byts / step_s / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},
