@@ -34,6 +34,7 @@ struct BigK {
   double* wsLv; double* wsUv;  // [nwarps][2][cap]
   unsigned short* wsLi; unsigned short* wsUi;
   int cap, RS;
+  const int* list;             // null: all B instances; else list[0] = count, list[1..] = instances
 };
 
 struct BigSmem {   // offsets in bytes inside one warp's dynamic shared memory
@@ -75,7 +76,9 @@ __global__ void __launch_bounds__(32) k_biglin(const __grid_constant__ BigK k, c
   unsigned short* Li = k.wsLi + (size_t)blockIdx.x * 2 * k.cap;
   unsigned short* Ui = k.wsUi + (size_t)blockIdx.x * 2 * k.cap;
 
-  for (long long inst = blockIdx.x; inst < k.B; inst += gridDim.x) {
+  const long long count = k.list ? (long long)k.list[0] : k.B;
+  for (long long idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const long long inst = k.list ? (long long)k.list[1 + idx] : idx;
     auto P = [&](int slot) -> double {
       int v = p.slot_vary[slot];
       return v < 0 ? p.nominal[slot] : k.vary[(long long)v * k.B + inst];
@@ -243,13 +246,21 @@ __global__ void __launch_bounds__(32) k_biglin(const __grid_constant__ BigK k, c
 struct ahk_engine;
 // host driver state of the large-n path (owned by ahk_engine)
 struct BigLin {
+  // dense-workspace kernel (biglin.cuh): fallback for instances whose rows outgrow the
+  // shared-memory slots of the sparse kernel, and for n > 1024
   double* wsA = nullptr; double* wsLv = nullptr; double* wsUv = nullptr;
   unsigned short* wsLi = nullptr; unsigned short* wsUi = nullptr;
   double* d_sweep = nullptr; int sweep_cap = 0;
   int nwarps = 0, cap = 0;
+  // sparse shared-memory kernel (biglin2.cuh)
+  double* s2Lv = nullptr; double* s2Uv = nullptr; unsigned short* s2Li = nullptr; unsigned short* s2Ui = nullptr;
+  int* d_ovf = nullptr; long long ovf_cap = 0;
+  int nwarps2 = 0, cap2 = 0;
   void release() {
     cudaFree(wsA); cudaFree(wsLv); cudaFree(wsUv); cudaFree(wsLi); cudaFree(wsUi); cudaFree(d_sweep);
+    cudaFree(s2Lv); cudaFree(s2Uv); cudaFree(s2Li); cudaFree(s2Ui); cudaFree(d_ovf);
     wsA = wsLv = wsUv = nullptr; wsLi = wsUi = nullptr; d_sweep = nullptr; nwarps = 0;
+    s2Lv = s2Uv = nullptr; s2Li = s2Ui = nullptr; d_ovf = nullptr; nwarps2 = 0; ovf_cap = 0;
   }
   int run(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_host, int npts,
           double* x_out, int32_t* iters, int32_t* status, double* resid, cudaStream_t s,

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "biglin.cuh"
+#include "biglin2.cuh"
 #include "kernels.cuh"
 
 using namespace ahk;
@@ -83,23 +83,7 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
   } while (0)
   const Prog& h = e->H.hdr;
   const int n = h.n;
-  if (n > 60000) { err = "n too large"; return -1; }
-  const int RS = (n + 1) | 1;
-  BigSmem S = big_smem(n, h.npos);
-  if ((size_t)S.total > e->smem_max) { err = "circuit too large for the large-n path"; return -1; }
-  int per_sm = (int)std::min<size_t>(16, e->smem_max / (size_t)S.total);
-  int want = (int)std::min<long long>(batch->B, (long long)e->sm_count * per_sm);
-  const int capn = n * (n - 1) / 2 + n;
-  if (want > nwarps || capn != cap) {
-    CKB(cudaStreamSynchronize(s));
-    release();
-    nwarps = want; cap = capn;
-    CKB(cudaMalloc(&wsA, (size_t)nwarps * n * RS * sizeof(double)));
-    CKB(cudaMalloc(&wsLv, (size_t)nwarps * 2 * cap * sizeof(double)));
-    CKB(cudaMalloc(&wsUv, (size_t)nwarps * 2 * cap * sizeof(double)));
-    CKB(cudaMalloc(&wsLi, (size_t)nwarps * 2 * cap * sizeof(unsigned short)));
-    CKB(cudaMalloc(&wsUi, (size_t)nwarps * 2 * cap * sizeof(unsigned short)));
-  }
+  if (n >= 32768) { err = "n too large"; return -1; }
   if (npts > sweep_cap) {
     CKB(cudaStreamSynchronize(s));
     cudaFree(d_sweep);
@@ -107,12 +91,80 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
     CKB(cudaMalloc(&d_sweep, sweep_cap * sizeof(double)));
   }
   CKB(cudaMemcpyAsync(d_sweep, sweep_host, npts * sizeof(double), cudaMemcpyHostToDevice, s));
+
+  // ---- 1. sparse shared-memory kernel (n <= 1024) ----------------------------------------
+  const int W = (n + 31) / 32;
+  bool sparse = W <= 32 && !getenv("AHK_BIGLIN_DENSE");
+  int SC = 0, PC = 0;
+  Big2Smem S2;
+  if (sparse) {
+    // slots per row / points per solve chunk: as large as still lets 4 warps share an SM
+    const size_t budget = (228 * 1024) / 4 - 1024;
+    int maxrow = 0;
+    for (int r = 0; r < n; r++) maxrow = std::max(maxrow, e->H.row_ptr[r + 1] - e->H.row_ptr[r]);
+    PC = std::min(npts, 16);
+    SC = 12;
+    while (PC > 1 && (size_t)big2_smem(n, h.npos, SC, PC, W).total > budget) PC--;
+    while (SC > 6 && (size_t)big2_smem(n, h.npos, SC, PC, W).total > budget) SC--;
+    while (SC < 32 && SC < maxrow + 4 && (size_t)big2_smem(n, h.npos, SC + 1, PC, W).total <= budget) SC++;
+    if (const char* f = getenv("AHK_BIGLIN_SC")) SC = std::max(maxrow, atoi(f));   // tests: force overflows
+    S2 = big2_smem(n, h.npos, SC, PC, W);
+    if ((size_t)S2.total > e->smem_max || maxrow > SC) sparse = false;
+  }
+  if (sparse) {
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / ((size_t)S2.total + 1024)));
+    int want = (int)std::min<long long>(batch->B, (long long)e->sm_count * per_sm);
+    const int cap2n = n * (SC + 2);
+    if (want > nwarps2 || cap2n != cap2 || batch->B + 1 > ovf_cap) {
+      CKB(cudaStreamSynchronize(s));
+      cudaFree(s2Lv); cudaFree(s2Uv); cudaFree(s2Li); cudaFree(s2Ui); cudaFree(d_ovf);
+      nwarps2 = want; cap2 = cap2n; ovf_cap = batch->B + 1;
+      CKB(cudaMalloc(&s2Lv, (size_t)nwarps2 * 2 * cap2 * sizeof(double)));
+      CKB(cudaMalloc(&s2Uv, (size_t)nwarps2 * 2 * cap2 * sizeof(double)));
+      CKB(cudaMalloc(&s2Li, (size_t)nwarps2 * 2 * cap2 * sizeof(unsigned short)));
+      CKB(cudaMalloc(&s2Ui, (size_t)nwarps2 * 2 * cap2 * sizeof(unsigned short)));
+      CKB(cudaMalloc(&d_ovf, (size_t)ovf_cap * sizeof(int)));
+    }
+    CKB(cudaMemsetAsync(d_ovf, 0, sizeof(int), s));
+    Big2K k2;
+    k2.p = e->dprog; k2.o = e->o; k2.vary = batch->vary; k2.B = batch->B;
+    k2.src_elem = src_elem; k2.sweep = d_sweep; k2.npts = npts; k2.x0 = nullptr;
+    k2.x_out = x_out; k2.iters = iters; k2.status = status; k2.resid = resid;
+    k2.Lv = s2Lv; k2.Uv = s2Uv; k2.Li = s2Li; k2.Ui = s2Ui;
+    k2.cap2 = cap2; k2.SC = SC; k2.PC = PC; k2.W = W; k2.ovf = d_ovf;
+    if (S2.total > 48 * 1024)
+      CKB(cudaFuncSetAttribute(k_biglin2, cudaFuncAttributeMaxDynamicSharedMemorySize, S2.total));
+    if (getenv("AHK_DEBUG"))
+      fprintf(stderr, "[ahk] biglin2 n=%d SC=%d PC=%d smem %d B/warp, %d warps (%d per SM)\n", n, SC, PC,
+              S2.total, want, per_sm);
+    k_biglin2<<<want, 32, S2.total, s>>>(k2, S2);
+    CKB(cudaGetLastError());
+    launches++;
+  }
+
+  // ---- 2. dense-workspace kernel: everything (no sparse pass) or the overflow list ------------
+  const int RS = (n + 1) | 1;
+  BigSmem S = big_smem(n, h.npos);
+  if ((size_t)S.total > e->smem_max) { err = "circuit too large for the large-n path"; return -1; }
+  int per_sm = (int)std::min<size_t>(16, e->smem_max / (size_t)S.total);
+  int want = (int)std::min<long long>(batch->B, (long long)e->sm_count * (sparse ? 1 : per_sm));
+  const int capn = n * (n - 1) / 2 + n;
+  if (want > nwarps || capn != cap) {
+    CKB(cudaStreamSynchronize(s));
+    cudaFree(wsA); cudaFree(wsLv); cudaFree(wsUv); cudaFree(wsLi); cudaFree(wsUi);
+    nwarps = want; cap = capn;
+    CKB(cudaMalloc(&wsA, (size_t)nwarps * n * RS * sizeof(double)));
+    CKB(cudaMalloc(&wsLv, (size_t)nwarps * 2 * cap * sizeof(double)));
+    CKB(cudaMalloc(&wsUv, (size_t)nwarps * 2 * cap * sizeof(double)));
+    CKB(cudaMalloc(&wsLi, (size_t)nwarps * 2 * cap * sizeof(unsigned short)));
+    CKB(cudaMalloc(&wsUi, (size_t)nwarps * 2 * cap * sizeof(unsigned short)));
+  }
   BigK k;
   k.p = e->dprog; k.o = e->o; k.vary = batch->vary; k.B = batch->B;
   k.src_elem = src_elem; k.sweep = d_sweep; k.npts = npts; k.x0 = nullptr;
   k.x_out = x_out; k.iters = iters; k.status = status; k.resid = resid;
   k.wsA = wsA; k.wsLv = wsLv; k.wsUv = wsUv; k.wsLi = wsLi; k.wsUi = wsUi;
-  k.cap = cap; k.RS = RS;
+  k.cap = cap; k.RS = RS; k.list = sparse ? d_ovf : nullptr;
   if (S.total > 48 * 1024)
     CKB(cudaFuncSetAttribute(k_biglin, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
   k_biglin<<<want, 32, S.total, s>>>(k, S);

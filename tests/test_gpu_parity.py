@@ -210,3 +210,28 @@ def test_run_api_matches_engine():
         ahkab.options.vea, ahkab.options.iea = 1e-6, 1e-9
     assert (res['tran'].rows == 250).all()
     assert res['tran'].keys()[:3] == ['T', 'VDD', 'VND']
+
+
+def test_c5_big_linear_paths_agree(monkeypatch):
+    """n = 257: the sparse shared-memory kernel, the dense-workspace kernel, and the
+    overflow hand-over between them (slot capacity forced down) give the same sweep."""
+    w = W.c5_r2r(96)
+    sw = common.c5_sweep()
+    o = _oracle(w).dc_sweep(0, sw)
+    scale = np.abs(o['x']).max()
+    outs = {}
+    for tag, env in (('sparse', {}), ('dense', {'AHK_BIGLIN_DENSE': '1'}),
+                     ('overflow', {'AHK_BIGLIN_SC': '3'})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        e = _engine(w)
+        r = e.dc_sweep('V1', sw)
+        x = _np(r['x'])
+        assert (_np(r['status']) == 1).all() and (_np(r['iters']) == 2).all(), tag
+        assert np.abs(x - o['x']).max() / scale < 1e-13, tag
+        outs[tag] = x
+        rop = e.op()
+        assert np.abs(_np(rop['x']) - _oracle(w).op()['x']).max() / scale < 1e-13, tag
+        for k_ in env:
+            monkeypatch.delenv(k_)
+    assert np.abs(outs['sparse'] - outs['dense']).max() / scale < 1e-14
