@@ -63,7 +63,8 @@ METHODS = {'IMPLICIT_EULER': 0, 'TRAP': 1, 'GEAR1': 11, 'GEAR2': 12,
 EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_group', 'ahk_last_error', 'ahk_launch_count', 'ahk_op',
            'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64',
-           'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info')
+           'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info',
+           'ahk_h2d_columns')
 
 
 def _dp(a):
@@ -158,6 +159,8 @@ def load_library(path=None):
     lib.ahk_variant_count.restype = C.c_int
     lib.ahk_variant_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
     lib.ahk_variant_info.restype = C.c_int
+    lib.ahk_h2d_columns.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp]
+    lib.ahk_h2d_columns.restype = C.c_int
     lib.ahk_probe_fp64.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     lib.ahk_probe_fp64.restype = C.c_int
     if path == LIB_PATH:

@@ -419,6 +419,16 @@ int ahk_set_variant(ahk_engine* e, int real_id, int ac_id) {
   return 0;
 }
 
+int ahk_h2d_columns(double* dst, const double* src_host, int n_rows, int64_t row_len, int64_t lo,
+                    int64_t hi, void* stream) {
+  if (!dst || !src_host || n_rows < 0 || lo < 0 || hi < lo || hi > row_len) return fail("ahk_h2d_columns: bad argument");
+  if (n_rows == 0 || hi == lo) return 0;
+  CK(cudaMemcpy2DAsync(dst, (size_t)(hi - lo) * sizeof(double), src_host + lo, (size_t)row_len * sizeof(double),
+                       (size_t)(hi - lo) * sizeof(double), (size_t)n_rows, cudaMemcpyHostToDevice,
+                       (cudaStream_t)stream));
+  return 0;
+}
+
 int ahk_probe_fp64(int blocks, int threads, int iters, double* out, void* stream) {
   if (blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0 || !out)
     return fail("ahk_probe_fp64: bad argument");

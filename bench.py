@@ -52,6 +52,11 @@ FULL_B = dict(c1=4096, c2=65536, c3=16384, c4=16384, c5=4096)
 # bounded samples for the CPU arm (instances), sized for a few seconds per step
 CPU_SAMPLE = dict(c1=4096, c2=65536, c3=2048, c4=256, c5=64)
 C4_MAX_ROWS = 3072
+# chunks of the pipelined end-to-end step (copy-in / compute / copy-out overlap)
+# Only throughput-bound kernels gain: a latency-bound kernel that fits the machine in one
+# or two waves takes as long for a quarter of the batch as for all of it (measured: C3
+# 28 -> 44 ms, C4 262 -> 679 ms with 4 / 8 chunks), so those run as one chunk.
+E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=4)
 
 
 def LU(n):
@@ -86,6 +91,7 @@ class Runner(object):
         self.circ = self.w.circuit(Circuit)
         self.eng = Engine(self.circ, self.w.batch(), opts=self.w.opts)
         self.B = B
+        self.pipe = None
         self.vary_host = torch.empty(self.eng.vary.shape, dtype=torch.float64,
                                      pin_memory=True)
         self.vary_host.copy_(self.eng.vary)
@@ -100,8 +106,9 @@ class Runner(object):
             self.x0 = self.x0_host.cuda()
             self.h2d += self.x0_host.numel() * 8
 
-    def step(self):
-        e, W, n = self.eng, self.W, self.name
+    def step(self, e=None, x0=None):
+        e = e or self.eng
+        W, n = self.W, self.name
         if n == 'c2':
             return e.op()
         if n == 'c1':
@@ -115,18 +122,27 @@ class Runner(object):
             r['op_iters'] = op['iters']
             return r
         if n == 'c4':
-            return e.tran(self.x0, max_rows=C4_MAX_ROWS, **W.C4_TRAN)
+            return e.tran(self.x0 if x0 is None else x0, max_rows=C4_MAX_ROWS, **W.C4_TRAN)
         if n == 'c5':
             return e.dc_sweep('V1', self.sw)
 
     def e2e(self):
-        """host params -> device, analysis, every result tensor -> pinned host."""
-        self.eng.set_vary(self.vary_host)
-        if self.name == 'c4':
-            self.x0.copy_(self.x0_host, non_blocking=True)
-        raw = self.step()
-        host = self.eng.to_host(raw)
-        return raw, host
+        """host params -> device, analysis, every result tensor -> pinned host, cut into
+        chunks and pipelined over three streams (ahkab_b200/pipeline.py): the H2D of the
+        next chunk and the D2H of the previous one overlap the kernels."""
+        if E2E_CHUNKS[self.name] == 1:
+            self.eng.set_vary(self.vary_host)
+            if self.name == 'c4':
+                self.x0.copy_(self.x0_host, non_blocking=True)
+            raw = self.step()
+            return raw, self.eng.to_host(raw)
+        if self.pipe is None:
+            from ahkab_b200.pipeline import Pipeline
+            self.pipe = Pipeline(self.eng, nchunks=E2E_CHUNKS[self.name])
+        extra = {'x0': self.x0_host} if self.name == 'c4' else None
+        host = self.pipe.run(lambda sub, lo, hi, x: self.step(sub, x.get('x0')),
+                             self.vary_host, extra)
+        return host, host
 
     def d2h_bytes(self, host):
         return int(sum(v.numel() * v.element_size() for v in host.values()))
@@ -139,7 +155,7 @@ class Runner(object):
             return self.B * len(self.om)
         if n == 'c5':
             return self.B * len(self.sw)
-        return int(raw['rows'].sum().item())
+        return int(raw['rows'].sum().item())   # device tensor or pinned host tensor
 
     def algo(self, raw):
         """(flop, bytes) one step needs algorithmically."""
@@ -408,7 +424,8 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
 
         def e2e_fn():
             rr, hh = r.e2e()
-            ahk_dist.gather_rows(rr['status'].reshape(r.B, -1), r.B * world)
+            st = rr['status'] if rr['status'].is_cuda else rr['status'].to(device, non_blocking=True)
+            ahk_dist.gather_rows(st.reshape(r.B, -1), r.B * world)
             return rr, hh
     ms_e, (raw_e, host) = timer.timed(e2e_fn, steps, warmup)
     units_e = all_sum(r.units(raw_e), dist_on, device)
@@ -427,13 +444,16 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
                    "parallelism": "batch sharded, %d rank(s), no data-path collective" % world,
                    "status_ok_rank0": ok},
         "e2e": {"value": e2e_value, "unit": UNITS[name], "ms_per_step": ms_e / steps,
+                "chunks": E2E_CHUNKS[name],
                 "h2d_bytes_per_step": r.h2d, "d2h_bytes_per_step": r.d2h_bytes(host)},
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "fp64", "achieved": flop / step_s / 1e12, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": flop / step_s / 1e12 / fp64_peak if fp64_peak else None,
             "peak_source": "measured in this run: DFMA probe kernel (ahk_probe_fp64), best of 5",
-            "algorithmic_flop_per_step": flop, "traffic": measured_traffic(name),
+            "algorithmic_flop_per_step": flop,
+            "traffic": (measured_traffic(name) or {}).get("bytes"),
+            "traffic_source": measured_traffic(name),
             "hbm": {"bound": "hbm", "achieved": byts / step_s / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},

@@ -184,6 +184,13 @@ const char* ahk_last_error(void);
 /* Number of kernel launches issued by this library so far (all engines). */
 int64_t ahk_launch_count(void);
 
+/* Plumbing for chunked (pipelined) end-to-end runs: copies columns [lo, hi) of the
+ * slot-major host array src_host[n_rows][row_len] (pinned memory for the copy to be
+ * asynchronous) into the contiguous device array dst[n_rows][hi - lo] — the `vary`
+ * layout of a sub-batch — with one strided asynchronous copy on `stream`. */
+int ahk_h2d_columns(double* dst, const double* src_host, int n_rows,
+                    int64_t row_len, int64_t lo, int64_t hi, void* stream);
+
 /* Diagnostics (no reference counterpart): launches an FP64-FMA-only kernel,
  * blocks x threads (<= 256) threads each running 8 independent chains of
  * `iters` DFMAs = blocks*threads*iters*16 flop.  bench.py times it with CUDA
