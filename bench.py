@@ -324,6 +324,15 @@ def peaks():
 
 
 # ---- CPU arm: the oracle (C restatement of the reference), OpenMP ---------------------
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which
+    would silently turn the all-cores CPU arm into a 1-core run)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_step_fn(name, B):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle
@@ -334,27 +343,28 @@ def cpu_step_fn(name, B):
     w = W.ALL[name](B=B, seed=seeds[name])
     circ = w.circuit(Circuit)
     o = oracle.Oracle(circ, w.batch(), opts=w.opts)
+    NT = host_threads()
     if name == 'c2':
-        return (lambda: B), (lambda: o.op()), oracle.max_threads()
+        return (lambda: B), (lambda: o.op(threads=NT)), NT
     if name == 'c1':
         om = common.c1_omegas()
-        return (lambda: B * len(om)), (lambda: o.ac(om)), oracle.max_threads()
+        return (lambda: B * len(om)), (lambda: o.ac(om, threads=NT)), NT
     if name == 'c5':
         sw = common.c5_sweep()
-        return (lambda: B * len(sw)), (lambda: o.dc_sweep(0, sw)), oracle.max_threads()
+        return (lambda: B * len(sw)), (lambda: o.dc_sweep(0, sw, threads=NT)), NT
     box = {}
     if name == 'c3':
         def f():
-            x0 = common.c3_x0(o.op()['x'])
+            x0 = common.c3_x0(o.op(threads=NT)['x'])
             box['r'] = o.tran(x0, 0., W.C3_TRAN['tstep'], W.C3_TRAN['tstop'], 'TRAP',
-                              False, 256)
+                              False, 256, threads=NT)
     else:
         x0 = common.c4_x0(circ, B)
 
         def f():
             box['r'] = o.tran(x0, 0., W.C4_TRAN['tstep'], W.C4_TRAN['tstop'], 'GEAR2',
-                              True, C4_MAX_ROWS)
-    return (lambda: int(box['r']['rows'].sum())), f, oracle.max_threads()
+                              True, C4_MAX_ROWS, threads=NT)
+    return (lambda: int(box['r']['rows'].sum())), f, NT
 
 
 def cpu_measure(name, steps, warmup):
@@ -492,6 +502,8 @@ def main():
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=device)
     warmup = max(3, args.warmup)
     timer = Timer(dist_on, device)
@@ -503,17 +515,17 @@ def main():
     del probe
     head = bench_one(args.workload, rank, world, timer, sampler, args.steps, warmup, hbm_peak,
                      hbm_src, fp64_peak, dist_on, device, not args.no_cpu)
-    head["clocks"] = sampler.summary()
     cfgs = {}
     if not args.only:
         for name in ('c1', 'c3', 'c4', 'c5', 'c2'):
             if name == args.workload:
                 continue
             heavy = name in ('c3', 'c4', 'c5')
-            cfgs[name] = bench_one(name, rank, world, timer, None,
+            cfgs[name] = bench_one(name, rank, world, timer, sampler,
                                    min(args.steps, 3 if heavy else 10), 3, hbm_peak, hbm_src,
                                    fp64_peak, dist_on, device, not args.no_cpu)
         head["configs"] = cfgs
+    head["clocks"] = sampler.summary()     # sampled during every timed region of this run
     sampler.stop.set()
     head["gpu"] = torch.cuda.get_device_name(local)
     if dist_on:
