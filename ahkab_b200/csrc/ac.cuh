@@ -60,9 +60,9 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
   A.L.RS = A.RS;
   A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos);
   A.L.x = take(n);
-  A.L.dout = take(h.ndout); A.L.dst = take(2 * h.ndev);
+  A.L.dout = take(h.ndout); A.L.dst = take(H.nst);
   A.L.bytes = take(16);
-  A.L.Pv = take(h.nparams); A.L.dcon = take(H.ncon);
+  A.L.Pv = take(h.npersist); A.L.dcon = take(H.ncon);
   A.L.buflen = 1;
   // complex elements are 16-byte aligned: even stride, 2 mod 4 to spread the groups
   while (off % 4 != 2) off++;
@@ -238,7 +238,7 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     for (int k = 0; k < p.nsrc; k++) {
       const SrcOp& s = p.src[k];
       if (!s.has_ac) continue;
-      double mag = c.P(s.pbase + 1), ph = c.P(s.pbase + 2);
+      double mag = c.PP(s.ppb + 1), ph = c.PP(s.ppb + 2);
       cd v = {mag * cos(ph), mag * sin(ph)};
       if (s.is_v) Nac[s.row0] = cd{-1.0 * v.re, -1.0 * v.im};
       else {

@@ -94,9 +94,10 @@ struct Ctx {
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
   double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
 
-  // per-instance parameter value: staged copy in shared memory
-  AHK_MEM double P(int slot) const { return sm[L->Pv + slot]; }
-  AHK_MEM double Pglobal(int slot) const {
+  // persistent parameter (staged in shared memory; index = SrcOp/DevOp ppb/pmb + k)
+  AHK_MEM double PP(int pslot) const { return sm[L->Pv + pslot]; }
+  // any parameter, straight from HBM (set-up only)
+  AHK_MEM double P(int slot) const {
     int v = p->slot_vary[slot];
     return v < 0 ? p->nominal[slot] : vary[(long long)v * B + inst];
   }
@@ -130,7 +131,7 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   const Prog& p = *c.p;
   const int G = V::G;
   double* Pv = c.sm + c.L->Pv;
-  for (int s = c.sub; s < p.nparams; s += G) Pv[s] = c.Pglobal(s);
+  for (int s = c.sub; s < p.npersist; s += G) Pv[s] = c.P(p.pstage[s]);
   if (V::NC > 0) {   // the dense staging matrix is zeroed once: only the sparsity
     double* A = c.A();   // pattern (and the rhs column) is rewritten per iteration
     for (int i = c.sub; i < p.n * c.L->RS; i += G) A[i] = 0.0;
@@ -167,9 +168,19 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   double* dcon = c.sm + c.L->dcon;
   for (int d = c.sub; d < p.ndev; d += G) {
     const DevOp& dv = p.dev[d];
-    st[2 * d] = st[2 * d + 1] = 0.0;
-    if (dv.type == AHK_D) st[2 * d] = .425;
-    if (dv.type == AHK_SW) st[2 * d] = c.P(dv.pbase);
+    if (dv.st >= 0) {
+      st[dv.st] = st[dv.st + 1] = 0.0;
+      if (dv.type == AHK_D) st[dv.st] = .425;
+      if (dv.type == AHK_SW) st[dv.st] = c.PP(dv.ppb);
+    }
+    if (dv.type == AHK_D) {
+      DiodeP m;
+      m.IS = c.P(dv.mbase + 0); m.N = c.P(dv.mbase + 1); m.NBV = c.P(dv.mbase + 2);
+      m.ISR = c.P(dv.mbase + 3); m.NR = c.P(dv.mbase + 4); m.RS = c.P(dv.mbase + 5);
+      m.BV = c.P(dv.mbase + 6); m.IKF = c.P(dv.mbase + 7); m.VT = c.P(dv.mbase + 8);
+      m.AREA = c.P(dv.pbase);
+      diode_setup(m, dcon + dv.con);
+    }
     if (dv.type == AHK_EKV) {
       EkvP m;
       m.VTO = c.P(dv.mbase + 0); m.KP = c.P(dv.mbase + 1); m.GAMMA = c.P(dv.mbase + 2);
@@ -192,7 +203,7 @@ AHK_DEV void build_N(Ctx& c) {
     for (int k = 0; k < p.nsrc; k++) {
       const SrcOp& s = p.src[k];
       if (s.tf) continue;
-      double v = (s.elem == c.dc_src) ? c.dc_val : c.P(s.pbase);
+      double v = (s.elem == c.dc_src) ? c.dc_val : c.PP(s.ppb);
       if (s.is_v) Nc[s.row0] = -1.0 * v;
       else { if (s.row0 >= 0) Nc[s.row0] += v; if (s.row1 >= 0) Nc[s.row1] -= v; }
     }
@@ -210,16 +221,12 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
     const DevOp& dv = p.dev[d];
     if (!dv.active) continue;
     double* out = dout + dv.dout;
-    double* st = dst + 2 * d;
+    double* st = dst + (dv.st >= 0 ? dv.st : 0);
     switch (dv.type) {
-      case AHK_D: {
-        DiodeP m;
-        m.IS = c.P(dv.mbase + 0); m.N = c.P(dv.mbase + 1); m.NBV = c.P(dv.mbase + 2);
-        m.ISR = c.P(dv.mbase + 3); m.NR = c.P(dv.mbase + 4); m.RS = c.P(dv.mbase + 5);
-        m.BV = c.P(dv.mbase + 6); m.IKF = c.P(dv.mbase + 7); m.VT = c.P(dv.mbase + 8);
-        m.AREA = c.P(dv.pbase);
-        diode_eval(m, V_of(x, dv.node[0]) - V_of(x, dv.node[1]), o.vea, o.gmin, st, out);
-      } break;
+      case AHK_D:
+        diode_eval(c.sm + c.L->dcon + dv.con, V_of(x, dv.node[0]) - V_of(x, dv.node[1]), o.vea,
+                   o.gmin, st, out);
+        break;
       case AHK_EKV: {
         double vb = V_of(x, dv.node[3]);
         ekv_eval(c.sm + c.L->dcon + dv.con, dv.flags, V_of(x, dv.node[0]) - vb,
@@ -227,11 +234,11 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
       } break;
       case AHK_MOSQ: {
         MosqP m;
-        m.VTO = c.P(dv.mbase + 0); m.KP = c.P(dv.mbase + 1); m.GAMMA = c.P(dv.mbase + 2);
-        m.PHI = c.P(dv.mbase + 3); m.LAMBDA = c.P(dv.mbase + 4); m.AVT = c.P(dv.mbase + 5);
-        m.AKP = c.P(dv.mbase + 6);
-        m.W = c.P(dv.pbase + 0); m.L = c.P(dv.pbase + 1); m.M = c.P(dv.pbase + 2);
-        m.N = c.P(dv.pbase + 3); m.ZVT = c.P(dv.pbase + 4); m.ZKP = c.P(dv.pbase + 5);
+        m.VTO = c.PP(dv.pmb + 0); m.KP = c.PP(dv.pmb + 1); m.GAMMA = c.PP(dv.pmb + 2);
+        m.PHI = c.PP(dv.pmb + 3); m.LAMBDA = c.PP(dv.pmb + 4); m.AVT = c.PP(dv.pmb + 5);
+        m.AKP = c.PP(dv.pmb + 6);
+        m.W = c.PP(dv.ppb + 0); m.L = c.PP(dv.ppb + 1); m.M = c.PP(dv.ppb + 2);
+        m.N = c.PP(dv.ppb + 3); m.ZVT = c.PP(dv.ppb + 4); m.ZKP = c.PP(dv.ppb + 5);
         m.NP = dv.flags;
         double vs = V_of(x, dv.node[2]);
         mosq_eval(m, V_of(x, dv.node[0]) - vs, V_of(x, dv.node[1]) - vs,
@@ -239,8 +246,8 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
       } break;
       case AHK_SW: {
         SwP m;
-        m.VT = c.P(dv.mbase + 0); m.VH = c.P(dv.mbase + 1); m.RON = c.P(dv.mbase + 2);
-        m.ROFF = c.P(dv.mbase + 3);
+        m.VT = c.PP(dv.pmb + 0); m.VH = c.PP(dv.pmb + 1); m.RON = c.PP(dv.pmb + 2);
+        m.ROFF = c.PP(dv.pmb + 3);
         switch_eval(m, V_of(x, dv.node[0]) - V_of(x, dv.node[1]),
                     V_of(x, dv.node[2]) - V_of(x, dv.node[3]), o.gmin, st, out);
       } break;
@@ -520,7 +527,7 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
         const SrcOp& s = p.src[k];
         if (!s.tf) continue;
         double q[8];
-        for (int j = 0; j < 8; j++) q[j] = c.P(s.pbase + 3 + j);
+        for (int j = 0; j < 8; j++) q[j] = c.PP(s.ppb + 3 + j);
         double v = tf_eval(s.tf, q, time);
         if (s.is_v) Nd[s.row0] += -1 * v;
         else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
@@ -587,7 +594,7 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
       if (use_guess && p.nguess > 0) {   // dc_guess.py via the precomputed operator
         for (int j = 0; j < p.nguess; j++) {
           double T = p.gconst[j];
-          if (p.gslot[j] >= 0) T += p.gscale[j] * c.P(p.gslot[j]);
+          if (p.gpslot[j] >= 0) T += p.gscale[j] * c.PP(p.gpslot[j]);
           s += p.guessG[i * p.nguess + j] * T;
         }
       }

@@ -33,48 +33,67 @@ AHK_DEV double safe_exp(double x) { return x < 70 ? exp(x) : exp(70.0) + 10 * x;
 
 struct DiodeP { double IS, N, NBV, ISR, NR, RS, BV, IKF, VT, AREA; };
 
-AHK_DEV double diode_i_raw(const DiodeP& m, double v) {  // diode.py:387-395
-  double i_fwd = m.IS * (safe_exp(v / (m.N * m.VT)) - 1);
-  double i_rec = m.ISR != 0.0 ? m.ISR * (safe_exp(v / (m.NR * m.VT)) - 1) : 0.0;
-  double i_rev = -m.IS * (safe_exp(-(v + m.BV) / (m.NBV * m.VT)) - 1);
+// Per-instance constants of one diode: the reciprocals of the thermal-voltage products are
+// taken once when the instance is loaded (the reference divides at every evaluation).
+enum { DK_IS, DK_INVT, DK_INBVVT, DK_IVT, DK_ISR, DK_INRVT, DK_RS, DK_BV, DK_IKF, DK_AREA, DK_NCONST };
+
+AHK_DEV void diode_setup(const DiodeP& m, double* k) {
+  k[DK_IS] = m.IS; k[DK_INVT] = 1.0 / (m.N * m.VT); k[DK_INBVVT] = 1.0 / (m.NBV * m.VT);
+  k[DK_IVT] = 1.0 / m.VT; k[DK_ISR] = m.ISR; k[DK_INRVT] = 1.0 / (m.NR * m.VT);
+  k[DK_RS] = m.RS; k[DK_BV] = m.BV; k[DK_IKF] = m.IKF; k[DK_AREA] = m.AREA;
+}
+
+// diode.py:387-395.  BV = inf (the default): exp(-inf) = 0 exactly, no call needed.
+AHK_DEV double diode_i_raw(const double* k, double v, double efwd) {
+  const double IS = k[DK_IS];
+  double i_fwd = IS * (efwd - 1);
+  double i_rec = k[DK_ISR] != 0.0 ? k[DK_ISR] * (safe_exp(v * k[DK_INRVT]) - 1) : 0.0;
+  double erev = isinf(k[DK_BV]) ? (k[DK_BV] > 0 ? 0.0 : safe_exp(INFINITY)) : safe_exp(-(v + k[DK_BV]) * k[DK_INBVVT]);
+  double i_rev = -IS * (erev - 1);
   double k_inj = 1;
-  if (!isinf(m.IKF) && m.IKF > 0 && i_fwd > 0) k_inj = sqrt(m.IKF / (m.IKF + i_fwd));
+  const double IKF = k[DK_IKF];
+  if (!isinf(IKF) && IKF > 0 && i_fwd > 0) k_inj = sqrt(IKF / (IKF + i_fwd));
   return k_inj * i_fwd + i_rec + i_rev;
 }
 
-AHK_DEV double diode_gm_raw(const DiodeP& m, double v) {  // diode.py:402-406 (not d i/dv)
-  double g = m.IS / (m.N * m.VT) * safe_exp(v / (m.N * m.VT)) +
-             -m.IS / m.VT * (safe_exp(-(v + m.BV) / m.VT));
-  if (m.ISR != 0.0) g += m.ISR / (m.NR * m.VT) * safe_exp(v / (m.NR * m.VT));
+// diode.py:402-406 (not d i/dv: no NBV, sign of the breakdown term, no k_inj)
+AHK_DEV double diode_gm_raw(const double* k, double v, double efwd) {
+  const double IS = k[DK_IS];
+  double erev = isinf(k[DK_BV]) ? (k[DK_BV] > 0 ? 0.0 : safe_exp(INFINITY)) : safe_exp(-(v + k[DK_BV]) * k[DK_IVT]);
+  double g = IS * k[DK_INVT] * efwd + -IS * k[DK_IVT] * erev;
+  if (k[DK_ISR] != 0.0) g += k[DK_ISR] * k[DK_INRVT] * safe_exp(v * k[DK_INRVT]);
   return g;
 }
 
 // out[0] = i, out[1] = gm (with the gm==0 -> 2*gmin rule of diode.py:178-179);
 // *last_vd is the device state used by the RS != 0 inner Newton (diode.py:359-365).
-AHK_DEV void diode_eval(const DiodeP& m, double v, double vea, double gmin,
+AHK_DEV void diode_eval(const double* k, double v, double vea, double gmin,
                         double* last_vd, double* out) {
-  double gm = diode_gm_raw(m, v);
-  if (m.RS != 0.0) gm = 1. / (m.RS + 1. / (gm + 1e-3 * gmin));
-  gm *= m.AREA;
+  const double RS = k[DK_RS], AREA = k[DK_AREA];
+  const double efwd = safe_exp(v * k[DK_INVT]);     // shared by the current and the conductance
+  double gm = diode_gm_raw(k, v, efwd);
+  if (RS != 0.0) gm = 1. / (RS + 1. / (gm + 1e-3 * gmin));
+  gm *= AREA;
   if (gm == 0) gm = gmin * 2;
   double i;
-  if (!(m.RS != 0.0)) {
-    i = diode_i_raw(m, v) * m.AREA;
+  if (!(RS != 0.0)) {
+    i = diode_i_raw(k, v, efwd) * AREA;
     *last_vd = v;
   } else {
     // scipy.optimize.newton (Newton branch), tol = vea, x0 = last_vd
     double p0 = *last_vd, p = p0;
     for (int it = 0; it < 500; it++) {
-      double fval = p0 / m.RS - diode_i_raw(m, v - p0) * m.AREA;
+      const double e0 = safe_exp((v - p0) * k[DK_INVT]);
+      double fval = p0 / RS - diode_i_raw(k, v - p0, e0) * AREA;
       if (fval == 0) { p = p0; break; }
-      double fder = 1. / m.RS + m.AREA * diode_gm_raw(m, v - p0);
+      double fder = 1. / RS + AREA * diode_gm_raw(k, v - p0, e0);
       if (fder == 0) { p = p0; break; }
       p = p0 - fval / fder;
       if (fabs(p - p0) <= vea) break;
       p0 = p;
     }
     *last_vd = p;
-    i = diode_i_raw(m, v - p);  // AREA dropped, as diode.py:363 does
+    i = diode_i_raw(k, v - p, safe_exp((v - p) * k[DK_INVT]));  // AREA dropped, as diode.py:363 does
   }
   out[0] = i;
   out[1] = gm;

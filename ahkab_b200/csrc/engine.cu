@@ -187,7 +187,7 @@ size_t put(std::vector<unsigned char>& buf, const std::vector<T>& v) {
 int upload_program(ahk_engine* e) {
   HostProg& H = e->H;
   std::vector<unsigned char> buf;
-  size_t o_pcd = put(buf, H.pcd);
+  size_t o_pcd = put(buf, H.pcd), o_pst = put(buf, H.pstage), o_gps = put(buf, H.gpslot);
   size_t o_row = put(buf, H.row_ptr), o_pcol = put(buf, H.pcol), o_prowi = put(buf, H.prowi), o_pdiag = put(buf, H.pdiag);
   size_t o_tp = put(buf, H.term_ptr), o_ts = put(buf, H.term_slot), o_tk = put(buf, H.term_kind);
   size_t o_nlp = put(buf, H.nl_ptr), o_nls = put(buf, H.nl_src), o_nlg = put(buf, H.nl_sgn);
@@ -204,6 +204,7 @@ int upload_program(ahk_engine* e) {
   p.row_ptr = (const int*)(d + o_row); p.pcol = (const unsigned short*)(d + o_pcol);
   p.prowi = (const unsigned short*)(d + o_prowi); p.pdiag = d + o_pdiag;
   p.pcd = (const unsigned short*)(d + o_pcd);
+  p.pstage = (const int*)(d + o_pst); p.gpslot = (const int*)(d + o_gps);
   p.term_ptr = (const int*)(d + o_tp); p.term_slot = (const int*)(d + o_ts);
   p.term_kind = (const signed char*)(d + o_tk);
   p.nl_ptr = (const int*)(d + o_nlp); p.nl_src = (const short*)(d + o_nls);
@@ -290,7 +291,8 @@ int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, 
 // resident per SM (228 KB per SM, 1 KB reserved per block); smaller blocks waste
 // less of it.  Registers (<= 128 per thread for the common variants) allow 512
 // threads per SM.  Pick the block size with the most resident instances.
-int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int stride, Launch& L) {
+int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int stride, Launch& L,
+         int reg_blocks = 4) {
   const size_t sm_total = 228 * 1024;
   long long best_res = -1;
   for (int threads = 128; threads >= 32; threads >>= 1) {
@@ -301,7 +303,7 @@ int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int st
     long long blocks_sm = (long long)(sm_total / (smem + 1024));
     if (blocks_sm > 32) blocks_sm = 32;
     long long thr = blocks_sm * threads;
-    if (thr > 512) thr = 512;
+    if (thr > 128 * reg_blocks) thr = 128 * reg_blocks;
     const long long res = thr / v.G;
     if (res > best_res) {
       best_res = res;
@@ -338,7 +340,7 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   const VarInfo& v = real_variants()[vid];
   Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC);
   Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L)) return -1;
+  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC))) return -1;
   KDc k;
   k.b = make_base(e, batch, Ly);
   k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
@@ -487,7 +489,7 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   const VarInfo& v = real_variants()[vid];
   Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC);
   Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L)) return -1;
+  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC))) return -1;
   KTran k;
   k.b = make_base(e, batch, Ly);
   k.x0 = x0;

@@ -22,11 +22,18 @@ namespace ahk {
   X(4, 4, 1, 4) X(5, 6, 1, 8) X(6, 8, 2, 4) X(7, 10, 3, 4) X(8, 12, 3, 4)             \
   X(9, 16, 2, 8) X(10, 16, 1, 16) X(11, 24, 3, 8) X(12, 32, 2, 16)
 #define AHK_N_REAL_VARIANTS 13
-// complex128 rows cost twice the registers: one row per lane beyond n = 3
+// complex128 rows cost twice the registers: one row per lane beyond n = 3 (two rows per lane,
+// Var<16,2,8>, spills 1 KB at 168 registers and measured 2.01 vs 1.89 ms on C1)
 #define AHK_AC_VARIANTS(X)                                                            \
   X(0, 0, 0, 8) X(1, 0, 0, 32)                                                        \
   X(2, 4, 3, 1) X(3, 8, 1, 8) X(4, 16, 1, 16) X(5, 24, 1, 32) X(6, 32, 1, 32)
 #define AHK_N_AC_VARIANTS 7
+
+#ifndef AHK_MINB
+#define AHK_MINB 4   // resident 128-thread blocks per SM the small real variants are compiled for
+#endif
+// __launch_bounds__(128, min_blocks(NC)) caps the registers so that many blocks fit
+inline int real_min_blocks(int NC) { return NC <= 12 ? AHK_MINB : (NC <= 16 ? 3 : 2); }
 
 struct VarInfo { int NC, R, G; };
 inline const VarInfo* real_variants() {

@@ -18,6 +18,7 @@ struct LinOp {      // one linear element's contribution to MNA (Mv) or D (Dv)
 
 struct SrcOp {      // independent source: N, Tt(t), Nac
   int is_v, elem, pbase, tf, has_ac;
+  int ppb;          // first PERSISTENT slot of [dc, |ac|, arg(ac)] (+ waveform block)
   int row0, row1;   // V: row0 = KVL row; I: rows of n1, n2 (-1 = ground)
 };
 
@@ -26,6 +27,8 @@ struct DevOp {      // non-linear device
   int node[4];      // reduced indices (-1 ground): D n1,n2; MOS d,g,s,b; SW n1,n2,sn1,sn2
   int dout;         // first slot of this device's outputs
   int con;          // first slot of its per-instance constants (EKV), else -1
+  int ppb, pmb;     // first PERSISTENT slot of its own / its model's parameters, else -1
+  int st;           // first slot of its 2-double state (diode last_vd, switch is_on), else -1
   int active;       // 0: both output nodes grounded -> never evaluated (dc_analysis.py:863)
 };
 
@@ -40,6 +43,9 @@ struct Opts {
 
 struct Prog {
   int n, nv1, npos, nlin, nsrc, ntd, ndev, ndout, nlock, nguess, nparams, nac;
+  int npersist;                   // parameters staged in shared memory for the whole analysis
+  const int* pstage;              // [npersist] global parameter slot of each persistent slot
+  const int* gpslot;              // [nguess] persistent slot of each OP-guess term, or -1
   const int* row_ptr;             // [n+1] positions are sorted by (row, col)
   const unsigned short* pcol;     // [npos]
   const unsigned short* pcd;      // [npos] pcol | 0x8000 on node-row diagonals (n < 32768)

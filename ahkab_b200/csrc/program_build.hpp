@@ -24,7 +24,8 @@ namespace ahk {
 
 struct HostProg {
   Prog hdr;   // scalar fields valid; pointers filled by view()/upload
-  std::vector<int> row_ptr, nl_ptr, tx_ptr, lock, gslot, slot_vary;
+  std::vector<int> row_ptr, nl_ptr, tx_ptr, lock, gslot, slot_vary, pstage, gpslot;
+  int nst = 0;       // doubles of per-device state
   std::vector<unsigned short> pcol, prowi, pcd;
   std::vector<unsigned char> pdiag;
   std::vector<int> term_ptr, term_slot;
@@ -50,6 +51,7 @@ struct HostProg {
     p.lin = lin.data(); p.src = src.data(); p.dev = dev.data(); p.lock = lock.data();
     p.guessG = guessG.data(); p.gslot = gslot.data(); p.gscale = gscale.data();
     p.gconst = gconst.data(); p.nominal = nominal.data(); p.slot_vary = slot_vary.data();
+    p.pstage = pstage.data(); p.gpslot = gpslot.data();
     return p;
   }
 };
@@ -185,6 +187,14 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
     }
     if (H.term_slot.empty()) { H.term_slot.push_back(0); H.term_kind.push_back(0); }
   }
+  // persistent parameter slots: the values still needed after the per-instance set-up
+  // (sources, diode / mosq / switch devices, OP-guess terms); everything else (R, C, L,
+  // EKV model + geometry) is read once from HBM while the instance is loaded
+  auto persist = [&](int slot0, int cnt) {
+    int at = (int)H.pstage.size();
+    for (int i = 0; i < cnt; i++) H.pstage.push_back(slot0 + i);
+    return at;
+  };
   // sources: I first, then V (the reference's two loops)
   int ntd = 0, nac = 0;
   for (int pass = 0; pass < 2; pass++)
@@ -196,6 +206,7 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
       s.has_ac = (e.flags & AHK_FLAG_HAS_AC) ? 1 : 0;
       if (s.is_v) { s.row0 = nv1 + e.vde; s.row1 = -1; }
       else { s.row0 = e.n1 - 1; s.row1 = e.n2 - 1; }
+      s.ppb = persist(e.pbase, 3 + (e.tf ? 8 : 0));
       if (s.tf) ntd++;
       if (s.has_ac) nac++;
       H.src.push_back(s);
@@ -212,8 +223,12 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
     H.nonlinear = true;
     DevOp d; std::memset(&d, 0, sizeof d);
     d.type = e.type; d.pbase = e.pbase; d.mbase = e.mbase; d.flags = e.flags;
-    d.dout = ndout; d.active = 1; d.con = -1;
+    d.dout = ndout; d.active = 1; d.con = -1; d.ppb = d.pmb = d.st = -1;
     if (e.type == AHK_EKV) { d.con = H.ncon; H.ncon += 16; }
+    if (e.type == AHK_D) { d.con = H.ncon; H.ncon += 10; }
+    if (e.type == AHK_MOSQ) { d.ppb = persist(e.pbase, 6); d.pmb = persist(e.mbase, 7); }
+    if (e.type == AHK_SW) { d.ppb = persist(e.pbase, 1); d.pmb = persist(e.mbase, 4); }
+    if (e.type == AHK_D || e.type == AHK_SW) { d.st = H.nst; H.nst += 2; }
     const int b = ndout;
     switch (e.type) {
       case AHK_D:   // stamp path, diode.py:150-198
@@ -281,6 +296,9 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   H.gslot.assign(c->guess_slot, c->guess_slot + ng);
   H.gscale.assign(c->guess_scale, c->guess_scale + ng);
   H.gconst.assign(c->guess_const, c->guess_const + ng);
+  H.gpslot.assign(ng > 0 ? ng : 1, -1);
+  for (int j = 0; j < ng; j++) if (H.gslot[j] >= 0) H.gpslot[j] = persist(H.gslot[j], 1);
+  if (H.pstage.empty()) H.pstage.push_back(0);
   H.nominal.assign(c->nominal, c->nominal + c->n_params);
   H.slot_vary.assign(c->n_params > 0 ? c->n_params : 1, -1);
   // keep vectors non-empty so data() is a valid pointer everywhere
@@ -291,6 +309,12 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   h.n = n; h.nv1 = nv1; h.npos = np; h.nlin = (int)H.lin.size(); h.nsrc = (int)H.src.size();
   h.ntd = ntd; h.nac = nac; h.ndev = (int)H.dev.size(); h.ndout = ndout;
   h.nlock = (int)H.lock.size() / 2; h.nguess = ng; h.nparams = c->n_params;
+  h.npersist = 0;
+  for (auto& so : H.src) h.npersist = std::max(h.npersist, so.ppb + 3 + (so.tf ? 8 : 0));
+  for (auto& dv : H.dev) {
+    if (dv.pmb >= 0) h.npersist = std::max(h.npersist, dv.pmb + (dv.type == AHK_MOSQ ? 7 : 4));
+  }
+  for (int j = 0; j < ng; j++) h.npersist = std::max(h.npersist, H.gpslot[j] + 1);
 }
 
 inline void set_vary_slots(HostProg& H, int n_vary, const int* slots) {
@@ -323,11 +347,11 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   L.Bv = mode == MODE_TRAN ? take(h.npos) : L.Mv;
   L.Nc = take(n);
   L.Nd = h.ntd > 0 ? take(n) : L.Nc;      // N + Tt(t); no waveforms: N itself
-  L.dout = take(h.ndout); L.dst = take(2 * h.ndev);
+  L.dout = take(h.ndout); L.dst = take(H.nst);
   L.xs = take(n);
   L.x1 = mode == MODE_TRAN ? L.xs : take(n);   // x1: pass-1 solution of the OP only
   L.bytes = take(NC > 0 ? 0 : 16);
-  L.Pv = take(h.nparams); L.dcon = take(H.ncon);
+  L.Pv = take(h.npersist); L.dcon = take(H.ncon);
   L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);
   L.gsc = take(mode == MODE_TRAN && method >= AHK_GEAR1 ? 32 : 0);
   L.buflen = 1;

@@ -127,7 +127,9 @@ void emu_diode_eval(const double* model9, double area, double v, double vea, dou
   DiodeP m;
   m.IS = model9[0]; m.N = model9[1]; m.NBV = model9[2]; m.ISR = model9[3]; m.NR = model9[4];
   m.RS = model9[5]; m.BV = model9[6]; m.IKF = model9[7]; m.VT = model9[8]; m.AREA = area;
-  diode_eval(m, v, vea, gmin, last_vd, out2);
+  double k[DK_NCONST];
+  diode_setup(m, k);
+  diode_eval(k, v, vea, gmin, last_vd, out2);
 }
 void emu_switch_eval(const double* model4, double vout, double vin, double* is_on, double gmin,
                      double* out3) {
