@@ -127,33 +127,59 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
       for (int kk = 0; kk < n; kk++) {
         // candidate rows: entries of column kk in rows that are not pivot rows yet
         unsigned word = lane < W ? (cbits[kk * W + lane] & ~used[lane]) : 0u;
-        const int cnt = __popc(word);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-        const int ncand = __shfl_sync(FULL, incl, 31);
-        {
-          int o = incl - cnt;
-          while (word) { const int b = __ffs(word) - 1; word &= word - 1; pend_r[o++] = (unsigned short)(lane * 32 + b); }
-        }
-        __syncwarp();
+        const unsigned nzm = __ballot_sync(FULL, word != 0u);
+        int ncand = 0;
+        for (unsigned m2 = nzm; m2; m2 &= m2 - 1) ncand += __popc(__shfl_sync(FULL, word, __ffs(m2) - 1));
         double best = -1.0, sv = 0.0;
         int bi = -1;
-        for (int i = lane; i < ncand; i += 32) {
-          const int r = pend_r[i];
-          double v = 0.0;
-          const int c = scnt[r];
-          for (int t = 0; t < c; t++) if (scol[r * SC + t] == kk) { v = sval[r * SC + t]; break; }
-          pend_v[i] = v;
-          const double a = fabs(v);
-          if (bi < 0 || a > best) { best = a; bi = r; sv = v; }
-        }
+        if (ncand <= 8) {
+          // the usual case on circuit matrices: a handful of candidates.  Every lane walks
+          // them in ascending row order (warp-uniform), the slot look-up of each row is
+          // spread over the lanes; lane i keeps candidate i for the elimination.
+          int ci = 0, my_r = 0;
+          double my_v = 0.0;
+          for (unsigned m2 = nzm; m2; m2 &= m2 - 1) {
+            const int ww = __ffs(m2) - 1;
+            for (unsigned wv = __shfl_sync(FULL, word, ww); wv; wv &= wv - 1) {
+              const int r = ww * 32 + __ffs(wv) - 1;
+              const int c = scnt[r];
+              const bool hit = lane < c && scol[r * SC + lane] == kk;
+              const unsigned hb = __ballot_sync(FULL, hit);
+              const double v = hb ? __shfl_sync(FULL, lane < c ? sval[r * SC + lane] : 0.0, __ffs(hb) - 1) : 0.0;
+              const double a = fabs(v);
+              if (bi < 0 || a > best) { best = a; bi = r; sv = v; }
+              if (ci == lane) { my_r = r; my_v = v; }
+              ci++;
+            }
+          }
+          if (lane < ncand) { pend_r[lane] = (unsigned short)my_r; pend_v[lane] = my_v; }
+          __syncwarp();
+        } else {
+          const int cnt = __popc(word);
+          int incl = cnt;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(FULL, best, o), osv = __shfl_xor_sync(FULL, sv, o);
-          const int oi = __shfl_xor_sync(FULL, bi, o);
-          const bool take = (oi >= 0) && (bi < 0 || ov > best || (ov == best && oi < bi));
-          if (take) { best = ov; bi = oi; sv = osv; }
+          for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+          {
+            int o = incl - cnt;
+            while (word) { const int b = __ffs(word) - 1; word &= word - 1; pend_r[o++] = (unsigned short)(lane * 32 + b); }
+          }
+          __syncwarp();
+          for (int i = lane; i < ncand; i += 32) {
+            const int r = pend_r[i];
+            double v = 0.0;
+            const int c = scnt[r];
+            for (int t = 0; t < c; t++) if (scol[r * SC + t] == kk) { v = sval[r * SC + t]; break; }
+            pend_v[i] = v;
+            const double a = fabs(v);
+            if (bi < 0 || a > best) { best = a; bi = r; sv = v; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, best, o), osv = __shfl_xor_sync(FULL, sv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            const bool take = (oi >= 0) && (bi < 0 || ov > best || (ov == best && oi < bi));
+            if (take) { best = ov; bi = oi; sv = osv; }
+          }
         }
         if (bi < 0 || best == 0.0) { singular = 1; break; }
         if (Lbase + ncand > (m + 1) * k.cap2 || Ubase + SC + 1 > (m + 1) * k.cap2) { ovf = 1; break; }

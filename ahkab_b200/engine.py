@@ -116,6 +116,33 @@ class Engine(object):
     def _new(self, shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    _ES = {torch.float64: 8, torch.int32: 4}
+
+    def _new_packed(self, spec):
+        """Result tensors of one call as views into ONE device buffer, so that the
+        device->host read of an end-to-end step is a single copy.  spec: tuple of (key,
+        shape, dtype); float64 first keeps every view 8-byte aligned.  The byte layout is
+        cached per spec (this sits on the launch path of sub-100-us kernels)."""
+        lay = self._layouts.get(spec) if hasattr(self, '_layouts') else None
+        if lay is None:
+            if not hasattr(self, '_layouts'):
+                self._layouts = {}
+            items, off = [], 0
+            for k, shape, dtype in spec:
+                n_el = int(np.prod(shape))
+                nb = (n_el * self._ES[dtype] + 7) & ~7
+                items.append((k, tuple(shape), dtype, off, n_el * self._ES[dtype], nb))
+                off += nb
+            lay = (off, items)
+            self._layouts[spec] = lay
+        total, items = lay
+        base = torch.empty(total, dtype=torch.uint8, device=self.device)
+        out = {}
+        for k, shape, dtype, off, nbytes, _nb in items:
+            out[k] = base[off:off + nbytes].view(dtype).view(shape)
+        out['_packed'] = (base, items)
+        return out
+
     def _x0(self, x0):
         if x0 is None:
             return None
@@ -135,10 +162,12 @@ class Engine(object):
     # -- analyses -----------------------------------------------------------------
     def op(self, x0=None, use_guess=True, want_resid=True):
         x0 = self._x0(x0)
-        x = self._new((self.B, self.n))
-        resid = self._new((self.B, self.n)) if want_resid else None
-        iters = self._new((self.B,), torch.int32)
-        status = self._new((self.B,), torch.int32)
+        spec = (('x', (self.B, self.n), torch.float64),)
+        if want_resid:
+            spec += (('resid', (self.B, self.n), torch.float64),)
+        spec += (('iters', (self.B,), torch.int32), ('status', (self.B,), torch.int32))
+        pk = self._new_packed(spec)
+        x, resid, iters, status = pk['x'], pk.get('resid'), pk['iters'], pk['status']
         b = self._batch()
         with torch.cuda.device(self.device):
             rc = self.lib.ahk_op(self._h, C.byref(b), _ptr(x0),
@@ -146,16 +175,17 @@ class Engine(object):
                                  _ptr(iters), _ptr(status), self._stream())
         if rc != 0:
             raise EngineError(self._err())
-        return dict(x=x, resid=resid, iters=iters, status=status)
+        return dict(x=x, resid=resid, iters=iters, status=status, _packed=pk['_packed'])
 
     def dc_sweep(self, source, sweep_values, x0=None, use_guess=True):
         src = source if isinstance(source, int) else self.elem_index(source)
         sweep = np.ascontiguousarray(sweep_values, np.float64)
         P = len(sweep)
         x0 = self._x0(x0)
-        x = self._new((self.B, P, self.n))
-        iters = self._new((self.B, P), torch.int32)
-        status = self._new((self.B, P), torch.int32)
+        pk = self._new_packed((('x', (self.B, P, self.n), torch.float64),
+                               ('iters', (self.B, P), torch.int32),
+                               ('status', (self.B, P), torch.int32)))
+        x, iters, status = pk['x'], pk['iters'], pk['status']
         b = self._batch()
         with torch.cuda.device(self.device):
             rc = self.lib.ahk_dc_sweep(
@@ -165,7 +195,7 @@ class Engine(object):
                 self._stream())
         if rc != 0:
             raise EngineError(self._err())
-        return dict(x=x, iters=iters, status=status, sweep=sweep)
+        return dict(x=x, iters=iters, status=status, sweep=sweep, _packed=pk['_packed'])
 
     def tran(self, x0, tstart, tstep, tstop, method='TRAP',
              use_step_control=True, max_rows=None):
@@ -176,11 +206,12 @@ class Engine(object):
             max_rows = self.default_max_rows(tstart, tstep, tstop,
                                              use_step_control)
         x0 = self._x0(x0)
-        t = self._new((self.B, max_rows))
-        x = self._new((self.B, max_rows, self.n))
-        rows = self._new((self.B,), torch.int32)
-        counters = self._new((self.B, 4), torch.int32)
-        status = self._new((self.B,), torch.int32)
+        pk = self._new_packed((('t', (self.B, max_rows), torch.float64),
+                               ('x', (self.B, max_rows, self.n), torch.float64),
+                               ('rows', (self.B,), torch.int32),
+                               ('counters', (self.B, 4), torch.int32),
+                               ('status', (self.B,), torch.int32)))
+        t, x, rows, counters, status = pk['t'], pk['x'], pk['rows'], pk['counters'], pk['status']
         b = self._batch()
         with torch.cuda.device(self.device):
             rc = self.lib.ahk_tran(
@@ -190,7 +221,7 @@ class Engine(object):
                 _ptr(status), self._stream())
         if rc != 0:
             raise EngineError(self._err())
-        return dict(t=t, x=x, rows=rows, counters=counters, status=status)
+        return dict(t=t, x=x, rows=rows, counters=counters, status=status, _packed=pk['_packed'])
 
     @staticmethod
     def default_max_rows(tstart, tstep, tstop, use_step_control):
@@ -206,8 +237,9 @@ class Engine(object):
         om = np.ascontiguousarray(omegas, np.float64)
         P = len(om)
         x_op = self._x0(x_op)
-        xo = self._new((self.B, P, self.n, 2))
-        status = self._new((self.B,), torch.int32)
+        pk = self._new_packed((('x', (self.B, P, self.n, 2), torch.float64),
+                               ('status', (self.B,), torch.int32)))
+        xo, status = pk['x'], pk['status']
         b = self._batch()
         with torch.cuda.device(self.device):
             rc = self.lib.ahk_ac(self._h, C.byref(b), _ptr(x_op),
@@ -215,7 +247,7 @@ class Engine(object):
                                  _ptr(xo), _ptr(status), self._stream())
         if rc != 0:
             raise EngineError(self._err())
-        return dict(x=torch.view_as_complex(xo), status=status, omegas=om)
+        return dict(x=torch.view_as_complex(xo), status=status, omegas=om, _packed=pk['_packed'])
 
     def to_host(self, raw, keys=None):
         """Device->host read of a result dict into cached PINNED buffers
@@ -224,6 +256,20 @@ class Engine(object):
         if not hasattr(self, '_pinned'):
             self._pinned = {}
         out = {}
+        if keys is None and raw.get('_packed') is not None:
+            base, layout = raw['_packed']             # one copy for the whole result set
+            key = ('_packed', base.numel())
+            hb = self._pinned.get(key)
+            if hb is None:
+                hb = torch.empty(base.numel(), dtype=torch.uint8, pin_memory=True)
+                self._pinned[key] = hb
+            hb.copy_(base, non_blocking=True)
+            for k, shape, dtype, off, nbytes, _nb in layout:
+                out[k] = hb[off:off + nbytes].view(dtype).view(shape)
+            for k, v in raw.items():                  # tensors that are not part of the pack
+                if torch.is_tensor(v) and k not in out and k != '_packed':
+                    out[k] = v.cpu()
+            return out
         for k, v in raw.items():
             if not torch.is_tensor(v) or (keys is not None and k not in keys):
                 continue

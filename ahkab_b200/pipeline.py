@@ -24,10 +24,12 @@ class _SubEngine(object):
         self.B = B
         self.vary = vary
         self._pinned = {}
+        self._layouts = {}
         self._h_owner = eng          # keeps the parent (and the C handle) alive
 
-    def __getattr__(self, name):     # methods come from the parent's class
-        return getattr(type(self._h_owner), name).__get__(self)
+    def __getattr__(self, name):     # methods / class attributes come from the parent's class
+        a = getattr(type(self._h_owner), name)
+        return a.__get__(self) if hasattr(a, '__get__') and callable(a) else a
 
     def __del__(self):
         pass

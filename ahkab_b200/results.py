@@ -95,6 +95,28 @@ class solution(object):
     def status(self):
         return self._get('status')
 
+    def instance_array(self, b):
+        """(variables, samples) array of instance b — what the reference's
+        `solution.asarray()` returns for its single circuit."""
+        a = self.asarray()
+        return np.asarray(a[b]).reshape(len(self.variables), -1)
+
+    def write_csv(self, filename, b=0):
+        """Optional exporter: instance b in the reference's on-disk results format
+        (csvlib.write_csv, ahkab/csvlib.py:64-100): '#'-prefixed tab-separated header,
+        one row per sample, numpy.savetxt's '%.18e' (lossless for float64).  AC files
+        hold |x| and arg(x) columns like the reference (results.py:640-682)."""
+        data = self.instance_array(b)
+        headers = list(self.variables)
+        if np.iscomplexobj(data):
+            rows, names = [np.real(data[0])], [headers[0]]
+            for i in range(1, len(headers)):
+                rows += [np.abs(data[i]), np.angle(data[i])]
+                names += ['|%s|' % headers[i], 'arg(%s)' % headers[i]]
+            data, headers = np.stack(rows), names
+        with open(filename, 'wb') as fp:
+            np.savetxt(fp, data.T, delimiter=u"\t", header=u"\t".join(headers), comments='#')
+
     @property
     def ok(self):
         return (self.status & _abi.ST_OK) != 0
@@ -197,6 +219,9 @@ class tran_solution(solution):
         if i == 0:
             return self._masked(self._get('t'))
         return self._masked(self._get('x')[:, :, i - 1])
+
+    def instance_array(self, b):
+        return self.instance(b)
 
     def instance(self, b):
         """(1 + n, rows[b]) array of instance b — the reference's asarray()."""

@@ -130,3 +130,24 @@ def test_running_an_analysis_without_a_gpu_fails_loudly():
     w = W.c2_diode_op(4)
     with pytest.raises(ahkab.EngineError):
         ahkab.run(w.circuit(ahkab.Circuit), ahkab.new_op(), batch=w.batch())
+
+
+def test_write_csv_uses_the_reference_file_format(tmp_path):
+    """csvlib.write_csv layout: '#' + tab-separated names, then one '%.18e' row per sample."""
+    c3 = W.c3_colpitts(2).circuit(Circuit)
+    t = np.array([[1e-10, 2e-10, 3e-10, 0.0], [1e-10, 2e-10, 0.0, 0.0]])
+    x = np.random.default_rng(0).standard_normal((2, 4, 9))
+    sol = results.tran_solution(c3, dict(t=t, x=x, rows=np.array([3, 2]),
+                                         status=np.ones(2, np.int32)), 0, 1, 'TRAP')
+    f = tmp_path / 'a.tran'
+    sol.write_csv(str(f), b=0)
+    lines = open(f).read().splitlines()
+    assert lines[0] == '#' + ' ' + '\t'.join(sol.keys()) or lines[0] == '#' + '\t'.join(sol.keys())
+    assert len(lines) == 1 + 3
+    back = np.loadtxt(f, delimiter='\t', comments='#')
+    assert np.array_equal(back[:, 0], t[0, :3]) and np.array_equal(back[:, 1:], x[0, :3])   # lossless
+    op = results.op_solution(c3, dict(x=x[:, 0], resid=x[:, 1], iters=np.zeros(2, np.int32),
+                                      status=np.ones(2, np.int32)))
+    op.write_csv(str(tmp_path / 'a.op'), b=1)
+    back = np.loadtxt(tmp_path / 'a.op', delimiter='\t', comments='#')
+    assert np.array_equal(back, x[1, 0])
