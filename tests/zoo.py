@@ -1,0 +1,107 @@
+"""Small circuits that exercise every element type / analysis option of the hot path.
+
+Each entry: build(Circuit, tf) -> circuit (tf = the time_functions module of whichever
+package builds it: the reference's in oracle/make_golden_misc.py, ours in the tests),
+the analysis to run, and the options overrides.  Shared by the golden generator (live
+reference) and the parity tests (oracle, host emulation, GPU)."""
+
+
+def rectifier(Circuit, tf):
+    """diode with series resistance (inner Newton, diode.py:359-365) + sin source,
+    TRAP with LTE step control."""
+    c = Circuit('rectifier')
+    c.add_model('diode', 'dr', dict(IS=2e-14, N=1.2, RS=0.5))
+    c.add_vsource('V1', 'in', c.gnd, dc_value=0., function=tf.sin(0., 5., 1e3))
+    c.add_diode('D1', 'in', 'out', 'dr')
+    c.add_resistor('RL', 'out', c.gnd, 1e3)
+    c.add_capacitor('CL', 'out', c.gnd, 10e-6)
+    return c
+
+
+def mosq_inverter(Circuit, tf):
+    """square-law MOS (stamp path, D/S swap) — DC transfer curve."""
+    c = Circuit('mosq inverter')
+    c.add_model('mosq', 'nm', dict(TYPE='n', VTO=.5, KP=60e-6, LAMBDA=.03))
+    c.add_model('mosq', 'pm', dict(TYPE='p', VTO=-.5, KP=25e-6, LAMBDA=.05))
+    c.add_vsource('VDD', 'dd', c.gnd, dc_value=2.5)
+    c.add_vsource('VIN', 'in', c.gnd, dc_value=0.)
+    c.add_mos('M1', 'out', 'in', 'dd', 'dd', w=4e-6, l=1e-6, model_label='pm')
+    c.add_mos('M2', 'out', 'in', c.gnd, c.gnd, w=2e-6, l=1e-6, model_label='nm')
+    c.add_resistor('RL', 'out', c.gnd, 1e6)
+    return c
+
+
+def switch_rc(Circuit, tf):
+    """voltage-controlled switch with hysteresis driven by a pulse, IE with step control."""
+    c = Circuit('switch')
+    c.add_model('sw', 'swm', dict(VT=1.0, VH=0.2, RON=10., ROFF=1e6))
+    c.add_vsource('VDD', 'dd', c.gnd, dc_value=3.)
+    c.add_vsource('VC', 'ctl', c.gnd, dc_value=0.,
+                  function=tf.pulse(0., 2., 1e-6, 1e-6, 3e-6, 1e-6, 10e-6))
+    c.add_switch('S1', 'dd', 'out', 'ctl', c.gnd, False, 'swm')
+    c.add_resistor('RL', 'out', c.gnd, 1e3)
+    c.add_capacitor('CL', 'out', c.gnd, 1e-9)
+    return c
+
+
+def controlled(Circuit, tf):
+    """E, G, H, F controlled sources + I source — linear OP."""
+    c = Circuit('controlled sources')
+    c.add_vsource('V1', 'a', c.gnd, dc_value=2.)
+    c.add_resistor('R1', 'a', 'b', 1e3)
+    c.add_resistor('R2', 'b', c.gnd, 2e3)
+    c.add_vcvs('E1', 'c', c.gnd, 'b', c.gnd, 3.)
+    c.add_resistor('R3', 'c', 'd', 500.)
+    c.add_vccs('G1', 'd', c.gnd, 'a', 'b', 2e-3)
+    c.add_resistor('R4', 'd', c.gnd, 1e3)
+    c.add_ccvs('H1', 'e', c.gnd, 'V1', 50.)
+    c.add_resistor('R5', 'e', 'f', 100.)
+    c.add_cccs('F1', 'f', c.gnd, 'V1', 4.)
+    c.add_resistor('R6', 'f', c.gnd, 200.)
+    c.add_isource('I1', 'b', c.gnd, dc_value=1e-3)
+    return c
+
+
+def coupled(Circuit, tf):
+    """coupled inductors (M = K sqrt(L1 L2)) — AC transfer."""
+    c = Circuit('transformer')
+    c.add_vsource('V1', 'in', c.gnd, dc_value=0., ac_value=1.)
+    c.add_resistor('RS', 'in', 'p', 50.)
+    c.add_inductor('L1', 'p', c.gnd, 1e-3)
+    c.add_inductor('L2', 's', c.gnd, 4e-3)
+    c.add_inductor_coupling('K1', 'L1', 'L2', 0.9)
+    c.add_resistor('RL', 's', c.gnd, 200.)
+    c.add_capacitor('CL', 's', c.gnd, 1e-8)
+    return c
+
+
+def rc_gear3(Circuit, tf):
+    """RC low-pass driven by a pulse: GEAR3 with LTE control (tests/tran_gear3 style),
+    also run with IE and GEAR5."""
+    c = Circuit('rc pulse')
+    c.add_vsource('V1', 'in', c.gnd, dc_value=0.,
+                  function=tf.pulse(0., 1., 1e-6, 1e-7, 4e-6, 1e-7, 10e-6))
+    c.add_resistor('R1', 'in', 'out', 1e3)
+    c.add_capacitor('C1', 'out', c.gnd, 1e-9)
+    c.add_resistor('R2', 'out', 'o2', 2e3)
+    c.add_capacitor('C2', 'o2', c.gnd, 0.5e-9)
+    return c
+
+
+ZOO = {
+    'rectifier': dict(build=rectifier, an=dict(kind='tran', tstart=0., tstop=2e-3, tstep=1e-5,
+                                               method='TRAP', use_step_control=True, x0='op')),
+    'mosq_inverter': dict(build=mosq_inverter, an=dict(kind='dc', start=0., stop=2.5, points=26,
+                                                       source='VIN')),
+    'switch_rc': dict(build=switch_rc, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=1e-7,
+                                               method='IMPLICIT_EULER', use_step_control=True,
+                                               x0='op')),
+    'controlled': dict(build=controlled, an=dict(kind='op')),
+    'coupled': dict(build=coupled, an=dict(kind='ac', start=1e2, stop=1e6, points=41)),
+    'rc_gear3': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                             method='GEAR3', use_step_control=True, x0='op')),
+    'rc_gear5': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                             method='GEAR5', use_step_control=True, x0='op')),
+    'rc_ie': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                          method='IMPLICIT_EULER', use_step_control=True, x0='op')),
+}
