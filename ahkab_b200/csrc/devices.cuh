@@ -16,7 +16,13 @@
 #ifdef __CUDACC__
 #define AHK_DEV __device__ __forceinline__
 #define AHK_MEM __device__ __forceinline__
+#ifdef AHK_NOINLINE_DEV
+#define AHK_DEVFN __device__ __noinline__
 #else
+#define AHK_DEVFN __device__ __forceinline__
+#endif
+#else
+#define AHK_DEVFN static inline
 #define AHK_DEV static inline
 #define AHK_MEM inline
 #endif
@@ -175,7 +181,7 @@ AHK_DEV double ekv_vp(const double* k, double VG) {   // ekv.py:524-540
 
 // out[0] = Ids, out[1..3] = gmd, gmg, gms.  k = the device's ekv_setup() block,
 // NP = +1 (n) / -1 (p); (vd, vg, vs) are the drive-port voltages w.r.t. bulk.
-AHK_DEV void ekv_eval(const double* k, int NP, double vd, double vg, double vs, double gmin,
+AHK_DEVFN void ekv_eval(const double* k, int NP, double vd, double vg, double vs, double gmin,
                       double* out) {
   const double Ut = AHK_VTH, iUt = 1.0 / AHK_VTH;
   double VD = vd * NP, VG = vg * NP, VS = vs * NP;  // ekv.py:481-507
