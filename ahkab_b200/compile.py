@@ -48,7 +48,9 @@ def _src_block(elem, ov, B):
         abs_ac, arg_ac = 0.0, 0.0
     tfk, tfp = TF.encode(elem._time_function) if elem.is_timedependent \
         else (0, [])
-    if tfk:
+    if tfk == TF.TF_PWL:
+        tfp = list(tfp)                       # variable length: 4 + 2 * npts
+    elif tfk:
         tfp = list(tfp) + [0.0] * (N_TF - len(tfp))
     else:
         tfp = []      # no waveform -> no tf slots (keeps the staged block small)
@@ -147,7 +149,7 @@ def flatten(circ, batch=None):
             r['flags'] |= fl
             r['tf'] = tfk
             nm = ['dc_value', 'abs_ac', 'arg_ac'] + ['tf%d' % j
-                                                     for j in range(N_TF)]
+                                                     for j in range(len(blk))]
             r['pbase'] = push(pid, list(zip(nm[:len(blk)], blk)))
         elif isinstance(e, (C.EVSource, C.GISource)):
             if 'value' in ov:

@@ -526,9 +526,7 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
       for (int k = 0; k < p.nsrc; k++) {
         const SrcOp& s = p.src[k];
         if (!s.tf) continue;
-        double q[8];
-        for (int j = 0; j < 8; j++) q[j] = c.PP(s.ppb + 3 + j);
-        double v = tf_eval(s.tf, q, time);
+        double v = tf_eval(s.tf, c.sm + c.L->Pv + s.ppb + 3, time);
         if (s.is_v) Nd[s.row0] += -1 * v;
         else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
       }

@@ -358,6 +358,21 @@ AHK_DEV double tf_eval(int kind, const double* q, double time) {
       if (time <= td) return 0.;
       return sa * (oc + sin(2 * PI * fm * (time - td))) * sin(2 * PI * fc * (time - td));
     }
+    case 6: {  // pwl: q = npts td repeat repeat_time x0 y0 x1 y1 ... (k = 1 spline, extrapolating)
+      const int np_ = (int)q[0];
+      const double td = q[1], rpt = q[3];
+      const double* xy = q + 4;
+      const double xmax = xy[2 * (np_ - 1)];
+      if (time <= td) time = 0;
+      else {
+        time = time - td;
+        if (q[2] != 0.0 && time > xmax) time = fmod(time - xmax, xmax - rpt) + rpt;
+      }
+      int i = 0;   // segment [i, i+1] that holds (or, outside the table, is nearest to) time
+      while (i < np_ - 2 && time > xy[2 * (i + 1)]) i++;
+      const double x0 = xy[2 * i], y0 = xy[2 * i + 1], x1 = xy[2 * i + 2], y1 = xy[2 * i + 3];
+      return y0 + (y1 - y0) / (x1 - x0) * (time - x0);
+    }
   }
   return 0;
 }

@@ -206,7 +206,9 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
       s.has_ac = (e.flags & AHK_FLAG_HAS_AC) ? 1 : 0;
       if (s.is_v) { s.row0 = nv1 + e.vde; s.row1 = -1; }
       else { s.row0 = e.n1 - 1; s.row1 = e.n2 - 1; }
-      s.ppb = persist(e.pbase, 3 + (e.tf ? 8 : 0));
+      s.ntf = !e.tf ? 0 : (e.tf == AHK_TF_PWL ? 4 + 2 * (int)c->nominal[e.pbase + 3] : 8);
+      if (e.tf == AHK_TF_PWL && (int)c->nominal[e.pbase + 3] < 2) throw std::runtime_error("pwl needs at least 2 points");
+      s.ppb = persist(e.pbase, 3 + s.ntf);
       if (s.tf) ntd++;
       if (s.has_ac) nac++;
       H.src.push_back(s);
@@ -310,7 +312,7 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   h.ntd = ntd; h.nac = nac; h.ndev = (int)H.dev.size(); h.ndout = ndout;
   h.nlock = (int)H.lock.size() / 2; h.nguess = ng; h.nparams = c->n_params;
   h.npersist = 0;
-  for (auto& so : H.src) h.npersist = std::max(h.npersist, so.ppb + 3 + (so.tf ? 8 : 0));
+  for (auto& so : H.src) h.npersist = std::max(h.npersist, so.ppb + 3 + so.ntf);
   for (auto& dv : H.dev) {
     if (dv.pmb >= 0) h.npersist = std::max(h.npersist, dv.pmb + (dv.type == AHK_MOSQ ? 7 : 4));
   }

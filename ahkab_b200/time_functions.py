@@ -5,11 +5,10 @@ The classes keep the reference's constructor signatures.  `__call__` is
 provided for host-side inspection (plots, tests); during a transient the
 waveform is evaluated on the device from the 8-slot parameter block
 `encode()` produces (include/ahkab_b200.h: AHK_TF_*), so the batch axis can
-also vary waveform parameters.  `pwl` (variable-length spline table) is not
-carried across the ABI in this round."""
+also vary waveform parameters (`pwl` carries its table: 4 + 2*npts slots)."""
 import math
 
-TF_NONE, TF_PULSE, TF_SIN, TF_EXP, TF_SFFM, TF_AM = range(6)
+TF_NONE, TF_PULSE, TF_SIN, TF_EXP, TF_SFFM, TF_AM, TF_PWL = range(7)
 
 
 class pulse(object):
@@ -128,12 +127,56 @@ class am(object):
         return TF_AM, [self.sa, self.fc, self.fm, self.oc, self.td]
 
 
+class pwl(object):
+    """ahkab/time_functions.py:730-828: piece-wise linear through (x_i, y_i) — a k = 1
+    InterpolatedUnivariateSpline, i.e. linear extrapolation outside the table — with an
+    optional delay and repetition."""
+    def __init__(self, x, y, repeat=False, repeat_time=0, td=0):
+        self.x = [float(v) for v in x]
+        self.y = [float(v) for v in y]
+        if len(self.x) != len(self.y) or len(self.x) < 2:
+            raise ValueError("pwl needs two sequences of at least 2 points")
+        self.repeat = repeat
+        self.repeat_time = repeat_time
+        if self.repeat_time == max(self.x):
+            self.repeat_time = 0
+        self.td = td
+        self._type = "V"
+
+    def _normalize_time(self, time):
+        if time is None:
+            time = 0
+        if time <= self.td:
+            time = 0
+        else:
+            time = time - self.td
+            if self.repeat and time > max(self.x):
+                time = (time - max(self.x)) % (max(self.x) - self.repeat_time) + \
+                    self.repeat_time
+        return time
+
+    def __call__(self, time):
+        t = self._normalize_time(time)
+        i = 0
+        while i < len(self.x) - 2 and t > self.x[i + 1]:
+            i += 1
+        x0, y0, x1, y1 = self.x[i], self.y[i], self.x[i + 1], self.y[i + 1]
+        return y0 + (y1 - y0) / (x1 - x0) * (t - x0)
+
+    def _encode(self):
+        xy = []
+        for a, b in zip(self.x, self.y):
+            xy += [a, b]
+        return TF_PWL, [float(len(self.x)), self.td, 1.0 if self.repeat else 0.0,
+                        self.repeat_time] + xy
+
+
 def encode(fn):
-    """(kind, params[<=8]) for the ABI parameter block."""
+    """(kind, params) for the ABI parameter block: up to 8 values, or 4 + 2*npts for pwl."""
     if fn is None:
         return TF_NONE, []
     if hasattr(fn, '_encode'):
         return fn._encode()
     raise NotImplementedError(
         "time function %r cannot be evaluated on the device: only pulse, sin, "
-        "exp, sffm and am are carried across the ABI" % (fn,))
+        "exp, sffm, am and pwl are carried across the ABI" % (fn,))

@@ -45,8 +45,9 @@ enum {
   AHK_L = 3,   /* inductor (vde)      params: [L, ic]                      */
   AHK_K = 4,   /* inductor coupling   params: [K]  ref/ref2 = vde of L1/L2,
                                       aux0/aux1 = pbase of L1/L2           */
-  AHK_V = 5,   /* V source (vde)      params: [dc, |ac|, arg(ac)] + [tf0..tf7]
-                                      iff tf != AHK_TF_NONE                 */
+  AHK_V = 5,   /* V source (vde)      params: [dc, |ac|, arg(ac)] + the waveform
+                                      block iff tf != AHK_TF_NONE: 8 slots,
+                                      AHK_TF_PWL: 4 + 2*npts slots          */
   AHK_I = 6,   /* I source            params: as AHK_V                      */
   AHK_E = 7,   /* VCVS (vde)          params: [alpha]  n3,n4 = sense nodes  */
   AHK_G = 8,   /* VCCS                params: [alpha]  n3,n4 = sense nodes  */
@@ -71,7 +72,9 @@ enum {
   AHK_TF_SIN = 2,   /* vo va freq td theta phi          */
   AHK_TF_EXP = 3,   /* v1 v2 td1 tau1 td2 tau2          */
   AHK_TF_SFFM = 4,  /* vo va fc mdi fs td               */
-  AHK_TF_AM = 5     /* sa fc fm oc td                   */
+  AHK_TF_AM = 5,    /* sa fc fm oc td                   */
+  AHK_TF_PWL = 6    /* npts td repeat repeat_time x0 y0 x1 y1 ... (4 + 2*npts slots,
+                       linear interpolation / extrapolation, time_functions.py:730-828) */
 };
 
 #define AHK_FLAG_HAS_AC 0x100   /* V/I: |ac|, arg(ac) are meaningful       */

@@ -101,10 +101,12 @@ def test_time_functions_match_the_device_encoding():
     L = oracle.lib()
     fns = [TF.pulse(0., 1., 1e-9, 2e-9, 5e-9, 3e-9, 20e-9), TF.sin(0.5, 2., 1e8, 1e-9, 1e7, 30.),
            TF.exp(0., 1., 1e-9, 2e-9, 8e-9, 3e-9), TF.sffm(0., 1., 1e8, 2., 1e7, 1e-9),
-           TF.am(1., 1e8, 1e7, 0.5, 1e-9)]
+           TF.am(1., 1e8, 1e7, 0.5, 1e-9),
+           TF.pwl((0., 1e-9, 5e-9, 6e-9), (0., 1., 1., -2.), repeat=True, repeat_time=1e-9, td=2e-9),
+           TF.pwl((1e-9, 4e-9), (0.5, 2.))]
     for fn in fns:
         kind, prm = TF.encode(fn)
-        q = np.zeros(8)
+        q = np.zeros(max(8, len(prm)))
         q[:len(prm)] = prm
         for t in np.linspace(0, 45e-9, 91):
             c = L.ahko_tf_eval(C.c_int(kind), q.ctypes.data_as(C.POINTER(C.c_double)),

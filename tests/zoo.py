@@ -88,6 +88,19 @@ def rc_gear3(Circuit, tf):
     return c
 
 
+def pwl_rc(Circuit, tf):
+    """piece-wise linear source with delay and repetition into an RC network, GEAR2."""
+    c = Circuit('pwl')
+    x = (0., 1e-6, 1.5e-6, 3e-6, 3.5e-6)
+    y = (0., 0., 2., 2., 0.)      # continuous across the repetition wrap (y(3.5u) = y(1u))
+    c.add_vsource('V1', 'in', c.gnd, dc_value=0.,
+                  function=tf.pwl(x, y, repeat=True, repeat_time=1e-6, td=0.5e-6))
+    c.add_resistor('R1', 'in', 'out', 200.)
+    c.add_capacitor('C1', 'out', c.gnd, 2e-9)
+    c.add_resistor('R2', 'out', c.gnd, 2e3)
+    return c
+
+
 ZOO = {
     'rectifier': dict(build=rectifier, an=dict(kind='tran', tstart=0., tstop=2e-3, tstep=1e-5,
                                                method='TRAP', use_step_control=True, x0='op')),
@@ -102,6 +115,8 @@ ZOO = {
                                              method='GEAR3', use_step_control=True, x0='op')),
     'rc_gear5': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
                                              method='GEAR5', use_step_control=True, x0='op')),
+    'pwl_rc': dict(build=pwl_rc, an=dict(kind='tran', tstart=0., tstop=10e-6, tstep=1e-7,
+                                         method='GEAR2', use_step_control=True, x0='op')),
     'rc_ie': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
                                           method='IMPLICIT_EULER', use_step_control=True, x0='op')),
 }
