@@ -255,11 +255,18 @@ bool fits(const VarInfo& v, int n) {
   return v.NC - 1 >= n && v.R * v.G >= n;
 }
 
-// Smallest column count that fits (least padding); among those, few lanes per instance
-// when the batch alone fills the machine (no idle lanes, no cross-lane traffic), many
-// lanes when it does not (latency hiding needs the extra warps).
+int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int stride, Launch& L,
+         int reg_blocks, long long* resident);
+
+// Smallest column count that fits (least padding).  Among those: the FEWEST lanes per
+// instance (no idle lanes, no cross-lane traffic) whose resident instances per SM
+// (bounded by the shared-memory slice and the register cap) hold the SM's share of the
+// batch in one wave while still giving the SM >= 128 busy lanes; failing that, the
+// variant with the most busy lanes per SM (small batches, or slices too big for one
+// wave).  stride_of(v) = doubles per instance of the layout.
+template <typename StrideOf>
 int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, long long units,
-                 int* vid) {
+                 int reg_blocks_of(int), StrideOf stride_of, int* vid) {
   const int n = e->n;
   if (forced >= 0) {
     if (forced >= ntab || !fits(tab[forced], n)) return fail("forced kernel variant does not fit this circuit");
@@ -267,21 +274,33 @@ int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, 
     *vid = forced;
     return 0;
   }
-  const bool big_batch = units >= 32768;
-  int best = -1;
+  const long long per_sm = (units + e->sm_count - 1) / e->sm_count;   // instances one SM must hold
+  int minNC = 1 << 30;
+  for (int i = 2; i < ntab; i++)
+    if (fits(tab[i], n) && (e->group <= 0 || tab[i].G == e->group)) minNC = std::min(minNC, tab[i].NC);
+  int best = -1, best_one_wave = -1;
+  long long best_lanes = -1;
   for (int i = 2; i < ntab; i++) {
-    if (!fits(tab[i], n)) continue;
+    if (!fits(tab[i], n) || tab[i].NC != minNC) continue;
     if (e->group > 0 && tab[i].G != e->group) continue;
-    if (best < 0) { best = i; continue; }
-    const VarInfo &a = tab[i], &b = tab[best];
-    if (a.NC != b.NC) { if (a.NC < b.NC) best = i; continue; }
-    if (big_batch ? a.G < b.G : a.G > b.G) best = i;
+    long long res = 0;
+    Launch tmp;
+    if (plan(e, units, i, tab[i], stride_of(tab[i]), tmp, reg_blocks_of(tab[i].NC), &res))
+      continue;   // does not fit in shared memory
+    const long long lanes = std::min(res, per_sm) * tab[i].G;
+    if (res >= per_sm && per_sm * tab[i].G >= 128 &&
+        (best_one_wave < 0 || tab[i].G < tab[best_one_wave].G))
+      best_one_wave = i;
+    if (best < 0 || lanes > best_lanes || (lanes == best_lanes && tab[i].G < tab[best].G)) {
+      best = i; best_lanes = lanes;
+    }
   }
+  if (best_one_wave >= 0) best = best_one_wave;
   if (best < 0) {   // generic fallback
     if (n > AHK_SMALL_NMAX) return fail("circuit too large for the shared-memory engine");
     if (e->group > 0 && e->group != 8 && e->group != 32)
       return fail("no kernel variant with that many lanes fits this circuit");
-    best = e->group == 8 ? 0 : (e->group == 32 ? 1 : (big_batch ? 0 : 1));
+    best = e->group == 8 ? 0 : (e->group == 32 ? 1 : (units >= 32768 ? 0 : 1));
   }
   *vid = best;
   return 0;
@@ -292,7 +311,7 @@ int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, 
 // less of it.  Registers (<= 128 per thread for the common variants) allow 512
 // threads per SM.  Pick the block size with the most resident instances.
 int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int stride, Launch& L,
-         int reg_blocks = 4) {
+         int reg_blocks, long long* resident) {
   const size_t sm_total = 228 * 1024;
   long long best_res = -1;
   for (int threads = 128; threads >= 32; threads >>= 1) {
@@ -313,6 +332,7 @@ int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int st
   }
   if (best_res < 0)
     return fail("circuit too large for the shared-memory engine (n = " + std::to_string(e->n) + ")");
+  if (resident) { *resident = best_res; return 0; }
   if (getenv("AHK_DEBUG"))
     fprintf(stderr, "[ahk] n=%d variant %d (NC=%d R=%d G=%d) stride %d doubles, %d thr/block, %d blocks, "
             "%zu B smem/block, %lld instances resident/SM\n", e->n, vid, v.NC, v.R, v.G, stride, L.threads,
@@ -336,11 +356,13 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
                  const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
                  int32_t* status, cudaStream_t s) {
   int vid;
-  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, &vid)) return -1;
+  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
+                   [&](const VarInfo& q) { return make_layout(e->H, MODE_OP, 0, 0, q.G, q.NC).stride; }, &vid))
+    return -1;
   const VarInfo& v = real_variants()[vid];
   Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC);
   Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC))) return -1;
+  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
   KDc k;
   k.b = make_base(e, batch, Ly);
   k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
@@ -485,11 +507,14 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
   int vid;
-  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, &vid)) return -1;
+  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
+                   [&](const VarInfo& q) { return make_layout(e->H, MODE_TRAN, method, use_step_control, q.G, q.NC).stride; },
+                   &vid))
+    return -1;
   const VarInfo& v = real_variants()[vid];
   Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC);
   Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC))) return -1;
+  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
   KTran k;
   k.b = make_base(e, batch, Ly);
   k.x0 = x0;
@@ -514,11 +539,13 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
   }
   long long units = batch->B * nchunks;
   int vid;
-  if (pick_variant(e, ac_variants(), AHK_N_AC_VARIANTS, e->force_ac_vid, units, &vid)) return -1;
+  if (pick_variant(e, ac_variants(), AHK_N_AC_VARIANTS, e->force_ac_vid, units, ac_min_blocks,
+                   [&](const VarInfo& q) { return make_ac_layout(e->H, q.G, q.NC).stride; }, &vid))
+    return -1;
   const VarInfo& v = ac_variants()[vid];
   AcLayout AL = make_ac_layout(e->H, v.G, v.NC);
   Launch L;
-  if (plan(e, units, vid, v, AL.stride, L)) return -1;
+  if (plan(e, units, vid, v, AL.stride, L, ac_min_blocks(v.NC), nullptr)) return -1;
   {
     long long nb = (batch->B + 255) / 256;
     k_fill_i32<<<(int)nb, 256, 0, s>>>(status, batch->B, AHK_ST_OK);

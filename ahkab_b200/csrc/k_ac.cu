@@ -1,6 +1,8 @@
 // k_ac.cu — AC kernels (ac.ac_analysis): unit = (instance, frequency chunk).  sm_100a.
 #include "kernels.cuh"
 
+// (NC = 16 at 4 blocks / 128 registers spills: measured 1.98 vs 1.89 ms on C1)
+
 namespace ahk {
 
 template <class V>

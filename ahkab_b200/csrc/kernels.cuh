@@ -14,6 +14,7 @@
 
 namespace ahk {
 
+// (tried and dropped: Var<10,5,2> for C3 — 1.2 KB of spills at 128 registers, 32 vs 22 ms)
 // Kernel variants (id, NC, R, G): NC matrix columns incl. the rhs (0 = run-time n,
 // shared-memory fallback), R rows per lane, G lanes per instance.  R*G >= n, NC > n.
 #define AHK_REAL_VARIANTS(X)                                                          \
@@ -34,6 +35,7 @@ namespace ahk {
 #endif
 // __launch_bounds__(128, min_blocks(NC)) caps the registers so that many blocks fit
 inline int real_min_blocks(int NC) { return NC <= 12 ? AHK_MINB : (NC <= 16 ? 3 : 2); }
+inline int ac_min_blocks(int NC) { return (NC > 0 && NC <= 8) ? 4 : ((NC == 0 || NC <= 16) ? 3 : 2); }
 
 struct VarInfo { int NC, R, G; };
 inline const VarInfo* real_variants() {
