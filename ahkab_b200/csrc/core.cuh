@@ -45,6 +45,7 @@ struct Grp {
   }
   static AHK_DEV int all(int pred, unsigned m) { return G > 1 ? __all_sync(m, pred) : pred; }
   static AHK_DEV int any(int pred, unsigned m) { return G > 1 ? __any_sync(m, pred) : pred; }
+  static AHK_DEV double bcast(double v, int src, unsigned m) { return __shfl_sync(m, v, src, G); }
   // group maximum of a 64-bit key: xor butterfly (measured faster on B200 than two
   // dependent 32-bit REDUX.MAX: c3 21.6 vs 30.8 ms, c4 217 vs 297 ms)
   static AHK_DEV unsigned long long kmax(unsigned long long k, unsigned m) {
@@ -73,6 +74,7 @@ struct Grp {  // host emulation (tests/hostemu): G == 1 only
   static double fmin_all(double v, unsigned) { return v; }
   static int all(int p, unsigned) { return p; }
   static int any(int p, unsigned) { return p; }
+  static double bcast(double v, int, unsigned) { return v; }
   static unsigned long long kmax(unsigned long long k, unsigned) { return k; }
   static void argmax(double&, int&, unsigned) {}
 };
@@ -317,7 +319,10 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
       double pv[NC > 0 ? NC : 1];
-      if (G > 1) {   // the owner lane publishes its row, everybody reads it back
+      if (G > 1 && R == 1) {   // one row per lane: the pivot row comes straight out of the
+#pragma unroll                 // owner's registers by shuffles (no shared-memory round trip)
+        for (int j = k; j < NC; j++) pv[j] = Grp<G>::bcast(a[0][j], own, c.mask);
+      } else if (G > 1) {   // the owner lane publishes its row, everybody reads it back
         double* buf = pvb + (k & 1) * NC;
         if (mine) {
 #pragma unroll

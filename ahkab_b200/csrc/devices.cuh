@@ -148,11 +148,20 @@ AHK_DEV void ekv_setup(const EkvP& m, double* k) {
 // q, measured over v in [-40, 590]); the last exponential is updated by its series.
 // Stateless and branch-uniform: every lane does the same work.
 AHK_DEV double ekv_q(double v) {
-  double y;
-  if (v > 2.0) y = log(0.5 * v);
-  else if (v < -2.0) y = v;
-  else y = -0.85 + v * (0.555 - 0.065 * v);
-  double E = exp(y);
+  double y, E;
+  if (v > 2.0) {
+    // y0 = ln(v/2) to single precision (enough for a start: Halley is cubic), and
+    // E0 = v/2 taken directly instead of exp(y0): one fast log, no exponential
+#ifdef __CUDACC__
+    y = (double)__logf((float)(0.5 * v));
+#else
+    y = (double)logf((float)(0.5 * v));
+#endif
+    E = 0.5 * v;
+  } else {
+    y = v < -2.0 ? v : -0.85 + v * (0.555 - 0.065 * v);
+    E = exp(y);
+  }
   {
     double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
     double d = 2.0 * f * f1 / (2.0 * f1 * f1 - f * 2.0 * E);

@@ -11,6 +11,17 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests', 'hoste
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+    # fresh checkout: build the CUDA library (nvcc cross-compiles without a GPU), the
+    # oracle and the host-emulation library once, like __graft_entry__.build() does
+    import subprocess
+    for lib, script in ((os.path.join(ROOT, 'ahkab_b200', 'lib', 'libahkab_b200.so'),
+                         os.path.join(ROOT, 'ahkab_b200', 'csrc', 'build.sh')),
+                        (os.path.join(ROOT, 'oracle', '_build', 'libahk_oracle.so'),
+                         os.path.join(ROOT, 'oracle', 'build.sh')),
+                        (os.path.join(ROOT, 'tests', 'hostemu', '_build', 'libahk_hostemu.so'),
+                         os.path.join(ROOT, 'tests', 'hostemu', 'build.sh'))):
+        if not os.path.exists(lib):
+            subprocess.check_call(['sh', script], stdout=subprocess.DEVNULL)
 
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
