@@ -605,35 +605,45 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
     }
   }
   Grp<G>::sync(c.mask);
-  int n1 = 0, n2 = 0, m1 = 0, m2 = 0, status;
-  int s1 = dc_solve<V>(c, o.gmin, false, 0.0, o.dc_max_nr_iter, &n1, &m1);
+  // the two passes share ONE dc_solve call site (not unrolled): the Newton loop, the device
+  // models and the unrolled solve are instantiated once per kernel — instruction-cache
+  // misses were the largest stall of the C2 kernel when each pass had its own copy
+  int n1 = 0, n2 = 0, m1 = 0, m2 = 0, s1 = 0, s2 = 0, status;
+  double* r1 = c.sm + c.L->xs;   // residual of pass 1 (kept for PASS2_FAIL)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    int it = 0, me = 0;
+    const int sres = dc_solve<V>(c, pass == 0 ? o.gmin : 0.0, false, 0.0, o.dc_max_nr_iter, &it, &me);
+    if (pass == 0) {
+      s1 = sres; n1 = it; m1 = me;
+      if (!s1) break;
+      const double* res = c.sm + c.L->res;
+      for (int i = c.sub; i < n; i += G) { x1[i] = x[i]; r1[i] = res[i]; }
+      Grp<G>::sync(c.mask);
+    } else {
+      s2 = sres; n2 = it; m2 = me;
+    }
+  }
   if (!s1) {
     *iters = n1;
     status = (m1 << 1);
     const double qnan = nan("");
     for (int i = c.sub; i < n; i += G) x[i] = qnan;
+  } else if (!s2) {
+    double* resw = c.sm + c.L->res;
+    for (int i = c.sub; i < n; i += G) { x[i] = x1[i]; resw[i] = r1[i]; }
+    *iters = n1;
+    status = AHK_ST_OK | AHK_ST_PASS2_FAIL | (m1 << 1);
   } else {
-    double* r1 = c.sm + c.L->xs;   // residual of pass 1 (kept for PASS2_FAIL)
-    const double* res = c.sm + c.L->res;
-    for (int i = c.sub; i < n; i += G) { x1[i] = x[i]; r1[i] = res[i]; }
-    Grp<G>::sync(c.mask);
-    int s2 = dc_solve<V>(c, 0.0, false, 0.0, o.dc_max_nr_iter, &n2, &m2);
-    if (!s2) {
-      double* resw = c.sm + c.L->res;
-      for (int i = c.sub; i < n; i += G) { x[i] = x1[i]; resw[i] = r1[i]; }
-      *iters = n1;
-      status = AHK_ST_OK | AHK_ST_PASS2_FAIL | (m1 << 1);
-    } else {
-      *iters = n1 + n2;
-      int bad = 0;
-      for (int i = c.sub; i < n; i += G) {   // results.py:493-523
-        bool isv = i < p.nv1;
-        double er = isv ? o.ver : o.ier, ea = isv ? o.vea : o.iea;
-        if (fabs(x[i] - x1[i]) > er * fmax(fabs(x1[i]), fabs(x[i])) + ea) bad = 1;
-      }
-      status = AHK_ST_OK | (m2 << 1);
-      if (Grp<G>::any(bad, c.mask)) status |= AHK_ST_GMIN_CHECK;
+    *iters = n1 + n2;
+    int bad = 0;
+    for (int i = c.sub; i < n; i += G) {   // results.py:493-523
+      bool isv = i < p.nv1;
+      double er = isv ? o.ver : o.ier, ea = isv ? o.vea : o.iea;
+      if (fabs(x[i] - x1[i]) > er * fmax(fabs(x1[i]), fabs(x[i])) + ea) bad = 1;
     }
+    status = AHK_ST_OK | (m2 << 1);
+    if (Grp<G>::any(bad, c.mask)) status |= AHK_ST_GMIN_CHECK;
   }
   if (c.singular) status |= AHK_ST_SINGULAR;
   Grp<G>::sync(c.mask);
