@@ -7,4 +7,5 @@ ncu --set full --clock-control none --import-source on -k regex:$pat -s 1 -c 1 -
   python tools/ncu_target.py "$@" > gpurun_out/ncu_$tag.log 2>&1
 python tools/ncu_summary.py /tmp/$tag.ncu-rep > gpurun_out/sum_$tag.txt 2>&1
 python tools/ncu_lines.py /tmp/$tag.ncu-rep 70 > gpurun_out/lines_$tag.txt 2>&1
+python tools/ncu_lines.py /tmp/$tag.ncu-rep 40 stall_no_inst > gpurun_out/noinst_$tag.txt 2>&1
 ls -la /tmp/$tag.ncu-rep
