@@ -238,7 +238,7 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     for (int k = 0; k < p.nsrc; k++) {
       const SrcOp& s = p.src[k];
       if (!s.has_ac) continue;
-      double mag = c.PP(s.ppb + 1), ph = c.PP(s.ppb + 2);
+      double mag = c.P(s.pbase + 1), ph = c.P(s.pbase + 2);   // from HBM, once per instance
       cd v = {mag * cos(ph), mag * sin(ph)};
       if (s.is_v) Nac[s.row0] = cd{-1.0 * v.re, -1.0 * v.im};
       else {

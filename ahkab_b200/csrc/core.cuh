@@ -134,8 +134,8 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   const int G = V::G;
   double* Pv = c.sm + c.L->Pv;
   for (int s = c.sub; s < p.npersist; s += G) Pv[s] = c.P(p.pstage[s]);
-  if (V::NC > 0) {   // the dense staging matrix is zeroed once: only the sparsity
-    double* A = c.A();   // pattern (and the rhs column) is rewritten per iteration
+  if (V::NC > 0 && V::R == 1) {   // staging rows are zeroed once: only the sparsity
+    double* A = c.A();              // pattern is rewritten per iteration
     for (int i = c.sub; i < p.n * c.L->RS; i += G) A[i] = 0.0;
   }
   Grp<V::G>::sync(c.mask);
@@ -265,11 +265,15 @@ AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
   const double* x = c.x();
   const double* Bv = c.sm + c.L->Bv;
   const double* dout = c.sm + c.L->dout;
+  const double* Dv = c.sm + c.L->Dv;
+  const bool tran = Dv != Bv;          // transient layout: the matrix is Mv + C1 D (+ Gmin)
+  const double C1 = c.C1;
   double s = 0.0;
   const int k1 = p.row_ptr[r + 1];
   int q = p.nl_ptr[p.row_ptr[r]];
   for (int k = p.row_ptr[r]; k < k1; k++) {
     double v = Bv[k];
+    if (tran) v += C1 * Dv[k];
     const int pc = p.pcd[k];
     const int col = pc & 0x7fff;
     if (pc & 0x8000) v += c.gadd;
@@ -424,7 +428,13 @@ AHK_DEV int assemble_solve(Ctx& c) {
     for (int s = 0; s < R; s++) {
       const int r = c.sub + G * s;
       if (r < n) {
-        double* Ar = A + r * RS;
+        // R == 1: the lane's own staging row, zeroed once (only the pattern is rewritten);
+        // R > 1: ONE scratch row per lane, cleared before each of its rows
+        double* Ar = A + (R == 1 ? r : c.sub) * RS;
+        if (R > 1) {
+#pragma unroll
+          for (int j = 0; j < NC - 1; j++) Ar[j] = 0.0;
+        }
         a[s][NC - 1] = assemble_row(c, r, Ar);
 #pragma unroll
         for (int j = 0; j < NC - 1; j++) a[s][j] = Ar[j];
@@ -531,7 +541,7 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
       for (int k = 0; k < p.nsrc; k++) {
         const SrcOp& s = p.src[k];
         if (!s.tf) continue;
-        double v = tf_eval(s.tf, c.sm + c.L->Pv + s.ppb + 3, time);
+        double v = tf_eval(s.tf, c.sm + c.L->Pv + s.ppb + 1, time);
         if (s.is_v) Nd[s.row0] += -1 * v;
         else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
       }
@@ -550,17 +560,7 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
     if (enabled == 1) g = gmin_step_value(gidx);   // replaces Gmin (dc_analysis.py:262-269,452-455)
     else if (enabled == 2) f = source_step_value(sidx);
     Grp<G>::sync(c.mask);
-    if (Bv != Mv) {   // transient layout: Bv = Mv + C1 D + Gmin, built per attempt
-      for (int k = c.sub; k < p.npos; k += G) {
-        double v = Mv[k];
-        if (with_tran) v += c.C1 * Dv[k];
-        if (p.pdiag[k]) v += g;
-        Bv[k] = v;
-      }
-      c.gadd = 0.0;
-    } else {
-      c.gadd = g;     // OP/DC layout: Gmin is added while assembling
-    }
+    c.gadd = g;     // Gmin (and C1 D in a transient) are added while assembling
     for (int i = c.sub; i < n; i += G) T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + (with_tran ? Ntr[i] : 0.0);
     Grp<G>::sync(c.mask);
     int it = 0;

@@ -357,10 +357,10 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
                  int32_t* status, cudaStream_t s) {
   int vid;
   if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
-                   [&](const VarInfo& q) { return make_layout(e->H, MODE_OP, 0, 0, q.G, q.NC).stride; }, &vid))
+                   [&](const VarInfo& q) { return make_layout(e->H, MODE_OP, 0, 0, q.G, q.NC, q.R).stride; }, &vid))
     return -1;
   const VarInfo& v = real_variants()[vid];
-  Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC);
+  Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC, v.R);
   Launch L;
   if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
   KDc k;
@@ -508,11 +508,11 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   if (set_batch(e, batch, s)) return -1;
   int vid;
   if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
-                   [&](const VarInfo& q) { return make_layout(e->H, MODE_TRAN, method, use_step_control, q.G, q.NC).stride; },
+                   [&](const VarInfo& q) { return make_layout(e->H, MODE_TRAN, method, use_step_control, q.G, q.NC, q.R).stride; },
                    &vid))
     return -1;
   const VarInfo& v = real_variants()[vid];
-  Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC);
+  Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC, v.R);
   Launch L;
   if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
   KTran k;

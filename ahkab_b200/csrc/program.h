@@ -18,7 +18,7 @@ struct LinOp {      // one linear element's contribution to MNA (Mv) or D (Dv)
 
 struct SrcOp {      // independent source: N, Tt(t), Nac
   int is_v, elem, pbase, tf, has_ac;
-  int ppb;          // first PERSISTENT slot of [dc, |ac|, arg(ac)] (+ waveform block)
+  int ppb;          // first PERSISTENT slot of [dc] (+ waveform block)
   int ntf;          // slots of the waveform block (0, 8, or 4 + 2*npts for pwl)
   int row0, row1;   // V: row0 = KVL row; I: rows of n1, n2 (-1 = ground)
 };

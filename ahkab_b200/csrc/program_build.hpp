@@ -208,7 +208,10 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
       else { s.row0 = e.n1 - 1; s.row1 = e.n2 - 1; }
       s.ntf = !e.tf ? 0 : (e.tf == AHK_TF_PWL ? 4 + 2 * (int)c->nominal[e.pbase + 3] : 8);
       if (e.tf == AHK_TF_PWL && (int)c->nominal[e.pbase + 3] < 2) throw std::runtime_error("pwl needs at least 2 points");
-      s.ppb = persist(e.pbase, 3 + s.ntf);
+      // persistent block of a source: its dc value, then its waveform block; |ac| and
+      // arg(ac) are read from HBM by the AC kernel (once per instance)
+      s.ppb = persist(e.pbase, 1);
+      if (s.ntf) persist(e.pbase + 3, s.ntf);
       if (s.tf) ntd++;
       if (s.has_ac) nac++;
       H.src.push_back(s);
@@ -312,7 +315,7 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   h.ntd = ntd; h.nac = nac; h.ndev = (int)H.dev.size(); h.ndout = ndout;
   h.nlock = (int)H.lock.size() / 2; h.nguess = ng; h.nparams = c->n_params;
   h.npersist = 0;
-  for (auto& so : H.src) h.npersist = std::max(h.npersist, so.ppb + 3 + so.ntf);
+  for (auto& so : H.src) h.npersist = std::max(h.npersist, so.ppb + 1 + so.ntf);
   for (auto& dv : H.dev) {
     if (dv.pmb >= 0) h.npersist = std::max(h.npersist, dv.pmb + (dv.type == AHK_MOSQ ? 7 : 4));
   }
@@ -334,7 +337,7 @@ enum { MODE_OP = 0, MODE_TRAN = 1 };
 // Every array is allocated only when the mode / variant / circuit needs it: the
 // bytes per instance bound how many instances are resident per SM.
 inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_control, int G,
-                          int NC = 0) {
+                          int NC = 0, int R = 1) {
   const Prog& h = H.hdr;
   Layout L; std::memset(&L, 0, sizeof L);
   const int n = h.n;
@@ -342,16 +345,20 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   L.ARS = L.RS;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
-  L.A = take(n * L.RS);
+  // register variants with several rows per lane stage through one scratch row per lane
+  L.A = take((NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS);
   L.x = take(n); L.dx = take(n); L.T = take(n); L.res = take(n);
   L.Mv = take(h.npos);
-  // OP/DC: the matrix is Mv plus Gmin on the node diagonals, added on the fly
-  L.Bv = mode == MODE_TRAN ? take(h.npos) : L.Mv;
+  // the matrix values are formed while assembling: Mv (+ C1 Dv in a transient) plus Gmin
+  // on the node diagonals; Bv is kept as an alias of Mv
+  L.Bv = L.Mv;
   L.Nc = take(n);
   L.Nd = h.ntd > 0 ? take(n) : L.Nc;      // N + Tt(t); no waveforms: N itself
   L.dout = take(h.ndout); L.dst = take(H.nst);
-  L.xs = take(n);
-  L.x1 = mode == MODE_TRAN ? L.xs : take(n);   // x1: pass-1 solution of the OP only
+  // OP: xs = residual of pass 1, x1 = solution of pass 1.  Transient: xs = x(tstart), used
+  // only before the first accepted step, when the history ring still holds it in slot 0
+  // (aliased below); x1 is not used.
+  if (mode != MODE_TRAN) { L.xs = take(n); L.x1 = take(n); }
   L.bytes = take(NC > 0 ? 0 : 16);
   L.Pv = take(h.npersist); L.dcon = take(H.ncon);
   L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);
@@ -370,7 +377,9 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
     L.buflen = bl + 1;
     L.Dv = take(h.npos); L.Ntr = take(n); L.xacc = take(n);
     L.hx = take(L.buflen * n); L.hdx = take(n); L.ht = take(L.buflen);
-    L.C0 = take(n); L.pred = take(n);
+    L.xs = L.hx; L.x1 = L.hx;
+    L.C0 = take(n);
+    L.pred = use_step_control ? take(n) : L.C0;   // the predictor exists only with LTE control
   } else {
     L.Dv = L.Mv; L.Ntr = L.Nd; L.xacc = L.xs;
     L.hx = L.hdx = L.ht = L.C0 = L.pred = 0;

@@ -30,7 +30,7 @@ struct Emu {
     set_vary_slots(H, n_vary, slots);
     p = H.view();
     copy_opts(opts, o);
-    L = make_layout(H, mode, method, usc, 1, variant_nc());
+    L = make_layout(H, mode, method, usc, 1, variant_nc(), variant_nc() ? variant_nc() - 1 : 1);
     sm.assign(L.stride + 64, 0.0);
   }
   Ctx ctx(const double* vary, long long B, long long b) {
