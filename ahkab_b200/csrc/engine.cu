@@ -66,6 +66,7 @@ struct ahk_engine {
   size_t blob_bytes = 0;
   Prog dprog;              // device-pointer view
   int* d_slot_vary = nullptr;
+  DevOp* d_dev = nullptr;  // device copy of the device table (its constant-block offsets follow the batch)
   std::vector<int> cur_slots;
   bool slots_valid = false;
   double* d_scratch = nullptr;   // sweep values / omegas
@@ -213,6 +214,7 @@ int upload_program(ahk_engine* e) {
   p.tx_sgn = (const signed char*)(d + o_txg);
   p.lin = (const LinOp*)(d + o_lin); p.src = (const SrcOp*)(d + o_src);
   p.dev = (const DevOp*)(d + o_dev); p.lock = (const int*)(d + o_lock);
+  e->d_dev = (DevOp*)(d + o_dev);
   p.guessG = (const double*)(d + o_gG); p.gslot = (const int*)(d + o_gs);
   p.gscale = (const double*)(d + o_gsc); p.gconst = (const double*)(d + o_gc);
   p.nominal = (const double*)(d + o_nom);
@@ -233,6 +235,8 @@ int set_batch(ahk_engine* e, const ahk_batch* b, cudaStream_t s) {
   CK(cudaStreamSynchronize(s));   // in-flight kernels may still read the old table
   CK(cudaMemcpyAsync(e->d_slot_vary, e->H.slot_vary.data(), e->H.slot_vary.size() * sizeof(int),
                      cudaMemcpyHostToDevice, s));
+  if (!e->H.dev.empty())
+    CK(cudaMemcpyAsync(e->d_dev, e->H.dev.data(), e->H.dev.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s));
   e->cur_slots = slots;
   e->slots_valid = true;
   return 0;

@@ -14,7 +14,8 @@
 
 namespace ahk {
 
-// (tried and dropped: Var<10,5,2> for C3 — 1.2 KB of spills at 128 registers, 32 vs 22 ms)
+// (tried and dropped: Var<6,2,4> for C4 — one wave instead of 1.7 but 208 vs 202 ms, the
+// kernel is issue bound;  Var<10,5,2> for C3 — 1.2 KB of spills at 128 registers, 32 vs 22 ms)
 // Kernel variants (id, NC, R, G): NC matrix columns incl. the rhs (0 = run-time n,
 // shared-memory fallback), R rows per lane, G lanes per instance.  R*G >= n, NC > n.
 #define AHK_REAL_VARIANTS(X)                                                          \

@@ -66,6 +66,8 @@ inline int dout_count(int type) {
   return 0;
 }
 
+inline void assign_constant_blocks(HostProg& H);
+
 inline void build_program(const ahk_circuit* c, HostProg& H) {
   if (!c || c->abi_version != AHK_ABI_VERSION) throw std::runtime_error("ahk_circuit: bad abi_version");
   const int nn = c->n_nodes, nv1 = nn - 1, n = nv1 + c->n_vde;
@@ -228,9 +230,7 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
     H.nonlinear = true;
     DevOp d; std::memset(&d, 0, sizeof d);
     d.type = e.type; d.pbase = e.pbase; d.mbase = e.mbase; d.flags = e.flags;
-    d.dout = ndout; d.active = 1; d.con = -1; d.ppb = d.pmb = d.st = -1;
-    if (e.type == AHK_EKV) { d.con = H.ncon; H.ncon += 16; }
-    if (e.type == AHK_D) { d.con = H.ncon; H.ncon += 10; }
+    d.dout = ndout; d.active = 1; d.con = -1; d.ppb = d.pmb = d.st = -1;   // con: assign_constant_blocks
     if (e.type == AHK_MOSQ) { d.ppb = persist(e.pbase, 6); d.pmb = persist(e.mbase, 7); }
     if (e.type == AHK_SW) { d.ppb = persist(e.pbase, 1); d.pmb = persist(e.mbase, 4); }
     if (e.type == AHK_D || e.type == AHK_SW) { d.st = H.nst; H.nst += 2; }
@@ -306,6 +306,7 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   if (H.pstage.empty()) H.pstage.push_back(0);
   H.nominal.assign(c->nominal, c->nominal + c->n_params);
   H.slot_vary.assign(c->n_params > 0 ? c->n_params : 1, -1);
+  assign_constant_blocks(H);
   // keep vectors non-empty so data() is a valid pointer everywhere
   if (H.nl_src.empty()) { H.nl_src.push_back(0); H.nl_sgn.push_back(0); }
   if (H.tx_src.empty()) { H.tx_src.push_back(0); H.tx_sgn.push_back(0); }
@@ -322,12 +323,38 @@ inline void build_program(const ahk_circuit* c, HostProg& H) {
   for (int j = 0; j < ng; j++) h.npersist = std::max(h.npersist, H.gpslot[j] + 1);
 }
 
+// Per-instance device-constant blocks (EKV 16 doubles, diode 10).  Devices that share a
+// model and have identical, un-varied own parameters (e.g. the three NMOS of a ring
+// oscillator) share ONE block: fewer shared-memory bytes per instance.  Depends on which
+// slots the batch varies, so it is recomputed whenever they change.
+inline void assign_constant_blocks(HostProg& H) {
+  H.ncon = 0;
+  std::map<std::vector<double>, int> seen;
+  for (auto& d : H.dev) {
+    if (d.type != AHK_EKV && d.type != AHK_D) { d.con = -1; continue; }
+    const int own = d.type == AHK_EKV ? 4 : 1, size = d.type == AHK_EKV ? 16 : 10;
+    bool varied = false;
+    std::vector<double> key;
+    key.push_back(d.type); key.push_back(d.mbase); key.push_back(d.flags);
+    for (int i = 0; i < own; i++) {
+      if (H.slot_vary[d.pbase + i] >= 0) varied = true;
+      key.push_back(H.nominal[d.pbase + i]);
+    }
+    auto it = varied ? seen.end() : seen.find(key);
+    if (it != seen.end()) { d.con = it->second; continue; }
+    d.con = H.ncon;
+    H.ncon += size;
+    if (!varied) seen[key] = d.con;
+  }
+}
+
 inline void set_vary_slots(HostProg& H, int n_vary, const int* slots) {
   std::fill(H.slot_vary.begin(), H.slot_vary.end(), -1);
   for (int k = 0; k < n_vary; k++) {
     if (slots[k] < 0 || slots[k] >= H.hdr.nparams) throw std::runtime_error("vary slot out of range");
     H.slot_vary[slots[k]] = k;
   }
+  assign_constant_blocks(H);
 }
 
 enum { MODE_OP = 0, MODE_TRAN = 1 };
