@@ -502,8 +502,13 @@ def main():
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
+        # stdout must carry exactly the one JSON line: NCCL's version banner (NCCL_DEBUG =
+        # VERSION / WARN, the image default) goes to stdout, so it is switched off unless
+        # the caller asked for INFO / TRACE output, which is sent to stderr
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'WARN'):
+            os.environ['NCCL_DEBUG'] = 'NONE'
+        else:
+            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=device)
     warmup = max(3, args.warmup)
     timer = Timer(dist_on, device)
