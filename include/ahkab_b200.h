@@ -217,7 +217,10 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0,
 /* DC sweep — replaces dc_analysis.dc_analysis (ahkab/dc_analysis.py:461-595):
  * for every sweep value (host array, the caller builds it with the
  * reference's cumulative lin/log iterators, ahkab/utilities.py:246-378) the
- * full OP procedure, warm-started from the previous point.
+ * full OP procedure, warm-started from the previous point.  (Linear circuits with
+ * n > 64 take the sparse large-circuit path: both matrices are factored once per
+ * instance, the points are solved independently — each is one exact Newton step —
+ * and x0 / use_guess do not influence the result beyond rounding.)
  *   src_elem  index in circ->elems of the swept V or I source
  *   x_out   device [B][npts][n]; iters/status device [B][npts] */
 int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem,
