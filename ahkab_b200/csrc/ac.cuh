@@ -153,43 +153,61 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
       const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
-      cd pv[NC > 0 ? NC : 1];
-      if (G > 1) {
-        cd* buf = pvb + (k & 1) * NC;
-        if (mine) {
-#pragma unroll
-          for (int s = 0; s < R; s++)
-            if (slot == s) {
-#pragma unroll
-              for (int j = k; j < NC; j++) buf[j] = a[s][j];
-            }
-        }
-        Grp<G>::sync(c.mask);
-#pragma unroll
-        for (int j = k; j < NC; j++) pv[j] = buf[j];
-      } else {
-#pragma unroll
-        for (int j = k; j < NC; j++) {
-          cd t = a[0][j];
-#pragma unroll
-          for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
-          pv[j] = t;
-        }
-      }
-      if (mine) {
-        usedm |= 1u << slot;
-#pragma unroll
-        for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
-      }
-      const cd inv = crecip(pv[k]);
-#pragma unroll
-      for (int s = 0; s < R; s++) {
-        cd l = cmul(a[s][k], inv);
-        if (mine && slot == s) l = cd{0.0, 0.0};
+      if (G > 1 && R == 1) {
+        // one row per lane: every element of the pivot row is fetched from the owner's
+        // registers right where it is used (4 shuffles per complex element) — no pivot-row
+        // copy in registers, no shared-memory round trip, no barrier
+        const cd pk = cd{Grp<G>::bcast(a[0][k].re, own, c.mask), Grp<G>::bcast(a[0][k].im, own, c.mask)};
+        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
+        const cd inv = crecip(pk);
+        cd l = cmul(a[0][k], inv);
+        if (mine) l = cd{0.0, 0.0};
 #pragma unroll
         for (int j = k + 1; j < NC; j++) {
-          a[s][j].re -= l.re * pv[j].re - l.im * pv[j].im;
-          a[s][j].im -= l.re * pv[j].im + l.im * pv[j].re;
+          const double pre = Grp<G>::bcast(a[0][j].re, own, c.mask);
+          const double pim = Grp<G>::bcast(a[0][j].im, own, c.mask);
+          a[0][j].re -= l.re * pre - l.im * pim;
+          a[0][j].im -= l.re * pim + l.im * pre;
+        }
+      } else {
+        cd pv[NC > 0 ? NC : 1];
+        if (G > 1) {
+          cd* buf = pvb + (k & 1) * NC;
+          if (mine) {
+#pragma unroll
+            for (int s = 0; s < R; s++)
+              if (slot == s) {
+#pragma unroll
+                for (int j = k; j < NC; j++) buf[j] = a[s][j];
+              }
+          }
+          Grp<G>::sync(c.mask);
+#pragma unroll
+          for (int j = k; j < NC; j++) pv[j] = buf[j];
+        } else {
+#pragma unroll
+          for (int j = k; j < NC; j++) {
+            cd t = a[0][j];
+#pragma unroll
+            for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
+            pv[j] = t;
+          }
+        }
+        if (mine) {
+          usedm |= 1u << slot;
+#pragma unroll
+          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+        }
+        const cd inv = crecip(pv[k]);
+#pragma unroll
+        for (int s = 0; s < R; s++) {
+          cd l = cmul(a[s][k], inv);
+          if (mine && slot == s) l = cd{0.0, 0.0};
+#pragma unroll
+          for (int j = k + 1; j < NC; j++) {
+            a[s][j].re -= l.re * pv[j].re - l.im * pv[j].im;
+            a[s][j].im -= l.re * pv[j].im + l.im * pv[j].re;
+          }
         }
       }
     }

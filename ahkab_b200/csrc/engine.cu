@@ -540,6 +540,7 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
   {
     long long want = (long long)e->sm_count * 64;
     while (nchunks < npts && batch->B * nchunks < want && npts / (nchunks * 2) >= 4) nchunks *= 2;
+    if (const char* f = getenv("AHK_AC_CHUNKS")) nchunks = std::max(1, std::min(npts, atoi(f)));   // tuning
   }
   long long units = batch->B * nchunks;
   int vid;

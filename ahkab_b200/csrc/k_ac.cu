@@ -6,7 +6,7 @@
 namespace ahk {
 
 template <class V>
-__global__ void __launch_bounds__(128, (V::NC > 0 && V::NC <= 8) ? 4 : ((V::NC == 0 || V::NC <= 16) ? 3 : 2)) k_ac(const __grid_constant__ KAc k) {
+__global__ void __launch_bounds__(128, (V::NC > 0 && V::NC <= 16) ? 4 : (V::NC == 0 ? 3 : 2)) k_ac(const __grid_constant__ KAc k) {
   Ctx c; long long u;
   if (!make_ctx<V::G>(c, &k.p, &k.o, &k.AL.L, k.AL.stride, k.vary, k.B, k.B * k.nchunks, u)) return;
   c.inst = u / k.nchunks;

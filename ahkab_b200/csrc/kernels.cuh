@@ -36,7 +36,7 @@ namespace ahk {
 #endif
 // __launch_bounds__(128, min_blocks(NC)) caps the registers so that many blocks fit
 inline int real_min_blocks(int NC) { return NC <= 12 ? AHK_MINB : (NC <= 16 ? 3 : 2); }
-inline int ac_min_blocks(int NC) { return (NC > 0 && NC <= 8) ? 4 : ((NC == 0 || NC <= 16) ? 3 : 2); }
+inline int ac_min_blocks(int NC) { return (NC > 0 && NC <= 16) ? 4 : (NC == 0 ? 3 : 2); }
 
 struct VarInfo { int NC, R, G; };
 inline const VarInfo* real_variants() {
