@@ -322,43 +322,51 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
       const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
-      double pv[NC > 0 ? NC : 1];
-      if (G > 1 && R == 1) {   // one row per lane: the pivot row comes straight out of the
-#pragma unroll                 // owner's registers by shuffles (no shared-memory round trip)
-        for (int j = k; j < NC; j++) pv[j] = Grp<G>::bcast(a[0][j], own, c.mask);
-      } else if (G > 1) {   // the owner lane publishes its row, everybody reads it back
-        double* buf = pvb + (k & 1) * NC;
-        if (mine) {
+      if (G > 1 && R == 1) {
+        // one row per lane: every element of the pivot row is fetched from the owner's
+        // registers right where it is used — no pivot-row copy in registers, no
+        // shared-memory round trip, no barrier
+        const double pk = Grp<G>::bcast(a[0][k], own, c.mask);
+        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
+        const double l = mine ? 0.0 : a[0][k] * (1.0 / pk);
 #pragma unroll
-          for (int s = 0; s < R; s++)
-            if (slot == s) {
-#pragma unroll
-              for (int j = k; j < NC; j++) buf[j] = a[s][j];
-            }
-        }
-        Grp<G>::sync(c.mask);
-#pragma unroll
-        for (int j = k; j < NC; j++) pv[j] = buf[j];
+        for (int j = k + 1; j < NC; j++) a[0][j] -= l * Grp<G>::bcast(a[0][j], own, c.mask);
       } else {
+        double pv[NC > 0 ? NC : 1];
+        if (G > 1) {   // the owner lane publishes its row, everybody reads it back
+          double* buf = pvb + (k & 1) * NC;
+          if (mine) {
 #pragma unroll
-        for (int j = k; j < NC; j++) {
-          double t = a[0][j];
+            for (int s = 0; s < R; s++)
+              if (slot == s) {
 #pragma unroll
-          for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
-          pv[j] = t;
+                for (int j = k; j < NC; j++) buf[j] = a[s][j];
+              }
+          }
+          Grp<G>::sync(c.mask);
+#pragma unroll
+          for (int j = k; j < NC; j++) pv[j] = buf[j];
+        } else {
+#pragma unroll
+          for (int j = k; j < NC; j++) {
+            double t = a[0][j];
+#pragma unroll
+            for (int s = 1; s < R; s++) if (slot == s) t = a[s][j];
+            pv[j] = t;
+          }
         }
-      }
-      if (mine) {
-        usedm |= 1u << slot;
+        if (mine) {
+          usedm |= 1u << slot;
 #pragma unroll
-        for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
-      }
-      const double inv = 1.0 / pv[k];
+          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+        }
+        const double inv = 1.0 / pv[k];
 #pragma unroll
-      for (int s = 0; s < R; s++) {
-        const double l = (mine && slot == s) ? 0.0 : a[s][k] * inv;
+        for (int s = 0; s < R; s++) {
+          const double l = (mine && slot == s) ? 0.0 : a[s][k] * inv;
 #pragma unroll
-        for (int j = k + 1; j < NC; j++) a[s][j] -= l * pv[j];
+          for (int j = k + 1; j < NC; j++) a[s][j] -= l * pv[j];
+        }
       }
     }
   }
