@@ -8,17 +8,22 @@
 // triangular solves.  What changed is where the work happens:
 //
 //  * factorisation: each row is a small unordered slot list (column, value) in shared
-//    memory and each column a bitmap of the rows that hold an entry in it.  A pivot step
-//    reads the column's bitmap, looks the few candidate values up in their rows, and
+//    memory and each column a small list of the rows that hold an entry in it.  A pivot
+//    step reads the column's list, looks the few candidate values up in their rows, and
 //    updates / appends the few fill-ins — a few hundred cycles, no global memory, where
 //    biglin.cuh scanned a dense n-vector out of L2 per step (C5: 2 x 257 steps x 257 rows).
-//    A row that outgrows its slots sends the instance to the biglin.cuh kernel (overflow
-//    list, second launch that exits at once when the list is empty).
+//    A row or column that outgrows its slots sends the instance to the biglin.cuh kernel
+//    (overflow list, second launch that exits at once when the list is empty).
+//  * shared memory per warp bounds the warps resident per SM, and the kernel is latency
+//    bound: 52 KB (row slots 12 deep, column bitmaps, iterates in shared memory) gave 4
+//    warps/SM and 10.9 ms on C5; 30 KB (slots 6 deep, column lists, iterates in x_out) gives
+//    7 warps/SM = exactly 4 waves of the 4096 instances and 6.3 ms.
 //  * solves: the sweep points are independent for a linear circuit (the reference warm
 //    starts point k from point k-1, which only changes the start of an exact one-step
 //    Newton), so up to PC points are solved AT ONCE, one lane per right-hand side, each
 //    lane running its own forward / backward substitution with no warp synchronisation;
-//    L and U are streamed from the per-warp global lists (warp-uniform loads).
+//    L and U are streamed from the per-warp global lists (warp-uniform loads); the
+//    iterates live in their rows of x_out (L2), only the right-hand sides in shared memory.
 #pragma once
 #include "biglin.cuh"
 
@@ -47,12 +52,13 @@ inline Big2Smem big2_smem(int n, int npos, int SC, int PC, int W) {
   auto take = [&](int bytes) { int o = off; off += (bytes + 15) & ~15; return o; };
   s.Mv = take(8 * npos); s.prow = take(2 * 2 * n); s.nLc = take(2 * 2 * n); s.nUc = take(2 * 2 * n);
   s.un = off;
-  s.sval = take(8 * n * SC); s.pend_v = take(8 * n); s.pu_v = take(8 * (SC + 1));
-  s.scol = take(2 * n * SC); s.scnt = take(n); s.cbits = take(4 * n * W); s.used = take(4 * W);
-  s.pend_r = take(2 * n); s.pu_c = take(2 * (SC + 1));
+  // (cbits = the column lists: SC row indices per column + a 32-bit count per column)
+  s.sval = take(8 * n * SC); s.pend_v = take(8 * 32); s.pu_v = take(8 * (SC + 1));
+  s.scol = take(2 * n * SC); s.scnt = take(n); s.cbits = take(2 * n * SC + 4 * n); s.used = take(4 * W);
+  s.pend_r = take(2 * 32); s.pu_c = take(2 * (SC + 1));
   int fac_end = off;
   off = s.un;
-  s.b = take(8 * n * PC); s.x1 = take(8 * n * PC);
+  s.b = take(8 * n * PC); s.x1 = s.b;   // the iterates live in x_out (global)
   s.total = off > fac_end ? off : fac_end;
   return s;
 }
@@ -72,10 +78,12 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
   double* pu_v = (double*)(bsm + S.pu_v);
   unsigned short* scol = (unsigned short*)(bsm + S.scol);
   unsigned char* scnt = bsm + S.scnt;
-  unsigned* cbits = (unsigned*)(bsm + S.cbits); unsigned* used = (unsigned*)(bsm + S.used);
+  int* ccnt = (int*)(bsm + S.cbits);                                  // [n] entries per column
+  unsigned short* ccol = (unsigned short*)(bsm + S.cbits + 4 * n);    // [n][SC] rows of a column
+  unsigned* used = (unsigned*)(bsm + S.used);
   unsigned short* pend_r = (unsigned short*)(bsm + S.pend_r);
   unsigned short* pu_c = (unsigned short*)(bsm + S.pu_c);
-  double* bb = (double*)(bsm + S.b); double* x1 = (double*)(bsm + S.x1);
+  double* bb = (double*)(bsm + S.b);
   double* Lv = k.Lv + (size_t)blockIdx.x * 2 * k.cap2;
   double* Uv = k.Uv + (size_t)blockIdx.x * 2 * k.cap2;
   unsigned short* Li = k.Li + (size_t)blockIdx.x * 2 * k.cap2;
@@ -113,74 +121,47 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
           sval[r * SC + t] = Mv[q0 + t] + ((m == 0 && p.pdiag[q0 + t]) ? k.o.gmin : 0.0);
         }
       }
-      for (int i = lane; i < n * W; i += 32) cbits[i] = 0u;
+      for (int i = lane; i < n; i += 32) ccnt[i] = 0;
       if (lane < W) used[lane] = 0u;
       ovf = __any_sync(FULL, ovf);
       if (ovf) break;
       __syncwarp();
       for (int q = lane; q < p.npos; q += 32) {
-        const int r = p.prowi[q];
-        atomicOr(&cbits[(int)p.pcol[q] * W + (r >> 5)], 1u << (r & 31));
+        const int col = p.pcol[q];
+        const int t = atomicAdd(&ccnt[col], 1);
+        if (t < SC) ccol[col * SC + t] = p.prowi[q]; else ovf = 1;
       }
+      ovf = __any_sync(FULL, ovf);
+      if (ovf) break;
       __syncwarp();
       int Lbase = m * k.cap2, Ubase = m * k.cap2;
       for (int kk = 0; kk < n; kk++) {
-        // candidate rows: entries of column kk in rows that are not pivot rows yet
-        unsigned word = lane < W ? (cbits[kk * W + lane] & ~used[lane]) : 0u;
-        const unsigned nzm = __ballot_sync(FULL, word != 0u);
-        int ncand = 0;
-        for (unsigned m2 = nzm; m2; m2 &= m2 - 1) ncand += __popc(__shfl_sync(FULL, word, __ffs(m2) - 1));
-        double best = -1.0, sv = 0.0;
-        int bi = -1;
-        if (ncand <= 8) {
-          // the usual case on circuit matrices: a handful of candidates.  Every lane walks
-          // them in ascending row order (warp-uniform), the slot look-up of each row is
-          // spread over the lanes; lane i keeps candidate i for the elimination.
-          int ci = 0, my_r = 0;
-          double my_v = 0.0;
-          for (unsigned m2 = nzm; m2; m2 &= m2 - 1) {
-            const int ww = __ffs(m2) - 1;
-            for (unsigned wv = __shfl_sync(FULL, word, ww); wv; wv &= wv - 1) {
-              const int r = ww * 32 + __ffs(wv) - 1;
-              const int c = scnt[r];
-              const bool hit = lane < c && scol[r * SC + lane] == kk;
-              const unsigned hb = __ballot_sync(FULL, hit);
-              const double v = hb ? __shfl_sync(FULL, lane < c ? sval[r * SC + lane] : 0.0, __ffs(hb) - 1) : 0.0;
-              const double a = fabs(v);
-              if (bi < 0 || a > best) { best = a; bi = r; sv = v; }
-              if (ci == lane) { my_r = r; my_v = v; }
-              ci++;
-            }
-          }
-          if (lane < ncand) { pend_r[lane] = (unsigned short)my_r; pend_v[lane] = my_v; }
-          __syncwarp();
-        } else {
-          const int cnt = __popc(word);
-          int incl = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-          {
-            int o = incl - cnt;
-            while (word) { const int b = __ffs(word) - 1; word &= word - 1; pend_r[o++] = (unsigned short)(lane * 32 + b); }
-          }
-          __syncwarp();
-          for (int i = lane; i < ncand; i += 32) {
-            const int r = pend_r[i];
-            double v = 0.0;
+        // candidate rows: the column's list, minus the rows that are pivot rows already;
+        // lane t looks candidate t up in its row
+        const int ncol = ccnt[kk];
+        int my_r = -1;
+        double my_v = 0.0;
+        if (lane < ncol) {
+          const int r = ccol[kk * SC + lane];
+          if (!((used[r >> 5] >> (r & 31)) & 1u)) {
+            my_r = r;
             const int c = scnt[r];
-            for (int t = 0; t < c; t++) if (scol[r * SC + t] == kk) { v = sval[r * SC + t]; break; }
-            pend_v[i] = v;
-            const double a = fabs(v);
-            if (bi < 0 || a > best) { best = a; bi = r; sv = v; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(FULL, best, o), osv = __shfl_xor_sync(FULL, sv, o);
-            const int oi = __shfl_xor_sync(FULL, bi, o);
-            const bool take = (oi >= 0) && (bi < 0 || ov > best || (ov == best && oi < bi));
-            if (take) { best = ov; bi = oi; sv = osv; }
+            for (int t = 0; t < c; t++) if (scol[r * SC + t] == kk) { my_v = sval[r * SC + t]; break; }
           }
         }
+        const unsigned cm = __ballot_sync(FULL, my_r >= 0);
+        const int ncand = __popc(cm);
+        if (my_r >= 0) { const int i = __popc(cm & lt); pend_r[i] = (unsigned short)my_r; pend_v[i] = my_v; }
+        double best = my_r >= 0 ? fabs(my_v) : -1.0, sv = my_v;
+        int bi = my_r;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(FULL, best, o), osv = __shfl_xor_sync(FULL, sv, o);
+          const int oi = __shfl_xor_sync(FULL, bi, o);
+          const bool take = (oi >= 0) && (bi < 0 || ov > best || (ov == best && oi < bi));
+          if (take) { best = ov; bi = oi; sv = osv; }
+        }
+        __syncwarp();
         if (bi < 0 || best == 0.0) { singular = 1; break; }
         if (Lbase + ncand > (m + 1) * k.cap2 || Ubase + SC + 1 > (m + 1) * k.cap2) { ovf = 1; break; }
         const double piv = sv, inv = 1.0 / piv;
@@ -235,7 +216,8 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
             if (t < c) sval[r * SC + t] -= l * u;
             else if (c < SC) {
               scol[r * SC + c] = (unsigned short)col; sval[r * SC + c] = 0.0 - l * u; c++;
-              atomicOr(&cbits[col * W + (r >> 5)], 1u << (r & 31));
+              const int t = atomicAdd(&ccnt[col], 1);
+              if (t < SC) ccol[col * SC + t] = (unsigned short)r; else ovf = 1;
             } else ovf = 1;
           }
           scnt[r] = (unsigned char)c;
@@ -263,13 +245,18 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
         }
         continue;
       }
-      // x1 <- x0 (zeros if none)
-      for (int i = lane; i < n * PC; i += 32) x1[i] = k.x0 ? k.x0[inst * n + i / PC] : 0.0;
+      // The iterate of each point lives in its own row of x_out (global, L2-resident):
+      // shared memory only holds the right-hand sides.  x <- x0 (zeros if none), coalesced.
+      double* xg = k.x_out + (inst * k.npts + k0) * n;      // [pc][n]
+      for (int j = 0; j < pc; j++)
+        for (int i = lane; i < n; i += 32) xg[(long long)j * n + i] = k.x0 ? k.x0[inst * n + i] : 0.0;
       __syncwarp();
       int bad = 0;
       for (int m = 0; m < 2; m++) {
+        const unsigned short* pr = prow + m * n;
         if (act) {
           const int j = lane;
+          const double* xj = xg + (long long)j * n;
           // b = -(M x + N): N first (dc_analysis.py:1004-1040), then the mat-vec
           for (int r = 0; r < n; r++) bb[r * PC + j] = 0.0;
           for (int s = 0; s < p.nsrc; s++) {
@@ -283,16 +270,13 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
             for (int r = 0; r < n; r++) {
               double s = 0.0;
               for (int q = p.row_ptr[r]; q < p.row_ptr[r + 1]; q++)
-                s += (Mv[q] + ((m == 0 && p.pdiag[q]) ? k.o.gmin : 0.0)) * x1[(int)p.pcol[q] * PC + j];
+                s += (Mv[q] + ((m == 0 && p.pdiag[q]) ? k.o.gmin : 0.0)) * xj[p.pcol[q]];
               // residuo = M.x + N = s - (-N)
               const double rr = s - bb[r * PC + j];
               bb[r * PC + j] = -rr;
               if (m == 1 && k.resid) k.resid[orow * n + r] = rr;
             }
-          } else if (m == 1 && k.resid) {
-            for (int r = 0; r < n; r++) k.resid[orow * n + r] = -bb[r * PC + j];
           }
-          const unsigned short* pr = prow + m * n;
           // forward: b[r] -= l * b[pivot row]
           int e = m * k.cap2;
           for (int kk = 0; kk < n; kk++) {
@@ -314,25 +298,28 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
             for (int t = 1; t <= cnt; t++) s += Uv[ue + t] * bb[(int)pr[Ui[ue + t]] * PC + j];
             bb[(int)pr[kk] * PC + j] = (bb[(int)pr[kk] * PC + j] - s) / Uv[ue];
           }
-          // x <- x + dx (td = 1: a linear circuit has no locked nodes); gmin_check on pass 2
-          for (int c = 0; c < n; c++) {
-            const double xo = x1[c * PC + j], xn = xo + bb[(int)pr[c] * PC + j];
-            if (m == 1) {   // results.py:493-523
+        }
+        __syncwarp();
+        // x <- x + dx (td = 1: a linear circuit has no locked nodes), all lanes, coalesced;
+        // gmin_check on pass 2 (results.py:493-523)
+        for (int j = 0; j < pc; j++) {
+          double* xj = xg + (long long)j * n;
+          int badj = 0;
+          for (int c = lane; c < n; c += 32) {
+            const double xo = xj[c], xn = xo + bb[(int)pr[c] * PC + j];
+            if (m == 1) {
               const bool isv = c < p.nv1;
               const double er = isv ? k.o.ver : k.o.ier, ea = isv ? k.o.vea : k.o.iea;
-              if (fabs(xn - xo) > er * fmax(fabs(xo), fabs(xn)) + ea) bad = 1;
+              if (fabs(xn - xo) > er * fmax(fabs(xo), fabs(xn)) + ea) badj = 1;
             }
-            x1[c * PC + j] = xn;
+            xj[c] = xn;
           }
+          badj = __any_sync(FULL, badj);
+          if (lane == j && badj) bad = 1;
         }
         __syncwarp();
       }
       if (act) { k.iters[orow] = 2; k.status[orow] = AHK_ST_OK | (bad ? AHK_ST_GMIN_CHECK : 0); }
-      // coalesced store of the pc solution rows
-      for (int j = 0; j < pc; j++) {
-        double* xo = k.x_out + (inst * k.npts + k0 + j) * n;
-        for (int i = lane; i < n; i += 32) xo[i] = x1[i * PC + j];
-      }
       __syncwarp();
     }
   }

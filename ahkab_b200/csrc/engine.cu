@@ -99,16 +99,21 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
   int SC = 0, PC = 0;
   Big2Smem S2;
   if (sparse) {
-    // slots per row / points per solve chunk: as large as still lets 4 warps share an SM
-    const size_t budget = (228 * 1024) / 4 - 1024;
-    int maxrow = 0;
+    // slots per row and column / points per solve chunk: as large as still lets 7 warps share an SM
+    const size_t budget = (228 * 1024) / 7 - 1024;
+    int maxrow = 0;   // largest number of entries in a row or in a column of the pattern
     for (int r = 0; r < n; r++) maxrow = std::max(maxrow, e->H.row_ptr[r + 1] - e->H.row_ptr[r]);
+    {
+      std::vector<int> colcnt(n, 0);
+      for (int q = 0; q < h.npos; q++) maxrow = std::max(maxrow, ++colcnt[e->H.pcol[q]]);
+    }
     PC = std::min(npts, 16);
-    SC = 12;
+    SC = std::min(12, std::max(6, maxrow + 3));
     while (PC > 1 && (size_t)big2_smem(n, h.npos, SC, PC, W).total > budget) PC--;
     while (SC > 6 && (size_t)big2_smem(n, h.npos, SC, PC, W).total > budget) SC--;
     while (SC < 32 && SC < maxrow + 4 && (size_t)big2_smem(n, h.npos, SC + 1, PC, W).total <= budget) SC++;
     if (const char* f = getenv("AHK_BIGLIN_SC")) SC = std::max(maxrow, atoi(f));   // tests: force overflows
+    if (const char* f = getenv("AHK_BIGLIN_PC")) PC = std::max(1, std::min(npts, atoi(f)));   // tuning
     S2 = big2_smem(n, h.npos, SC, PC, W);
     if ((size_t)S2.total > e->smem_max || maxrow > SC) sparse = false;
   }
