@@ -64,7 +64,8 @@ EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_group', 'ahk_last_error', 'ahk_launch_count', 'ahk_op',
            'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64',
            'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info',
-           'ahk_h2d_columns')
+           'ahk_h2d_columns', 'ahk_set_jit', 'ahk_jit_launch_count',
+           'ahk_jit_build_count', 'ahk_jit_compile')
 
 
 def _dp(a):
@@ -163,6 +164,16 @@ def load_library(path=None):
     lib.ahk_h2d_columns.restype = C.c_int
     lib.ahk_probe_fp64.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     lib.ahk_probe_fp64.restype = C.c_int
+    lib.ahk_set_jit.argtypes = [vp, C.c_int, i64]
+    lib.ahk_set_jit.restype = C.c_int
+    lib.ahk_jit_launch_count.argtypes = []
+    lib.ahk_jit_launch_count.restype = i64
+    lib.ahk_jit_build_count.argtypes = []
+    lib.ahk_jit_build_count.restype = i64
+    lib.ahk_jit_compile.argtypes = [C.POINTER(ahk_circuit), C.POINTER(ahk_options),
+                                    C.c_int, C.POINTER(i32), C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.POINTER(i64)]
+    lib.ahk_jit_compile.restype = C.c_int
     if path == LIB_PATH:
         _lib = lib
     return lib

@@ -23,10 +23,30 @@
 //   transient.transient_analysis + IE/TRAP/GEAR get_df   transient.py:121-470,
 //       implicit_euler.py:125-205, trap.py:98-192, gear.py:122-208
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <string.h>
+#endif
 
 #include "devices.cuh"
 #include "program.h"
+
+// Specialised build (jit_gen.hpp): the program is a set of constants, so the loops over it
+// have constant bounds — unrolling them lets every index load and branch fold away.  The
+// interpreted build keeps them rolled (run-time bounds).
+#if defined(AHK_JIT) && defined(__CUDACC__)
+#define AHK_UNROLL _Pragma("unroll")
+#else
+#define AHK_UNROLL
+#endif
+// "for (i = lane; i < cnt; i += G)": the items of a vector this lane owns.  The specialised
+// build gives the loop a constant trip count (cnt and G are constants, the lane is not).
+#ifdef AHK_JIT
+#define AHK_LANES(i, cnt)                                                  \
+  AHK_UNROLL for (int i##_q = 0; i##_q < ((cnt) + G - 1) / G; i##_q++)     \
+    if (const int i = c.sub + i##_q * G; i < (cnt))
+#else
+#define AHK_LANES(i, cnt) for (int i = c.sub; i < (cnt); i += G)
+#endif
 
 namespace ahk {
 
@@ -133,16 +153,18 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   const Prog& p = *c.p;
   const int G = V::G;
   double* Pv = c.sm + c.L->Pv;
-  for (int s = c.sub; s < p.npersist; s += G) Pv[s] = c.P(p.pstage[s]);
+  AHK_LANES(s, p.npersist) Pv[s] = c.P(p.pstage[s]);
   if (V::NC > 0 && V::R == 1) {   // staging rows are zeroed once: only the sparsity
     double* A = c.A();              // pattern is rewritten per iteration
-    for (int i = c.sub; i < p.n * c.L->RS; i += G) A[i] = 0.0;
+    AHK_LANES(i, p.n * c.L->RS) A[i] = 0.0;
   }
   Grp<V::G>::sync(c.mask);
   double* Mv = c.sm + c.L->Mv;
   double* Dv = c.sm + c.L->Dv;
   if (c.sub == 0) {
+    AHK_UNROLL
     for (int k = 0; k < p.npos; k++) { Mv[k] = 0.0; if (with_D) Dv[k] = 0.0; }
+    AHK_UNROLL
     for (int k = 0; k < p.nlin; k++) {
       const LinOp& op = p.lin[k];
       const int* q = op.pos;
@@ -163,12 +185,13 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
 #undef SETP
     }
     if (with_D && c.o->cmin > 0)
+      AHK_UNROLL
       for (int k = 0; k < p.npos; k++) if (p.pdiag[k]) Dv[k] += c.o->cmin;
   }
   // device constants + fresh device state (diode.py:89, switch.py:98): one device per lane
   double* st = c.sm + c.L->dst;
   double* dcon = c.sm + c.L->dcon;
-  for (int d = c.sub; d < p.ndev; d += G) {
+  AHK_LANES(d, p.ndev) {
     const DevOp& dv = p.dev[d];
     if (dv.st >= 0) {
       st[dv.st] = st[dv.st + 1] = 0.0;
@@ -201,7 +224,9 @@ AHK_DEV void build_N(Ctx& c) {
   const Prog& p = *c.p;
   double* Nc = c.sm + c.L->Nc;
   if (c.sub == 0) {
+    AHK_UNROLL
     for (int i = 0; i < p.n; i++) Nc[i] = 0.0;
+    AHK_UNROLL
     for (int k = 0; k < p.nsrc; k++) {
       const SrcOp& s = p.src[k];
       if (s.tf) continue;
@@ -219,7 +244,12 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
   const Opts& o = *c.o;
   double* dout = c.sm + c.L->dout;
   double* dst = c.sm + c.L->dst;
-  for (int d = c.sub; d < p.ndev; d += c.G) {
+#ifdef AHK_JIT
+  const int G = AHK_JIT_G;
+#else
+  const int G = c.G;
+#endif
+  AHK_LANES(d, p.ndev) {
     const DevOp& dv = p.dev[d];
     if (!dv.active) continue;
     double* out = dout + dv.dout;
@@ -271,6 +301,7 @@ AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
   double s = 0.0;
   const int k1 = p.row_ptr[r + 1];
   int q = p.nl_ptr[p.row_ptr[r]];
+  AHK_UNROLL
   for (int k = p.row_ptr[r]; k < k1; k++) {
     double v = Bv[k];
     if (tran) v += C1 * Dv[k];
@@ -279,10 +310,12 @@ AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
     if (pc & 0x8000) v += c.gadd;
     s += v * x[col];
     const int q1 = p.nl_ptr[k + 1];
+    AHK_UNROLL
     for (; q < q1; q++) v += (double)p.nl_sgn[q] * dout[p.nl_src[q]];
     Ar[col] = v;
   }
   double tx = 0.0;
+  AHK_UNROLL
   for (int t = p.tx_ptr[r]; t < p.tx_ptr[r + 1]; t++) tx += (double)p.tx_sgn[t] * dout[p.tx_src[t]];
   const double rr = s + (c.sm + c.L->T)[r] + tx;
   (c.sm + c.L->res)[r] = rr;
@@ -485,7 +518,7 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
     if (o.nr_damp_first_iters) td = it < 10 ? 1e-2 : (it < 20 ? 0.1 : 1.0);
     if (o.nl_voltages_lock && p.nlock) {
       double t = 1.0;
-      for (int k = c.sub; k < p.nlock; k += G) {
+      AHK_LANES(k, p.nlock) {
         int n1 = p.lock[2 * k], n2 = p.lock[2 * k + 1];
         double d;
         if (n1 != 0) d = n2 != 0 ? fabs(dx[n1 - 1] - dx[n2 - 1]) : fabs(dx[n1 - 1]);
@@ -497,7 +530,7 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
     // convergence_check (utilities.py:392-549): np.allclose(x, x + dx) per unit class and
     // |residual| <= the other class's absolute tolerance; NaN never passes
     int ok = 1, finite = 1;
-    for (int i = c.sub; i < n; i += G) {
+    AHK_LANES(i, n) {
       const double d = dx[i];
       const double xn = x[i] + td * d;
       x[i] = xn;
@@ -542,10 +575,11 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
   double* Bv = c.sm + c.L->Bv;
   const double* Mv = c.sm + c.L->Mv;
   const double* Dv = c.sm + c.L->Dv;
-  for (int i = c.sub; i < n; i += G) Nd[i] = Nc[i];
+  AHK_LANES(i, n) Nd[i] = Nc[i];
   if (p.ntd) {   // Tt(t), dc_analysis.py:222-237
     Grp<G>::sync(c.mask);
     if (c.sub == 0) {
+      AHK_UNROLL
       for (int k = 0; k < p.nsrc; k++) {
         const SrcOp& s = p.src[k];
         if (!s.tf) continue;
@@ -569,7 +603,7 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
     else if (enabled == 2) f = source_step_value(sidx);
     Grp<G>::sync(c.mask);
     c.gadd = g;     // Gmin (and C1 D in a transient) are added while assembling
-    for (int i = c.sub; i < n; i += G) T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + (with_tran ? Ntr[i] : 0.0);
+    AHK_LANES(i, n) T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + (with_tran ? Ntr[i] : 0.0);
     Grp<G>::sync(c.mask);
     int it = 0;
     int r = mdn_solver<V>(c, MAXIT, &it);
@@ -600,9 +634,10 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
   double* x1 = c.sm + c.L->x1;
   build_N(c);
   if (!have_x0) {
-    for (int i = c.sub; i < n; i += G) {
+    AHK_LANES(i, n) {
       double s = 0.0;
       if (use_guess && p.nguess > 0) {   // dc_guess.py via the precomputed operator
+        AHK_UNROLL
         for (int j = 0; j < p.nguess; j++) {
           double T = p.gconst[j];
           if (p.gpslot[j] >= 0) T += p.gscale[j] * c.PP(p.gpslot[j]);
@@ -626,7 +661,7 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
       s1 = sres; n1 = it; m1 = me;
       if (!s1) break;
       const double* res = c.sm + c.L->res;
-      for (int i = c.sub; i < n; i += G) { x1[i] = x[i]; r1[i] = res[i]; }
+      AHK_LANES(i, n) { x1[i] = x[i]; r1[i] = res[i]; }
       Grp<G>::sync(c.mask);
     } else {
       s2 = sres; n2 = it; m2 = me;
@@ -636,16 +671,16 @@ AHK_DEV int op_analysis(Ctx& c, bool have_x0, bool use_guess, int* iters) {
     *iters = n1;
     status = (m1 << 1);
     const double qnan = nan("");
-    for (int i = c.sub; i < n; i += G) x[i] = qnan;
+    AHK_LANES(i, n) x[i] = qnan;
   } else if (!s2) {
     double* resw = c.sm + c.L->res;
-    for (int i = c.sub; i < n; i += G) { x[i] = x1[i]; resw[i] = r1[i]; }
+    AHK_LANES(i, n) { x[i] = x1[i]; resw[i] = r1[i]; }
     *iters = n1;
     status = AHK_ST_OK | AHK_ST_PASS2_FAIL | (m1 << 1);
   } else {
     *iters = n1 + n2;
     int bad = 0;
-    for (int i = c.sub; i < n; i += G) {   // results.py:493-523
+    AHK_LANES(i, n) {   // results.py:493-523
       bool isv = i < p.nv1;
       double er = isv ? o.ver : o.ier, ea = isv ? o.vea : o.iea;
       if (fabs(x[i] - x1[i]) > er * fmax(fabs(x1[i]), fabs(x[i])) + ea) bad = 1;
@@ -693,23 +728,23 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
     if (predict && avail > 1) {
       const double* xm = HX(1);
       double dt = HT(0) - HT(1);
-      for (int i = c.sub; i < n; i += G) pred[i] = (x0[i] - xm[i]) / dt * step + x0[i];
+      AHK_LANES(i, n) pred[i] = (x0[i] - xm[i]) / dt * step + x0[i];
       d.pred_lte = -0.5 * step * (HT(0) + step - HT(1));
       d.has_pred = 1;
     }
-    for (int i = c.sub; i < n; i += G) C0[i] = -1. / step * x0[i];
+    AHK_LANES(i, n) C0[i] = -1. / step * x0[i];
   } else if (method == AHK_TRAP) {                   // trap.py:98-192
     d.C1 = 2.0 / step;
     d.x_lte = 1.0 / 12 * step * step * step;
     const double* x0 = HX(0);
-    for (int i = c.sub; i < n; i += G) C0[i] = -1.0 * (2.0 / step * x0[i] + hdx[i]);
+    AHK_LANES(i, n) C0[i] = -1.0 * (2.0 / step * x0[i] + hdx[i]);
     if (predict && nh > 2) {
       // quadratic through the last three points (trap.py:171-186 solves the same
       // interpolation with inv(A)); divided differences about t_n
       const double* xa = HX(1);
       const double* xb = HX(2);
       double t1 = HT(1) - HT(0), t2 = HT(2) - HT(0);
-      for (int i = c.sub; i < n; i += G) {
+      AHK_LANES(i, n) {
         double d1 = (xa[i] - x0[i]) / t1, d2 = (xb[i] - x0[i]) / t2;
         double a2 = (d1 - d2) / (t1 - t2), a1 = d1 - a2 * t1;
         pred[i] = a2 * step * step + a1 * step + x0[i];
@@ -725,37 +760,46 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
     double* gamma = s + 16;
     if (c.sub == 0) {
       s[0] = 0;
+      AHK_UNROLL
       for (int i = 1; i < order + 2; i++) s[i] = step + HT(0) - HT(i - 1);
+      AHK_UNROLL
       for (int k = 1; k < order + 2; k++) {
         double a = 1.0;
+        AHK_UNROLL
         for (int j = 1; j < order + 2; j++) a *= (j == k) ? 1.0 : s[j] / (s[j] - s[k]);
         alpha[k] = a;
       }
       double g0 = 0;
+      AHK_UNROLL
       for (int k = 1; k < order + 1; k++) {
         gamma[k] = alpha[k] * ((1.0 / s[order + 1]) - (1.0 / s[k]));
         g0 -= gamma[k];
       }
       gamma[0] = g0;
       double xl = 0.0, fact = 1.0;
+      AHK_UNROLL
       for (int k = 2; k <= order + 1; k++) fact *= k;
+      AHK_UNROLL
       for (int k = 1; k < order + 1; k++) xl += ipow(s[k], order + 1) * (-1.0 * gamma[k] / g0);
       s[24] = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;    // x_lte
       double pl = -1.0 / fact;
+      AHK_UNROLL
       for (int k = 1; k < order + 2; k++) pl *= s[k];
       s[25] = pl;                                                      // pred_lte
     }
     Grp<G>::sync(c.mask);
     d.C1 = gamma[0];
     d.x_lte = s[24];
-    for (int i = c.sub; i < n; i += G) {
+    AHK_LANES(i, n) {
       double a = 0.0;
+      AHK_UNROLL
       for (int k = 0; k < order; k++) a = a + gamma[k + 1] * HX(k)[i];
       C0[i] = a;
     }
     if (predict) {
-      for (int i = c.sub; i < n; i += G) {
+      AHK_LANES(i, n) {
         double a = 0.0;
+        AHK_UNROLL
         for (int k = 1; k < order + 2; k++) a = a + alpha[k] * HX(k - 1)[i];
         pred[i] = a;
       }
@@ -784,6 +828,11 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   const Opts& o = *c.o;
   const int n = p.n;
   const int buflen = c.L->buflen;
+#ifdef AHK_JIT   // specialised build: the integration method is a constant of the kernel
+  const int method = AHK_JIT_METHOD, use_step_control = AHK_JIT_USC;
+#else
+  const int method = a.method, use_step_control = a.use_step_control;
+#endif
   double* x = c.x();
   double* xacc = c.sm + c.L->xacc;   // last accepted x
   double* ht = c.sm + c.L->ht;
@@ -795,9 +844,9 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   const double* Dv = c.sm + c.L->Dv;
   double* xs = c.sm + c.L->xs;       // NR start point when nothing better exists
   int order, max_x, max_dx, pmax_x;
-  if (a.method == AHK_IMPLICIT_EULER) { order = 1; max_x = 0; max_dx = -1; pmax_x = 1; }
-  else if (a.method == AHK_TRAP) { order = 2; max_x = 0; max_dx = 0; pmax_x = 2; }
-  else { order = a.method - 10; max_x = order; max_dx = -1; pmax_x = order; }
+  if (method == AHK_IMPLICIT_EULER) { order = 1; max_x = 0; max_dx = -1; pmax_x = 1; }
+  else if (method == AHK_TRAP) { order = 2; max_x = 0; max_dx = 0; pmax_x = 2; }
+  else { order = method - 10; max_x = order; max_dx = -1; pmax_x = order; }
   int first_iters = 0;   // transient.py:272-278
   if (max_x > 0 || max_dx >= 0) { first_iters = max_x; if (max_dx >= 0 && max_dx + 1 > first_iters) first_iters = max_dx + 1; }
   const int start_pred = pmax_x > 0 ? pmax_x : 0;
@@ -805,11 +854,11 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   double tstep = a.tstep;
   build_N(c);
   int h0 = 0, nh = 1;
-  for (int i = c.sub; i < n; i += G) { hx[i] = x[i]; xs[i] = x[i]; xacc[i] = x[i]; }
+  AHK_LANES(i, n) { hx[i] = x[i]; xs[i] = x[i]; xacc[i] = x[i]; }
   if (c.sub == 0) ht[0] = a.tstart;
   Grp<G>::sync(c.mask);
   double time = a.tstart;
-  if (a.use_step_control) tstep = fmin((a.tstop - a.tstart) / 9999.0, HMAX);
+  if (use_step_control) tstep = fmin((a.tstop - a.tstart) / 9999.0, HMAX);
   int iter_n = 0, solved = 1, have_x = 0, status = 0;
   long long nrows = 0;
   int n_solves = 0, n_nr = 0, n_rej = 0, n_cut = 0;
@@ -817,19 +866,20 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   double* x_out = a.x_out + c.inst * a.max_rows * n;
   while (time < a.tstop) {
     DfOut d;
-    bool predict = a.use_step_control && iter_n >= start_pred;
-    get_df<V>(c, a.method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
+    bool predict = use_step_control && iter_n >= start_pred;
+    get_df<V>(c, method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
     // NR start point (transient.py:335-338)
-    if (o.transient_prediction_as_x0 && a.use_step_control && d.has_pred) {
-      for (int i = c.sub; i < n; i += G) x[i] = pred[i];
+    if (o.transient_prediction_as_x0 && use_step_control && d.has_pred) {
+      AHK_LANES(i, n) x[i] = pred[i];
     } else if (have_x) {
-      for (int i = c.sub; i < n; i += G) x[i] = xacc[i];
+      AHK_LANES(i, n) x[i] = xacc[i];
     } else {
-      for (int i = c.sub; i < n; i += G) x[i] = xs[i];
+      AHK_LANES(i, n) x[i] = xs[i];
     }
     // Ntran = D . C0
-    for (int r = c.sub; r < n; r += G) {
+    AHK_LANES(r, n) {
       double s = 0.0;
+      AHK_UNROLL
       for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) s += Dv[k] * C0[p.pcol[k]];
       Ntr[r] = s;
     }
@@ -840,12 +890,12 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
     n_solves++; n_nr += it;
     if (ok) {
       double old_step = tstep;
-      if (a.use_step_control && d.has_pred) {
+      if (use_step_control && d.has_pred) {
         // transient.py:356-365: coeff = min(2, min_i ((aerr + rerr |x_prev_i|) / lte_i)^(1/(order+1)));
         // the power is monotone, so the minimum ratio is found first and raised once.
         double rmin = INFINITY;
         const double sc = d.x_lte / (d.pred_lte - d.x_lte);
-        for (int i = c.sub; i < n; i += G) {
+        AHK_LANES(i, n) {
           double lte = fabs(sc * (pred[i] - x[i]));
           if (lte != 0) {
             double re = i < p.nv1 ? o.ver : o.ier;
@@ -873,7 +923,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
       // accept: store the row, dxdt = C1*x + C0, push to the ring (transient.py:385-393)
       h0 = (h0 + buflen - 1) % buflen;
       double* hnew = hx + h0 * n;
-      for (int i = c.sub; i < n; i += G) {
+      AHK_LANES(i, n) {
         double xi = x[i];
         xacc[i] = xi;
         hnew[i] = xi;
@@ -885,7 +935,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
       if (nh < buflen) nh++;
       Grp<G>::sync(c.mask);
     } else {
-      if (a.use_step_control) {
+      if (use_step_control) {
         tstep = tstep / 5.0;
         if (check_step(o, tstep, time, a.tstop, HMAX)) { status |= AHK_ST_HMIN; solved = 0; break; }
         n_cut++;

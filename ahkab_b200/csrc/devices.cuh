@@ -11,7 +11,11 @@
 // once and every output is derived from that single evaluation; the EKV inner
 // solve is stateless (no warm-start state) and converged to ~1e-12.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#else   // NVRTC: the math functions are built in, the macros of math.h are not
+#define INFINITY __builtin_bit_cast(double, 0x7ff0000000000000ULL)
+#endif
 
 #ifdef __CUDACC__
 #define AHK_DEV __device__ __forceinline__

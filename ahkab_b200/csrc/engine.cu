@@ -7,12 +7,22 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "biglin2.cuh"
+#include "jit.hpp"
+#include "jit_gen.hpp"
 #include "kernels.cuh"
+
+namespace ahk { namespace jit {
+const Source g_sources[] = {
+#include "jit_sources.inc"
+};
+const int g_nsources = (int)(sizeof(g_sources) / sizeof(g_sources[0]));
+} }
 
 using namespace ahk;
 
@@ -20,6 +30,8 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_jit_launches{0};   // launches of circuit-specialised kernels
+std::atomic<long long> g_jit_builds{0};     // NVRTC compilations
 
 int fail(const std::string& m) { g_err = m; return -1; }
 
@@ -72,6 +84,13 @@ struct ahk_engine {
   double* d_scratch = nullptr;   // sweep values / omegas
   size_t scratch_cap = 0;
   BigLin big;              // large-n linear path (biglin.cuh)
+  // circuit-specialised kernels (jit_gen.hpp): 0 = never, 1 = always (failing to build one
+  // is an error), 2 = batches of at least jit_min_batch instances, interpreted kernel if
+  // NVRTC is not available
+  int jit_mode = 2;
+  long long jit_min_batch = 4096;
+  long long slots_epoch = 0, opts_epoch = 0;   // bumped when the varied slots / options change
+  std::map<std::vector<long long>, jit::Kernel> jit_cache;
 };
 
 int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_host,
@@ -244,6 +263,7 @@ int set_batch(ahk_engine* e, const ahk_batch* b, cudaStream_t s) {
     CK(cudaMemcpyAsync(e->d_dev, e->H.dev.data(), e->H.dev.size() * sizeof(DevOp), cudaMemcpyHostToDevice, s));
   e->cur_slots = slots;
   e->slots_valid = true;
+  e->slots_epoch++;
   return 0;
 }
 
@@ -361,6 +381,45 @@ KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
   return k;
 }
 
+// The specialised kernel for (analysis, variant, launch shape, options, varied slots) —
+// compiled on first use, cached in the engine.  *out = nullptr: use the interpreted kernel.
+int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, const Layout& Ly,
+            const Launch& L, int reg_blocks, int method, int usc, jit::Kernel** out) {
+  *out = nullptr;
+  if (e->jit_mode == 0 || v.NC == 0) return 0;   // the generic shared-memory fallback is not specialised
+  if (e->jit_mode == 2 && B < e->jit_min_batch) return 0;
+  const bool must = e->jit_mode == 1;
+  std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, e->slots_epoch, e->opts_epoch};
+  auto it = e->jit_cache.find(key);
+  if (it == e->jit_cache.end()) {
+    jit::Kernel k;
+    JitCfg cfg = {v.NC, v.R, v.G, L.threads, std::max(1, std::min(32, reg_blocks * 128 / L.threads)), mode, method, usc};
+    std::string err;
+    const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg);
+    if (!jit::build(spec, mode == MODE_TRAN ? "ahk_jit_tran" : "ahk_jit_dc", L.smem, k, err)) {
+      k.failed = true; k.why = err;
+      if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] specialised kernel not built: %s\n", err.c_str());
+    } else {
+      g_jit_builds++;
+      if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] specialised kernel built (mode %d, variant %d)\n", mode, vid);
+    }
+    it = e->jit_cache.emplace(key, k).first;
+  }
+  if (it->second.failed) {
+    if (must) return fail("specialised kernel: " + it->second.why);
+    return 0;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+int jit_launched(bool ok, const std::string& err) {
+  if (!ok) return fail(err);
+  g_launches++;
+  g_jit_launches++;
+  return 0;
+}
+
 int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* d_sweep, int npts,
                  const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
                  int32_t* status, cudaStream_t s) {
@@ -372,6 +431,13 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC, v.R);
   Launch L;
   if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
+  jit::Kernel* jk = nullptr;
+  if (get_jit(e, batch->B, MODE_OP, vid, v, Ly, L, real_min_blocks(v.NC), 0, 0, &jk)) return -1;
+  if (jk) {
+    KDcJ kj = {batch->vary, batch->B, DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status}};
+    std::string err;
+    return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
+  }
   KDc k;
   k.b = make_base(e, batch, Ly);
   k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
@@ -413,6 +479,7 @@ void ahk_destroy(ahk_engine* e) {
   if (!e) return;
   if (e->blob) cudaFree(e->blob);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  for (auto& kv : e->jit_cache) jit::unload(kv.second);
   e->big.release();
   delete e;
 }
@@ -422,7 +489,40 @@ int ahk_size(const ahk_engine* e) { return e ? e->n : -1; }
 int ahk_set_options(ahk_engine* e, const ahk_options* opts) {
   if (!e || !opts) return fail("null argument");
   std::memcpy(&e->o, opts, sizeof(Opts));
+  e->opts_epoch++;
   return 0;
+}
+
+int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch) {
+  if (!e) return fail("null engine");
+  if (mode < 0 || mode > 2) return fail("ahk_set_jit: mode must be 0 (off), 1 (on) or 2 (auto)");
+  e->jit_mode = mode;
+  if (min_batch > 0) e->jit_min_batch = min_batch;
+  return 0;
+}
+
+int64_t ahk_jit_launch_count(void) { return g_jit_launches.load(); }
+int64_t ahk_jit_build_count(void) { return g_jit_builds.load(); }
+
+int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary, const int32_t* vary_slots,
+                    int tran, int method, int use_step_control, int variant_id, int64_t* cubin_bytes) {
+  if (!circ || !opts || variant_id < 2 || variant_id >= AHK_N_REAL_VARIANTS) return fail("ahk_jit_compile: bad argument");
+  try {
+    HostProg H;
+    build_program(circ, H);
+    set_vary_slots(H, n_vary, vary_slots);
+    const VarInfo& v = real_variants()[variant_id];
+    if (!fits(v, H.hdr.n)) return fail("variant does not fit this circuit");
+    Opts o; std::memcpy(&o, opts, sizeof(Opts));
+    const int mode = tran ? MODE_TRAN : MODE_OP;
+    Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R);
+    JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
+    std::string err;
+    std::vector<char> cubin = jit::compile(jit_spec_source(H, o, Ly, cfg), err);
+    if (cubin.empty()) return fail(err);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return 0;
+  } catch (const std::exception& ex) { return fail(ex.what()); }
 }
 
 int ahk_set_group(ahk_engine* e, int lanes) {
@@ -524,6 +624,16 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC, v.R);
   Launch L;
   if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
+  jit::Kernel* jk = nullptr;
+  if (get_jit(e, batch->B, MODE_TRAN, vid, v, Ly, L, real_min_blocks(v.NC), method, use_step_control ? 1 : 0, &jk))
+    return -1;
+  if (jk) {
+    KTranJ kj = {batch->vary, batch->B, x0,
+                 TranArgs{tstart, tstep, tstop, method, use_step_control, max_rows, t_out, x_out, rows, counters},
+                 status};
+    std::string err;
+    return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
+  }
   KTran k;
   k.b = make_base(e, batch, Ly);
   k.x0 = x0;

@@ -59,4 +59,32 @@ AHK_DEV void run_tran(Ctx& c, const double* x0, const TranArgs& a, int* status) 
   if (c.sub == 0) status[c.inst] = st;
 }
 
+// kernel parameters of the circuit-specialised kernels (jit_kernels.cuh; filled by
+// engine.cu): no program / options / layout — those are constants of the build
+struct KDcJ { const double* vary; long long B; DcArgs a; };
+struct KTranJ { const double* vary; long long B; const double* x0; TranArgs a; int* status; };
+
+#ifdef __CUDACC__
+// the group's context: its lanes, its instance, its shared-memory slice
+template <int G>
+__device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
+                                         int stride, const double* vary, long long B,
+                                         long long units, long long& unit) {
+  extern __shared__ __align__(16) double smem[];
+  const int gi = threadIdx.x / G;
+  const int ipb = blockDim.x / G;
+  unit = (long long)blockIdx.x * ipb + gi;
+  if (unit >= units) return false;
+  const int lane = threadIdx.x & 31;
+  c.p = p; c.o = o; c.L = L;
+  c.sm = smem + (size_t)gi * stride;
+  c.vary = vary; c.B = B; c.inst = unit;
+  c.sub = threadIdx.x % G;
+  c.G = G;
+  c.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  return true;
+}
+
+#endif
+
 }  // namespace ahk

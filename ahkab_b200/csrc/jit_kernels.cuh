@@ -1,0 +1,38 @@
+// jit_kernels.cuh — entry points of the circuit-specialised kernels (see jit_gen.hpp).
+// Compiled at run time by NVRTC for sm_100a as
+//     #include "jit_spec.h"       (generated: Prog / Opts / Layout as constants)
+//     #include "jit_kernels.cuh"
+// One translation unit = one (circuit, options, analysis, kernel variant).  The
+// per-instance algorithm is the one of the interpreted kernels: entry.cuh / core.cuh.
+#pragma once
+#ifndef AHK_JIT
+#error "jit_kernels.cuh needs the generated jit_spec.h first"
+#endif
+#include "entry.cuh"
+
+namespace ahk {
+
+#ifdef __CUDACC__
+__device__ const Prog jit_prog{};
+__device__ const Opts jit_opts{};
+__device__ const Layout jit_layout{};
+typedef Var<AHK_JIT_NC, AHK_JIT_R, AHK_JIT_G> JitVar;
+
+#if AHK_JIT_MODE == 0
+extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
+ahk_jit_dc(const __grid_constant__ KDcJ k) {
+  Ctx c; long long u;
+  if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
+  run_dc<JitVar>(c, k.a);
+}
+#else
+extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
+ahk_jit_tran(const __grid_constant__ KTranJ k) {
+  Ctx c; long long u;
+  if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
+  run_tran<JitVar>(c, k.x0, k.a, k.status);
+}
+#endif
+#endif
+
+}  // namespace ahk

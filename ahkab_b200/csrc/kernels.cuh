@@ -72,25 +72,6 @@ int launch_tran(const KTran& k, const Launch& L, cudaStream_t s);
 int launch_ac(const KAc& k, const Launch& L, cudaStream_t s);
 
 #ifdef __CUDACC__
-template <int G>
-__device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
-                                         int stride, const double* vary, long long B,
-                                         long long units, long long& unit) {
-  extern __shared__ __align__(16) double smem[];
-  const int gi = threadIdx.x / G;
-  const int ipb = blockDim.x / G;
-  unit = (long long)blockIdx.x * ipb + gi;
-  if (unit >= units) return false;
-  const int lane = threadIdx.x & 31;
-  c.p = p; c.o = o; c.L = L;
-  c.sm = smem + (size_t)gi * stride;
-  c.vary = vary; c.B = B; c.inst = unit;
-  c.sub = threadIdx.x % G;
-  c.G = G;
-  c.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  return true;
-}
-
 template <typename KernelT, typename Args>
 int do_launch(KernelT kern, const Args& args, const Launch& L, cudaStream_t s) {
   if (L.smem > 48 * 1024) {

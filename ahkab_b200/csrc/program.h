@@ -33,6 +33,7 @@ struct DevOp {      // non-linear device
   int active;       // 0: both output nodes grounded -> never evaluated (dc_analysis.py:863)
 };
 
+#ifndef AHK_JIT   // specialised build (jit_gen.hpp): Opts / Prog / Layout are compile-time constants
 struct Opts {
   double vea, ver, iea, ier, gmin, cmin, hmin;
   double nl_voltages_lock_factor, transient_aposteriori_step_threshold;
@@ -87,5 +88,6 @@ struct Layout {     // offsets in doubles inside one instance's slice
   int buflen;
   int stride;       // doubles per instance (padded: stride % 16 == (G*RS) % 16)
 };
+#endif  // AHK_JIT
 
 }  // namespace ahk

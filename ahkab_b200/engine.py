@@ -102,6 +102,20 @@ class Engine(object):
         if self.lib.ahk_set_variant(self._h, int(real), int(ac)) != 0:
             raise EngineError(self._err())
 
+    JIT_MODES = {'off': 0, 'on': 1, 'auto': 2}
+
+    def set_jit(self, mode='auto', min_batch=0):
+        """Circuit-specialised kernels (include/ahkab_b200.h: ahk_set_jit): 'off' = always
+        the interpreted kernels, 'on' = always a kernel compiled for this circuit (NVRTC,
+        seconds on first use), 'auto' = for batches of at least min_batch instances."""
+        m = self.JIT_MODES[mode] if isinstance(mode, str) else int(mode)
+        if self.lib.ahk_set_jit(self._h, m, int(min_batch)) != 0:
+            raise EngineError(self._err())
+        return self
+
+    def jit_launch_count(self):
+        return int(self.lib.ahk_jit_launch_count())
+
     def _batch(self):
         b = _abi.ahk_batch()
         b.B = self.B

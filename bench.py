@@ -73,6 +73,9 @@ AC_FLOP = 4 * LU(14) + 8 * 14 ** 2            # per (instance, frequency)
 C5_FLOP = (2 * LU(257) - 2 * 2 * 257 ** 2) / 10.0 + 2 * (2 * 257 ** 2 + 2 * 257 ** 2)
 
 
+JIT_MODE = 'auto'   # --jit: circuit-specialised kernels (ahk_set_jit); auto = batches >= 4096
+
+
 # ---------------------------------------------------------------------------------
 class Runner(object):
     """One workload on one GPU: `step()` with inputs resident, `e2e()` from host."""
@@ -90,6 +93,7 @@ class Runner(object):
         self.w = W.ALL[name](B=B, seed=seeds[name] + 1000 * seed_off)
         self.circ = self.w.circuit(Circuit)
         self.eng = Engine(self.circ, self.w.batch(), opts=self.w.opts)
+        self.eng.set_jit(JIT_MODE)
         self.B = B
         self.pipe = None
         self.vary_host = torch.empty(self.eng.vary.shape, dtype=torch.float64,
@@ -420,9 +424,10 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     r = Runner(name, seed_off=rank)
     eng = r.eng
     # kernel path, inputs resident
-    l0 = eng.launch_count()
+    l0, j0 = eng.launch_count(), eng.jit_launch_count()
     ms, raw = timer.timed(r.step, steps, warmup, sampler)
     launches = (eng.launch_count() - l0) // (steps + warmup) * steps
+    jit_launches = (eng.jit_launch_count() - j0) // (steps + warmup) * steps
     units = all_sum(r.units(raw), dist_on, device)
     flop, byts = r.algo(raw)
     value = units * steps / (ms * 1e-3)
@@ -452,7 +457,9 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
                    "units_per_step_rank0": r.units(raw), "n_unknowns": eng.n,
                    "l2": "flushed (512 MiB write) before every timed step",
                    "parallelism": "batch sharded, %d rank(s), no data-path collective" % world,
-                   "status_ok_rank0": ok},
+                   "status_ok_rank0": ok,
+                   "kernels": ("%d of %d launches per run are circuit-specialised kernels "
+                               "(NVRTC, sm_100a; --jit %s)" % (jit_launches, launches, JIT_MODE))},
         "e2e": {"value": e2e_value, "unit": UNITS[name], "ms_per_step": ms_e / steps,
                 "chunks": E2E_CHUNKS[name],
                 "h2d_bytes_per_step": r.h2d, "d2h_bytes_per_step": r.d2h_bytes(host)},
@@ -485,7 +492,11 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(UNITS))
     ap.add_argument('--only', action='store_true', help='headline workload only')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--jit', default='auto', choices=['auto', 'on', 'off'],
+                    help='circuit-specialised kernels: auto (batches >= 4096), on, off (interpreted)')
     args = ap.parse_args()
+    global JIT_MODE
+    JIT_MODE = args.jit
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))

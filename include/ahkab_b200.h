@@ -30,7 +30,12 @@
 #ifndef AHKAB_B200_H
 #define AHKAB_B200_H
 
+#ifdef __CUDACC_RTC__   /* NVRTC has no host headers */
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -164,6 +169,8 @@ enum {
 
 typedef struct ahk_engine ahk_engine;
 
+#ifndef __CUDACC_RTC__   /* host entry points: not part of a device-only (NVRTC) build */
+
 /* Build the device-side stamp program for one topology. Host call. */
 int ahk_create(const ahk_circuit* circ, const ahk_options* opts,
                ahk_engine** out);
@@ -183,6 +190,24 @@ int ahk_set_group(ahk_engine* e, int lanes);
 int ahk_variant_count(int kind);
 int ahk_variant_info(int kind, int id, int32_t* nc_r_g);
 int ahk_set_variant(ahk_engine* e, int real_id, int ac_id);
+/* Circuit-specialised kernels (no reference counterpart).  The stock OP/DC/transient
+ * kernels interpret the stamp program; for large batches the engine can instead compile,
+ * once per (circuit, options, analysis), the same per-instance source with the program,
+ * options and memory layout folded in as constants (NVRTC, sm_100a) — same results,
+ * several times fewer instructions.  mode 0 = never, 1 = always (an NVRTC failure is an
+ * error), 2 = for batches of at least min_batch instances, default (2, 4096);
+ * min_batch <= 0 keeps the current threshold.  The first call with a new combination pays
+ * the compilation (seconds); the kernel is cached in the engine. */
+int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch);
+/* Launches through specialised kernels / NVRTC compilations so far (all engines). */
+int64_t ahk_jit_launch_count(void);
+int64_t ahk_jit_build_count(void);
+/* Host-only check (needs NVRTC, no GPU): compiles the specialised OP/DC (tran = 0) or
+ * transient (tran = 1) kernel of this circuit for kernel variant variant_id and returns
+ * the size of the sm_100a cubin. */
+int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary,
+                    const int32_t* vary_slots, int tran, int method,
+                    int use_step_control, int variant_id, int64_t* cubin_bytes);
 const char* ahk_last_error(void);
 /* Number of kernel launches issued by this library so far (all engines). */
 int64_t ahk_launch_count(void);
@@ -252,6 +277,7 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0,
 int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op,
            const double* omegas, int npts, double* x_out, int32_t* status,
            void* stream);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ using std::isnan; using std::isinf; using std::isfinite;
 #include "../../ahkab_b200/csrc/entry.cuh"
 #include "../../ahkab_b200/csrc/program_build.hpp"
 #include "../../ahkab_b200/csrc/ac.cuh"
+#include "../../ahkab_b200/csrc/jit_gen.hpp"
 
 using namespace ahk;
 
@@ -99,6 +100,27 @@ int emu_ac(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, co
     if (nc) run_ac<Var<4, 3, 1> >(cx, AL, a); else run_ac<Var<0, 0, 1> >(cx, AL, a);
   }
   return 0;
+}
+
+// Text of the generated jit_spec.h (jit_gen.hpp) for this circuit / batch / analysis / variant:
+// returns its length (the text is truncated to cap - 1 bytes), < 0 on error.
+int emu_jit_source(const ahk_circuit* c, const ahk_options* o, int n_vary, const int32_t* slots,
+                   int mode, int method, int usc, int NC, int R, int G, int threads, int min_blocks,
+                   char* buf, int64_t cap) {
+  try {
+    HostProg H;
+    build_program(c, H);
+    set_vary_slots(H, n_vary, slots);
+    Opts q; copy_opts(o, q);
+    Layout L = make_layout(H, mode, method, usc, G, NC, R);
+    JitCfg cfg = {NC, R, G, threads, min_blocks, mode, method, usc};
+    std::string t = jit_spec_source(H, q, L, cfg);
+    if (buf && cap > 0) {
+      size_t m = std::min<size_t>(t.size(), (size_t)cap - 1);
+      std::memcpy(buf, t.data(), m); buf[m] = 0;
+    }
+    return (int)t.size();
+  } catch (...) { return -1; }
 }
 
 // ---- single-device entry points (same device code the kernels inline) -------------------

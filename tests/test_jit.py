@@ -1,0 +1,213 @@
+"""Circuit-specialised kernels (ahkab_b200/csrc/jit_gen.hpp, jit.hpp).
+
+CPU: the generated constants + the engine's per-instance source compile for sm_100a with
+NVRTC (no GPU needed), and the same specialised source built for the host gives results
+bit-identical to the interpreted host build.  GPU: specialised == interpreted kernels on
+the workloads, through the C-ABI."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import common  # noqa: F401  (sys.path set-up)
+from ahkab_b200 import _abi, workloads as W
+from ahkab_b200.circuit import Circuit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'hostemu'))
+
+
+def _emu(w):
+    import emu
+    return emu.Emu(w.circuit(Circuit), w.batch(), w.opts)
+
+
+def _nvrtc_available():
+    for p in (os.environ.get('AHK_NVRTC', ''), 'libnvrtc.so.12',
+              '/usr/local/cuda/lib64/libnvrtc.so.12'):
+        if not p:
+            continue
+        try:
+            C.CDLL(p)
+            return True
+        except OSError:
+            pass
+    return False
+
+
+CASES = [('c2', W.c2_diode_op, 0, 'TRAP', 0, (2, 3, 4)),
+         ('c3', W.c3_colpitts, 1, 'TRAP', 0, (7,)),
+         ('c3op', W.c3_colpitts, 0, 'TRAP', 0, (7,)),
+         ('c4', W.c4_ring3, 1, 'GEAR2', 1, (3, 5)),
+         ('c4ie', W.c4_ring3, 1, 'IMPLICIT_EULER', 1, (5,))]
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC not installed")
+@pytest.mark.parametrize('name,mk,tran,method,usc,vids', CASES, ids=[c[0] for c in CASES])
+def test_specialised_source_compiles_for_sm_100a(name, mk, tran, method, usc, vids):
+    import oracle
+    lib = _abi.load_library()
+    w = mk(B=16)
+    o = oracle.Oracle(w.circuit(Circuit), w.batch(), w.opts)
+    for vid in vids:
+        nb = C.c_int64(0)
+        rc = lib.ahk_jit_compile(C.byref(o.desc.c), C.byref(o.opts), len(o.slots),
+                                 o.slots.ctypes.data_as(C.POINTER(C.c_int32)), tran,
+                                 _abi.METHODS[method], usc, vid, C.byref(nb))
+        assert rc == 0, lib.ahk_last_error().decode()[:2000]
+        assert nb.value > 10000      # an sm_100a cubin came back
+
+
+def _build_host_jit(spec, tag):
+    d = tempfile.mkdtemp(prefix='ahk_jit_%s_' % tag)
+    open(os.path.join(d, 'jit_spec.h'), 'w').write(spec)
+    so = os.path.join(d, 'libemuj.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I', d,
+                           '-I', os.path.join(ROOT, 'ahkab_b200', 'csrc'), '-o', so,
+                           os.path.join(ROOT, 'tests', 'hostemu', 'hostemu_jit.cpp'), '-lm'])
+    return C.CDLL(so)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def test_specialised_host_build_is_bit_identical_op():
+    import emu
+    w = W.c2_diode_op(B=256)
+    e = _emu(w)
+    emu.set_variant(1)                                    # Var<4,3,1>
+    try:
+        ref = e.op()
+    finally:
+        emu.set_variant(0)
+    lib = _build_host_jit(e.jit_source(0, NC=4, R=3, G=1), 'c2')
+    B, n = e.B, e.n
+    x = np.zeros((B, n)); res = np.zeros((B, n))
+    it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+    rc = lib.emuj_dc(C.c_int64(B), _dp(e.vary), C.c_int(-1), None, C.c_int(1), None, C.c_int(1),
+                     _dp(x), _dp(res), _ip(it), _ip(st))
+    assert rc == 0
+    assert (st == ref['status']).all() and (it == ref['iters']).all()
+    assert np.array_equal(x, ref['x']) and np.array_equal(res, ref['resid'])
+
+
+def test_specialised_host_build_is_bit_identical_tran():
+    import emu
+    w = W.c4_ring3(B=2)
+    e = _emu(w)
+    tr = dict(W.C4_TRAN)
+    rows_cap = 4096
+    x0 = np.zeros((e.B, e.n))
+    emu.set_variant(2)                                    # Var<6,5,1>
+    try:
+        ref = e.tran(x0, tr['tstart'], tr['tstep'], tr['tstop'] / 10, 'GEAR2', True, rows_cap)
+    finally:
+        emu.set_variant(0)
+    lib = _build_host_jit(e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1), 'c4')
+    B, n = e.B, e.n
+    t = np.full((B, rows_cap), np.nan); x = np.full((B, rows_cap, n), np.nan)
+    rows = np.zeros(B, np.int32); cnt = np.zeros((B, 4), np.int32); st = np.zeros(B, np.int32)
+    rc = lib.emuj_tran(C.c_int64(B), _dp(e.vary), _dp(x0), C.c_double(tr['tstart']),
+                       C.c_double(tr['tstep']), C.c_double(tr['tstop'] / 10), C.c_int64(rows_cap),
+                       _dp(t), _dp(x), _ip(rows), _ip(cnt), _ip(st))
+    assert rc == 0
+    assert (rows == ref['rows']).all() and (rows > 20).all()
+    assert (st == ref['status']).all() and (cnt == ref['counters']).all()
+    assert np.array_equal(t, ref['t'], equal_nan=True) and np.array_equal(x, ref['x'], equal_nan=True)
+
+
+# ---- GPU: specialised kernels == interpreted kernels, through the C-ABI --------------------
+def _engine(w):
+    from ahkab_b200.engine import Engine
+    return Engine(w.circuit(Circuit), w.batch(), opts=w.opts)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _same(a, b, what):
+    """Same source, same compiler: expected bit-identical; rounding-level slack is allowed
+    because constant folding may change which products are contracted into FMAs."""
+    a, b = _np(a), _np(b)
+    if a.dtype.kind == 'f':
+        fin = np.isfinite(a) & np.isfinite(b)
+        assert (np.isfinite(a) == np.isfinite(b)).all(), what
+        assert np.abs(a[fin] - b[fin]).max(initial=0.0) <= 1e-9 * (1 + np.abs(b[fin]).max(initial=0.0)), what
+    else:
+        assert (a != b).mean() < 0.002, what
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('vid', [-1, 2, 3, 4])
+def test_gpu_specialised_op_and_sweep(vid):
+    w = W.c2_diode_op(8192)
+    e = _engine(w)
+    e.set_variant(real=vid)
+    n0 = e.jit_launch_count()
+    e.set_jit('off'); a = e.op(); sa = e.dc_sweep('V1', np.linspace(0.2, 1.4, 7))
+    assert e.jit_launch_count() == n0
+    e.set_jit('on'); b = e.op(); sb = e.dc_sweep('V1', np.linspace(0.2, 1.4, 7))
+    assert e.jit_launch_count() == n0 + 2          # the specialised kernels really ran
+    for k in ('x', 'resid', 'iters', 'status'):
+        _same(a[k], b[k], 'op ' + k)
+    for k in ('x', 'iters', 'status'):
+        _same(sa[k], sb[k], 'sweep ' + k)
+    assert (_np(b['status']) & 1).all()
+    # automatic policy: this batch is above the default threshold, a small one is not
+    e.set_jit('auto'); e.op()
+    assert e.jit_launch_count() == n0 + 3
+    small = _engine(W.c2_diode_op(64)); small.op()
+    assert small.jit_launch_count() == n0 + 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('vid', [-1, 7, 9])
+def test_gpu_specialised_fixed_step_transient(vid):
+    w = W.c3_colpitts(256)
+    e = _engine(w)
+    e.set_variant(real=vid)
+    e.set_jit('off'); opa = e.op()
+    x0 = common.c3_x0(_np(opa['x']))
+    ta = e.tran(x0, max_rows=256, **W.C3_TRAN)
+    n0 = e.jit_launch_count()
+    e.set_jit('on'); opb = e.op(); tb = e.tran(x0, max_rows=256, **W.C3_TRAN)
+    assert e.jit_launch_count() == n0 + 2
+    _same(opa['x'], opb['x'], 'op x')
+    assert (_np(tb['rows']) == 250).all() and (_np(tb['status']) & 1).all()
+    for k in ('rows', 'status', 'counters'):
+        _same(ta[k], tb[k], 'tran ' + k)
+    assert np.array_equal(_np(ta['t'])[:, :250], _np(tb['t'])[:, :250])
+    xa, xb = _np(ta['x'])[:, :250], _np(tb['x'])[:, :250]
+    assert np.abs(xa - xb).max() < 1e-6        # 250 steps of an oscillator amplify rounding
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('vid', [-1, 3, 5])
+def test_gpu_specialised_lte_transient(vid):
+    w = W.c4_ring3(128)
+    e = _engine(w)
+    e.set_variant(real=vid)
+    tr = dict(W.C4_TRAN); tr['tstop'] = 10e-9
+    e.set_jit('off'); ta = e.tran(None, max_rows=2048, **tr)
+    n0 = e.jit_launch_count()
+    e.set_jit('on'); tb = e.tran(None, max_rows=2048, **tr)
+    assert e.jit_launch_count() == n0 + 1
+    ra, rb = _np(ta['rows']), _np(tb['rows'])
+    assert (_np(tb['status']) & 1).all()
+    # LTE step control amplifies last-bit differences: step counts agree within 2 %
+    assert np.abs(ra - rb).max() <= np.maximum(3, 0.02 * ra).max()
+    same = ra == rb
+    assert same.mean() > 0.5
+    xa, xb = _np(ta['x']), _np(tb['x'])
+    for i in np.nonzero(same)[0][:16]:
+        assert np.abs(xa[i, :ra[i]] - xb[i, :rb[i]]).max() < 1e-2
