@@ -412,6 +412,65 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
   return 1;
 }
 
+// ---- dense solve, one lane per instance (Var<NC,R,1>): LU in registers -------------------
+// dgesv as LAPACK's unblocked dgetf2 + dgetrs run it: at step k the largest |a| of column k
+// among rows k.. (first maximum wins, exact comparison), an explicit row swap (register
+// selects, the indices stay compile-time), multipliers l = a * (1 / pivot), elimination of
+// the rows below only, then back-substitution (with the stored pivot reciprocals).  About a
+// third of the instructions of the Gauss-Jordan form below, which pays for keeping every
+// lane of a group busy — pointless when the group is one lane.  0 = a pivot is exactly zero.
+template <class V>
+AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
+  const int NC = V::NC, R = V::R;
+  const int n = c.p->n;
+  double* dx = c.sm + c.L->dx;
+  double inv[R > 0 ? R : 1], xk[R > 0 ? R : 1];
+#pragma unroll
+  for (int k = 0; k < R; k++) { inv[k] = 0.0; xk[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    if (k < n) {
+      double best = fabs(a[k][k]);
+      int p = k;
+#pragma unroll
+      for (int r = k + 1; r < R; r++) {
+        const double v = fabs(a[r][k]);
+        if (r < n && v > best) { best = v; p = r; }
+      }
+      if (best == 0.0) return 0;
+#pragma unroll
+      for (int j = k; j < NC; j++) {        // swap rows k and p (columns < k are not needed again)
+        const double t = a[k][j];
+        double q = t;
+#pragma unroll
+        for (int r = k + 1; r < R; r++) if (p == r) q = a[r][j];
+        a[k][j] = q;
+#pragma unroll
+        for (int r = k + 1; r < R; r++) if (p == r) a[r][j] = t;
+      }
+      const double iv = 1.0 / a[k][k];
+      inv[k] = iv;
+#pragma unroll
+      for (int r = k + 1; r < R; r++) {     // rows >= n are zero: l = 0
+        const double l = a[r][k] * iv;
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) a[r][j] -= l * a[k][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = R - 1; k >= 0; k--) {
+    if (k < n) {
+      double s = a[k][NC - 1];
+#pragma unroll
+      for (int j = k + 1; j < R; j++) s -= a[k][j] * xk[j];   // columns >= n are zero
+      xk[k] = s * inv[k];
+      dx[k] = xk[k];
+    }
+  }
+  return 1;
+}
+
 // ---- dense solve, generic fallback (Var<0,0,G>): matrix in shared memory ----------------
 // Gaussian elimination with implicit partial pivoting + back-substitution, run-time n.
 template <int G>
@@ -457,6 +516,37 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
   return 1;
 }
 
+#ifdef AHK_JIT
+// Specialised build: the row is a COMPILE-TIME constant, so its column indices, gather
+// lists and signs fold into straight-line code that writes the matrix row directly into
+// the registers of the solve (no staging row in shared memory).  With several lanes per
+// instance the lane's row is only known at run time: a switch runs each row's code for
+// the lanes that own it (divergent, but a few dozen instructions per row, and no index
+// loads, loop control or shared-memory round trip).
+template <int ROW, int NC>
+AHK_DEV double assemble_row_const(Ctx& c, double (&row)[NC]) {
+#pragma unroll
+  for (int j = 0; j < NC - 1; j++) row[j] = 0.0;
+  return assemble_row(c, ROW, row);
+}
+template <int NC>
+AHK_DEV double assemble_row_switch(Ctx& c, int r, double (&row)[NC]) {
+  switch (r) {
+#define AHK_ROW_CASE(i) case i: if constexpr (i < Prog::n) return assemble_row_const<i, NC>(c, row); else break;
+    AHK_ROW_CASE(0) AHK_ROW_CASE(1) AHK_ROW_CASE(2) AHK_ROW_CASE(3) AHK_ROW_CASE(4) AHK_ROW_CASE(5)
+    AHK_ROW_CASE(6) AHK_ROW_CASE(7) AHK_ROW_CASE(8) AHK_ROW_CASE(9) AHK_ROW_CASE(10) AHK_ROW_CASE(11)
+    AHK_ROW_CASE(12) AHK_ROW_CASE(13) AHK_ROW_CASE(14) AHK_ROW_CASE(15) AHK_ROW_CASE(16) AHK_ROW_CASE(17)
+    AHK_ROW_CASE(18) AHK_ROW_CASE(19) AHK_ROW_CASE(20) AHK_ROW_CASE(21) AHK_ROW_CASE(22) AHK_ROW_CASE(23)
+    AHK_ROW_CASE(24) AHK_ROW_CASE(25) AHK_ROW_CASE(26) AHK_ROW_CASE(27) AHK_ROW_CASE(28) AHK_ROW_CASE(29)
+    AHK_ROW_CASE(30)
+#undef AHK_ROW_CASE
+  }
+#pragma unroll
+  for (int j = 0; j < NC; j++) row[j] = 0.0;
+  return 0.0;
+}
+#endif
+
 // one Newton linear step: assemble at x() and solve into dx(); 0 = singular
 template <class V>
 AHK_DEV int assemble_solve(Ctx& c) {
@@ -468,6 +558,22 @@ AHK_DEV int assemble_solve(Ctx& c) {
 #pragma unroll
     for (int s = 0; s < R; s++) {
       const int r = c.sub + G * s;
+#ifdef AHK_JIT
+      (void)A; (void)RS;
+      if (G == 1) {   // r == s: a compile-time constant
+        if (s < n) {
+#pragma unroll
+          for (int j = 0; j < NC - 1; j++) a[s][j] = 0.0;
+          a[s][NC - 1] = assemble_row(c, s, a[s]);
+        }
+      } else if (r < n) {
+        a[s][NC - 1] = assemble_row_switch<NC>(c, r, a[s]);
+      }
+      if (G == 1 ? s >= n : r >= n) {
+#pragma unroll
+        for (int j = 0; j < NC; j++) a[s][j] = 0.0;
+      }
+#else
       if (r < n) {
         // R == 1: the lane's own staging row, zeroed once (only the pattern is rewritten);
         // R > 1: ONE scratch row per lane, cleared before each of its rows
@@ -483,8 +589,10 @@ AHK_DEV int assemble_solve(Ctx& c) {
 #pragma unroll
         for (int j = 0; j < NC; j++) a[s][j] = 0.0;
       }
+#endif
     }
-    return gj_solve<V>(c, a);
+    if constexpr (V::G == 1) return lu_solve_thread<V>(c, a);
+    else return gj_solve<V>(c, a);
   } else {
     for (int r = c.sub; r < n; r += G) {
       double* Ar = A + r * RS;

@@ -1,4 +1,5 @@
 """Short single-workload run for ncu captures: python tools/ncu_target.py c2 [variant] [reps] [B]"""
+import os
 import sys
 import torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
@@ -15,6 +16,7 @@ w = W.ALL[name](B) if B else W.ALL[name]()
 circ = w.circuit(Circuit)
 e = Engine(circ, w.batch(), opts=w.opts)
 e.set_variant(real=G if name != 'c1' else -1, ac=G if name == 'c1' else -1)
+e.set_jit(os.environ.get('AHK_JIT', 'auto'))   # circuit-specialised kernels: auto / on / off
 for _ in range(reps):
     if name == 'c2':
         r = e.op()
