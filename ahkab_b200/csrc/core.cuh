@@ -154,10 +154,12 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   const int G = V::G;
   double* Pv = c.sm + c.L->Pv;
   AHK_LANES(s, p.npersist) Pv[s] = c.P(p.pstage[s]);
+#ifndef AHK_JIT                    // (the specialised build has no staging rows)
   if (V::NC > 0 && V::R == 1) {   // staging rows are zeroed once: only the sparsity
     double* A = c.A();              // pattern is rewritten per iteration
     AHK_LANES(i, p.n * c.L->RS) A[i] = 0.0;
   }
+#endif
   Grp<V::G>::sync(c.mask);
   double* Mv = c.sm + c.L->Mv;
   double* Dv = c.sm + c.L->Dv;

@@ -413,6 +413,34 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
   return 0;
 }
 
+bool wants_jit(const ahk_engine* e, long long B) {
+  return e->jit_mode == 1 || (e->jit_mode == 2 && B >= e->jit_min_batch);
+}
+
+// Variant, layout and launch shape of a small-circuit OP/DC (mode MODE_OP) or transient
+// call, and its specialised kernel if the policy asks for one (*jk = nullptr: launch the
+// interpreted kernel).  A specialised kernel has its own, smaller layout; if it cannot be
+// built under the automatic policy the call is planned again for the interpreted kernel.
+int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
+                  Launch* L, jit::Kernel** jk) {
+  *jk = nullptr;
+  for (int jit = wants_jit(e, B) ? 1 : 0; jit >= 0; jit--) {
+    int vid;
+    if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, B, real_min_blocks,
+                     [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, jit != 0).stride; },
+                     &vid))
+      return -1;
+    const VarInfo& v = real_variants()[vid];
+    *vid_out = vid;
+    *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, jit != 0 && v.NC > 0);
+    if (plan(e, B, vid, v, Ly->stride, *L, real_min_blocks(v.NC), nullptr)) return -1;
+    if (!jit || v.NC == 0) return 0;
+    if (get_jit(e, B, mode, vid, v, *Ly, *L, real_min_blocks(v.NC), method, usc, jk)) return -1;
+    if (*jk) return 0;
+  }
+  return 0;
+}
+
 int jit_launched(bool ok, const std::string& err) {
   if (!ok) return fail(err);
   g_launches++;
@@ -423,16 +451,9 @@ int jit_launched(bool ok, const std::string& err) {
 int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* d_sweep, int npts,
                  const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
                  int32_t* status, cudaStream_t s) {
-  int vid;
-  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
-                   [&](const VarInfo& q) { return make_layout(e->H, MODE_OP, 0, 0, q.G, q.NC, q.R).stride; }, &vid))
-    return -1;
-  const VarInfo& v = real_variants()[vid];
-  Layout Ly = make_layout(e->H, MODE_OP, 0, 0, v.G, v.NC, v.R);
-  Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
+  int vid; Layout Ly; Launch L;
   jit::Kernel* jk = nullptr;
-  if (get_jit(e, batch->B, MODE_OP, vid, v, Ly, L, real_min_blocks(v.NC), 0, 0, &jk)) return -1;
+  if (prepare_small(e, batch->B, MODE_OP, 0, 0, &vid, &Ly, &L, &jk)) return -1;
   if (jk) {
     KDcJ kj = {batch->vary, batch->B, DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status}};
     std::string err;
@@ -515,7 +536,7 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
     if (!fits(v, H.hdr.n)) return fail("variant does not fit this circuit");
     Opts o; std::memcpy(&o, opts, sizeof(Opts));
     const int mode = tran ? MODE_TRAN : MODE_OP;
-    Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R);
+    Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R, true);
     JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
     std::string err;
     std::vector<char> cubin = jit::compile(jit_spec_source(H, o, Ly, cfg), err);
@@ -615,18 +636,9 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   if (e->n > AHK_SMALL_NMAX) return fail("transient needs n <= 64 in this build");
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
-  int vid;
-  if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, batch->B, real_min_blocks,
-                   [&](const VarInfo& q) { return make_layout(e->H, MODE_TRAN, method, use_step_control, q.G, q.NC, q.R).stride; },
-                   &vid))
-    return -1;
-  const VarInfo& v = real_variants()[vid];
-  Layout Ly = make_layout(e->H, MODE_TRAN, method, use_step_control, v.G, v.NC, v.R);
-  Launch L;
-  if (plan(e, batch->B, vid, v, Ly.stride, L, real_min_blocks(v.NC), nullptr)) return -1;
+  int vid; Layout Ly; Launch L;
   jit::Kernel* jk = nullptr;
-  if (get_jit(e, batch->B, MODE_TRAN, vid, v, Ly, L, real_min_blocks(v.NC), method, use_step_control ? 1 : 0, &jk))
-    return -1;
+  if (prepare_small(e, batch->B, MODE_TRAN, method, use_step_control ? 1 : 0, &vid, &Ly, &L, &jk)) return -1;
   if (jk) {
     KTranJ kj = {batch->vary, batch->B, x0,
                  TranArgs{tstart, tstep, tstop, method, use_step_control, max_rows, t_out, x_out, rows, counters},

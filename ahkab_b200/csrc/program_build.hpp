@@ -363,8 +363,10 @@ enum { MODE_OP = 0, MODE_TRAN = 1 };
 // NC > 0: register variant with NC matrix columns (staging rows of NC - 1 doubles).
 // Every array is allocated only when the mode / variant / circuit needs it: the
 // bytes per instance bound how many instances are resident per SM.
+// jit: layout of a circuit-specialised kernel (jit_gen.hpp) — it assembles straight into
+// registers and needs no staging rows.
 inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_control, int G,
-                          int NC = 0, int R = 1) {
+                          int NC = 0, int R = 1, bool jit = false) {
   const Prog& h = H.hdr;
   Layout L; std::memset(&L, 0, sizeof L);
   const int n = h.n;
@@ -373,7 +375,7 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
   // register variants with several rows per lane stage through one scratch row per lane
-  L.A = take((NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS);
+  L.A = take(jit && NC > 0 ? 0 : (NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS);
   L.x = take(n); L.dx = take(n); L.T = take(n); L.res = take(n);
   L.Mv = take(h.npos);
   // the matrix values are formed while assembling: Mv (+ C1 Dv in a transient) plus Gmin

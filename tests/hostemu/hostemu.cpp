@@ -112,7 +112,7 @@ int emu_jit_source(const ahk_circuit* c, const ahk_options* o, int n_vary, const
     build_program(c, H);
     set_vary_slots(H, n_vary, slots);
     Opts q; copy_opts(o, q);
-    Layout L = make_layout(H, mode, method, usc, G, NC, R);
+    Layout L = make_layout(H, mode, method, usc, G, NC, R, true);
     JitCfg cfg = {NC, R, G, threads, min_blocks, mode, method, usc};
     std::string t = jit_spec_source(H, q, L, cfg);
     if (buf && cap > 0) {
