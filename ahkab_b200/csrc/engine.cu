@@ -91,6 +91,21 @@ struct ahk_engine {
   long long jit_min_batch = 4096;
   long long slots_epoch = 0, opts_epoch = 0;   // bumped when the varied slots / options change
   std::map<std::vector<long long>, jit::Kernel> jit_cache;
+  // host-buffer entry points (ahk_op_host): three internal streams + two chunk workspaces
+  struct HostPipe {
+    enum { NS = 8 };   // chunk slots: each has its own kernel stream, events and workspace
+    cudaStream_t s_in = nullptr, s_comp[NS] = {}, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_in[NS] = {}, ev_comp[NS] = {}, ev_out[NS] = {}, ev_done = nullptr;
+    unsigned char* ws[NS] = {};   // per slot: vary | x | resid | iters | status
+    size_t ws_bytes = 0;
+    bool ready = false;
+    // the whole chunked sequence as ONE CUDA graph (a dozen driver calls per chunk would
+    // otherwise make the call CPU bound): captured the second time the same call is seen
+    cudaStream_t s_org = nullptr;
+    std::vector<long long> last_key, graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0, graph_jit_launches = 0;
+  } hp;
 };
 
 int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_host,
@@ -424,15 +439,17 @@ bool wants_jit(const ahk_engine* e, long long B) {
 int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
                   Launch* L, jit::Kernel** jk) {
   *jk = nullptr;
+  static const bool full_layout = getenv("AHK_JIT_FULL_LAYOUT") != nullptr;   // tuning experiments
   for (int jit = wants_jit(e, B) ? 1 : 0; jit >= 0; jit--) {
     int vid;
+    const bool slim = jit != 0 && !full_layout;
     if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, B, real_min_blocks,
-                     [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, jit != 0).stride; },
+                     [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, slim).stride; },
                      &vid))
       return -1;
     const VarInfo& v = real_variants()[vid];
     *vid_out = vid;
-    *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, jit != 0 && v.NC > 0);
+    *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, slim && v.NC > 0);
     if (plan(e, B, vid, v, Ly->stride, *L, real_min_blocks(v.NC), nullptr)) return -1;
     if (!jit || v.NC == 0) return 0;
     if (get_jit(e, B, mode, vid, v, *Ly, *L, real_min_blocks(v.NC), method, usc, jk)) return -1;
@@ -501,6 +518,17 @@ void ahk_destroy(ahk_engine* e) {
   if (e->blob) cudaFree(e->blob);
   if (e->d_scratch) cudaFree(e->d_scratch);
   for (auto& kv : e->jit_cache) jit::unload(kv.second);
+  if (e->hp.ready) {
+    if (e->hp.graph_exec) cudaGraphExecDestroy(e->hp.graph_exec);
+    cudaStreamDestroy(e->hp.s_org);
+    cudaStreamDestroy(e->hp.s_in); cudaStreamDestroy(e->hp.s_out);
+    cudaEventDestroy(e->hp.ev_start); cudaEventDestroy(e->hp.ev_done);
+    for (int i = 0; i < ahk_engine::HostPipe::NS; i++) {
+      cudaStreamDestroy(e->hp.s_comp[i]);
+      cudaEventDestroy(e->hp.ev_in[i]); cudaEventDestroy(e->hp.ev_comp[i]); cudaEventDestroy(e->hp.ev_out[i]);
+      if (e->hp.ws[i]) cudaFree(e->hp.ws[i]);
+    }
+  }
   e->big.release();
   delete e;
 }
@@ -602,6 +630,141 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0, int use_gues
     return e->big.run(e, batch, -1, &v, 1, x, iters, status, resid, s, g_err, g_launches);
   }
   return run_dc_small(e, batch, -1, nullptr, 1, x0, use_guess, x, resid, iters, status, s);
+}
+
+// Operating point with HOST buffers: the batch is cut into chunks; one copy-in stream, one
+// kernel stream PER CHUNK SLOT and one copy-out stream, so that the PCIe traffic of both
+// directions overlaps the kernels — and the kernels overlap each other: these kernels are
+// latency bound (a quarter of the batch takes as long as all of it), so the chunks must
+// run side by side, not back to back.  Asynchronous: `stream` waits for the
+// last copy; the caller synchronises `stream` before reading the results.
+int ahk_op_host(ahk_engine* e, int64_t B, int n_vary, const int32_t* vary_slots, const double* vary_host,
+                int use_guess, double* x_host, double* resid_host, int32_t* iters_host,
+                int32_t* status_host, int nchunks, void* stream) {
+  if (!e || B <= 0 || n_vary < 0 || (n_vary > 0 && (!vary_slots || !vary_host)) || !x_host || !iters_host ||
+      !status_host)
+    return fail("ahk_op_host: bad argument");
+  if (e->n > AHK_SMALL_NMAX) return fail("ahk_op_host: small circuits only (n <= 64)");
+  cudaStream_t user = (cudaStream_t)stream;
+  auto& hp = e->hp;
+  const int NS = ahk_engine::HostPipe::NS;
+  if (!hp.ready) {
+    CK(cudaStreamCreateWithFlags(&hp.s_org, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&hp.ev_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&hp.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < NS; i++) {
+      CK(cudaStreamCreateWithFlags(&hp.s_comp[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&hp.ev_comp[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+    }
+    hp.ready = true;
+  }
+  const int n = e->n;
+  if (nchunks == 0) {
+    // zero-copy: the kernel reads the parameters from and writes the results to the
+    // caller's PINNED host buffers directly (unified addressing maps them into the device's
+    // address space): no DMA copies, no staging — the PCIe traffic of both directions
+    // overlaps the computation inside the one kernel
+    ahk_batch b; b.B = B; b.n_vary = n_vary; b.vary_slots = vary_slots; b.vary = vary_host;
+    if (set_batch(e, &b, user)) return -1;
+    return run_dc_small(e, &b, -1, nullptr, 1, nullptr, use_guess, x_host, resid_host, iters_host, status_host, user);
+  }
+  if (nchunks < 1) nchunks = 1;
+  if ((int64_t)nchunks > B) nchunks = (int)B;
+  const int64_t Bc_max = (B + nchunks - 1) / nchunks;
+  // workspace of one slot: vary[n_vary][Bc] | x[Bc][n] | resid[Bc][n] | iters[Bc] | status[Bc]
+  const size_t o_x = (size_t)n_vary * Bc_max * 8, o_r = o_x + (size_t)Bc_max * n * 8,
+               o_i = o_r + (size_t)Bc_max * n * 8, o_s = o_i + (((size_t)Bc_max * 4 + 7) & ~size_t(7)),
+               need = o_s + (size_t)Bc_max * 4 + 64;
+  if (need > hp.ws_bytes) {
+    CK(cudaDeviceSynchronize());
+    if (hp.graph_exec) { cudaGraphExecDestroy(hp.graph_exec); hp.graph_exec = nullptr; }   // it points into ws
+    hp.graph_key.clear(); hp.last_key.clear();
+    for (int i = 0; i < NS; i++) { if (hp.ws[i]) cudaFree(hp.ws[i]); hp.ws[i] = nullptr; }
+    for (int i = 0; i < NS; i++) CK(cudaMalloc(&hp.ws[i], need));
+    hp.ws_bytes = need;
+  }
+  // the varied slots must be installed before any chunk launches (may synchronise once)
+  {
+    ahk_batch b0; b0.B = Bc_max; b0.n_vary = n_vary; b0.vary_slots = vary_slots; b0.vary = (const double*)hp.ws[0];
+    const long long epoch = e->slots_epoch;
+    if (set_batch(e, &b0, hp.s_comp[0])) return -1;
+    if (e->slots_epoch != epoch) CK(cudaStreamSynchronize(hp.s_comp[0]));   // table upload: before ANY chunk
+  }
+  // ---- graph replay / capture / eager ------------------------------------------------------
+  const std::vector<long long> key = {B, n_vary, (long long)(size_t)vary_host, (long long)(size_t)x_host,
+                                      (long long)(size_t)resid_host, (long long)(size_t)iters_host,
+                                      (long long)(size_t)status_host, nchunks, use_guess, e->slots_epoch,
+                                      e->opts_epoch, e->jit_mode, e->jit_min_batch, e->force_vid, e->group};
+  static const bool no_graph = getenv("AHK_NO_GRAPH") != nullptr;
+  if (hp.graph_exec && key == hp.graph_key) {
+    CK(cudaGraphLaunch(hp.graph_exec, user));
+    g_launches += hp.graph_launches;
+    g_jit_launches += hp.graph_jit_launches;
+    return 0;
+  }
+  const bool capture = !no_graph && key == hp.last_key;   // second identical call: kernels are built
+  hp.last_key = key;
+  const long long l0 = g_launches.load(), j0 = g_jit_launches.load();
+  cudaStream_t org = capture ? hp.s_org : user;
+  if (capture) CK(cudaStreamBeginCapture(hp.s_org, cudaStreamCaptureModeRelaxed));
+  auto issue = [&]() -> int {
+  CK(cudaEventRecord(hp.ev_start, org));
+  CK(cudaStreamWaitEvent(hp.s_in, hp.ev_start, 0));
+  CK(cudaStreamWaitEvent(hp.s_out, hp.ev_start, 0));
+  int64_t lo = 0;
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t hi = std::min<int64_t>(B, lo + Bc_max), Bc = hi - lo;
+    if (Bc <= 0) break;
+    const int slot = c % NS;
+    cudaStream_t sc = hp.s_comp[slot];
+    unsigned char* w = hp.ws[slot];
+    double* d_vary = (double*)w; double* d_x = (double*)(w + o_x); double* d_r = (double*)(w + o_r);
+    int32_t* d_i = (int32_t*)(w + o_i); int32_t* d_s = (int32_t*)(w + o_s);
+    // copy-in: the slot's previous chunk must have been computed AND copied out
+    if (c >= NS) { CK(cudaStreamWaitEvent(hp.s_in, hp.ev_out[slot], 0)); }
+    if (n_vary)
+      CK(cudaMemcpy2DAsync(d_vary, (size_t)Bc * 8, vary_host + lo, (size_t)B * 8, (size_t)Bc * 8, (size_t)n_vary,
+                           cudaMemcpyHostToDevice, hp.s_in));
+    CK(cudaEventRecord(hp.ev_in[slot], hp.s_in));
+    // kernels
+    CK(cudaStreamWaitEvent(sc, hp.ev_in[slot], 0));   // (ev_in was recorded after ev_start / ev_out[slot])
+    ahk_batch b; b.B = Bc; b.n_vary = n_vary; b.vary_slots = vary_slots; b.vary = d_vary;
+    if (run_dc_small(e, &b, -1, nullptr, 1, nullptr, use_guess, d_x, resid_host ? d_r : nullptr, d_i, d_s, sc))
+      return -1;
+    CK(cudaEventRecord(hp.ev_comp[slot], sc));
+    // copy-out
+    CK(cudaStreamWaitEvent(hp.s_out, hp.ev_comp[slot], 0));
+    CK(cudaMemcpyAsync(x_host + lo * n, d_x, (size_t)Bc * n * 8, cudaMemcpyDeviceToHost, hp.s_out));
+    if (resid_host)
+      CK(cudaMemcpyAsync(resid_host + lo * n, d_r, (size_t)Bc * n * 8, cudaMemcpyDeviceToHost, hp.s_out));
+    CK(cudaMemcpyAsync(iters_host + lo, d_i, (size_t)Bc * 4, cudaMemcpyDeviceToHost, hp.s_out));
+    CK(cudaMemcpyAsync(status_host + lo, d_s, (size_t)Bc * 4, cudaMemcpyDeviceToHost, hp.s_out));
+    CK(cudaEventRecord(hp.ev_out[slot], hp.s_out));
+    lo = hi;
+  }
+  CK(cudaEventRecord(hp.ev_done, hp.s_out));
+  CK(cudaStreamWaitEvent(org, hp.ev_done, 0));
+  return 0;
+  };
+  const int rc = issue();
+  if (!capture) return rc;
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(hp.s_org, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(std::string("ahk_op_host: graph capture: ") + cudaGetErrorString(ce));
+  if (hp.graph_exec) { cudaGraphExecDestroy(hp.graph_exec); hp.graph_exec = nullptr; }
+  ce = cudaGraphInstantiate(&hp.graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { hp.graph_exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+  hp.graph_key = key;
+  hp.graph_launches = g_launches.load() - l0;       // kernels of one replay (counted at capture)
+  hp.graph_jit_launches = g_jit_launches.load() - j0;
+  CK(cudaGraphLaunch(hp.graph_exec, user));
+  return 0;
 }
 
 int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_values,

@@ -191,6 +191,39 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(x=x, resid=resid, iters=iters, status=status, _packed=pk['_packed'])
 
+    def op_host(self, vary_host=None, use_guess=True, want_resid=True, nchunks=4):
+        """Operating point from HOST parameters to HOST results (ahk_op_host): the batch
+        flows in chunks through copy-in / kernel / copy-out streams inside the library.
+        vary_host: pinned [n_vary][B] float64 tensor (default: the batch the engine was
+        built with).  Returns pinned host tensors; asynchronous on the current stream —
+        synchronise before reading them."""
+        if vary_host is None:
+            if self._vary_host is None:
+                self._vary_host = torch.empty(self.vary.shape, dtype=torch.float64, pin_memory=True)
+                self._vary_host.copy_(self.vary)
+                torch.cuda.synchronize(self.device)
+            vary_host = self._vary_host
+        B = vary_host.shape[1] if vary_host.numel() else self.B
+        key = ('op_host', B, bool(want_resid))
+        if not hasattr(self, '_pinned'):
+            self._pinned = {}
+        out = self._pinned.get(key)
+        if out is None:
+            out = dict(x=torch.empty((B, self.n), dtype=torch.float64, pin_memory=True),
+                       iters=torch.empty((B,), dtype=torch.int32, pin_memory=True),
+                       status=torch.empty((B,), dtype=torch.int32, pin_memory=True))
+            if want_resid:
+                out['resid'] = torch.empty((B, self.n), dtype=torch.float64, pin_memory=True)
+            self._pinned[key] = out
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_op_host(
+                self._h, B, len(self._slots), self._slots.ctypes.data_as(C.POINTER(C.c_int32)),
+                _ptr(vary_host), int(bool(use_guess)), _ptr(out['x']), _ptr(out.get('resid')),
+                _ptr(out['iters']), _ptr(out['status']), int(nchunks), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(out)
+
     def dc_sweep(self, source, sweep_values, x0=None, use_guess=True):
         src = source if isinstance(source, int) else self.elem_index(source)
         sweep = np.ascontiguousarray(sweep_values, np.float64)

@@ -57,6 +57,12 @@ C4_MAX_ROWS = 3072
 # or two waves takes as long for a quarter of the batch as for all of it (measured: C3
 # 28 -> 44 ms, C4 262 -> 679 ms with 4 / 8 chunks), so those run as one chunk.
 E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=4)
+# AHK_E2E_OP_HOST=<chunks>: route the c2 end-to-end step through ahk_op_host (host buffers,
+# chunk pipeline inside the library; 0 = zero-copy).  Measured on B200 (50 steps): one packed
+# D2H through the Engine 0.129 ms; op_host 1 / 2 / 4 / 8 chunks 0.143 / 0.136 / 0.215 / 0.244 ms
+# (every extra DMA costs ~8 us: the kernels are too short to hide them), zero-copy 0.414 ms
+# ([B][n] rows written from one lane per instance are partial PCIe sectors).
+OP_HOST = os.environ.get('AHK_E2E_OP_HOST')
 
 
 def LU(n):
@@ -134,6 +140,9 @@ class Runner(object):
         """host params -> device, analysis, every result tensor -> pinned host, cut into
         chunks and pipelined over three streams (ahkab_b200/pipeline.py): the H2D of the
         next chunk and the D2H of the previous one overlap the kernels."""
+        if self.name == 'c2' and OP_HOST is not None:
+            host = self.eng.op_host(self.vary_host, nchunks=int(OP_HOST))
+            return host, host
         if E2E_CHUNKS[self.name] == 1:
             self.eng.set_vary(self.vary_host)
             if self.name == 'c4':

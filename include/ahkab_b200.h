@@ -239,6 +239,19 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0,
            int use_guess, double* x, double* resid, int32_t* iters,
            int32_t* status, void* stream);
 
+/* Operating point with HOST buffers (what a caller holding numpy arrays binds): the same
+ * analysis as ahk_op, but parameters and results live in host memory (pinned memory for
+ * the copies to be asynchronous).  The batch is cut into `nchunks` chunks that flow
+ * through three internal streams — copy-in, kernels, copy-out — so that the PCIe traffic
+ * of both directions overlaps the kernels.  Asynchronous: `stream` is made to wait for
+ * the last copy; synchronise it before reading the results.
+ *   vary_slots host [n_vary], vary_host host [n_vary][B] (slot-major, as ahk_batch.vary)
+ *   x_host [B][n], resid_host [B][n] or NULL, iters_host [B], status_host [B] */
+int ahk_op_host(ahk_engine* e, int64_t B, int n_vary, const int32_t* vary_slots,
+                const double* vary_host, int use_guess, double* x_host,
+                double* resid_host, int32_t* iters_host, int32_t* status_host,
+                int nchunks, void* stream);
+
 /* DC sweep — replaces dc_analysis.dc_analysis (ahkab/dc_analysis.py:461-595):
  * for every sweep value (host array, the caller builds it with the
  * reference's cumulative lin/log iterators, ahkab/utilities.py:246-378) the

@@ -59,6 +59,25 @@ def test_c2_diode_op(gold):
         assert (_np(r['iters']) != g['iters']).mean() < 0.004, v
 
 
+@pytest.mark.parametrize('B,chunks', [(4096, 4), (1000, 3), (64, 1), (5, 8), (4096, 0), (77, 0)])
+def test_op_host_matches_op(B, chunks):
+    """ahk_op_host (host buffers, chunks pipelined inside the library) == ahk_op."""
+    import torch
+    w = W.c2_diode_op(B)
+    e = _engine(w)
+    r = e.op()
+    ref = {k: _np(r[k]).copy() for k in ('x', 'resid', 'iters', 'status')}
+    for _ in range(4):        # 1st call eager, 2nd captured into a CUDA graph, then replays
+        h = e.op_host(nchunks=chunks)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert np.array_equal(h[k].numpy(), ref[k]), (k, B, chunks)
+    h = e.op_host(nchunks=chunks, want_resid=False)
+    torch.cuda.synchronize()
+    assert 'resid' not in h and np.array_equal(h['x'].numpy(), ref['x'])
+    assert (ref['status'] & 1).all()
+
+
 @pytest.mark.parametrize('v', [-1, 0, 1, 7, 8, 9, 10, 11, 12])
 def test_c3_colpitts_op_tran(gold, v):
     g = gold('c3')
