@@ -46,9 +46,10 @@ def step_source():
 
 
 class _Gpu(object):
-    def __init__(self, circ, batch=None, opts=None):
+    def __init__(self, circ, batch=None, opts=None, jit='auto'):
         from ahkab_b200.engine import Engine
         self.e = Engine(circ, batch, opts=opts)
+        self.e.set_jit(jit)
 
     @staticmethod
     def _np(r):
@@ -67,13 +68,14 @@ class _Gpu(object):
 def _sims(circ, batch=None, opts=None, gpu=False):
     o = oracle.Oracle(circ, batch, opts=opts)
     if gpu:
-        return _Gpu(circ, batch, opts), o
+        return _Gpu(circ, batch, opts, jit='on' if gpu == 'jit' else 'off'), o
     import emu
     emu.set_variant(0)
     return emu.Emu(circ, batch, opts=opts), o
 
 
-BACKENDS = [pytest.param(False, id='host-build'), pytest.param(True, id='cuda', marks=pytest.mark.gpu)]
+BACKENDS = [pytest.param(False, id='host-build'), pytest.param(True, id='cuda', marks=pytest.mark.gpu),
+            pytest.param('jit', id='cuda-specialised', marks=pytest.mark.gpu)]
 
 
 @pytest.mark.parametrize('gpu', BACKENDS)
