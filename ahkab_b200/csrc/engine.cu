@@ -411,12 +411,15 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
     JitCfg cfg = {v.NC, v.R, v.G, L.threads, std::max(1, std::min(32, reg_blocks * 128 / L.threads)), mode, method, usc};
     std::string err;
     const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg);
-    if (!jit::build(spec, mode == MODE_TRAN ? "ahk_jit_tran" : "ahk_jit_dc", L.smem, k, err)) {
+    bool cached = false;
+    if (!jit::build(spec, mode == MODE_TRAN ? "ahk_jit_tran" : "ahk_jit_dc", L.smem, k, err, &cached)) {
       k.failed = true; k.why = err;
       if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] specialised kernel not built: %s\n", err.c_str());
     } else {
-      g_jit_builds++;
-      if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] specialised kernel built (mode %d, variant %d)\n", mode, vid);
+      if (!cached) g_jit_builds++;
+      if (getenv("AHK_DEBUG"))
+        fprintf(stderr, "[ahk] specialised kernel %s (mode %d, variant %d)\n",
+                cached ? "loaded from the disk cache" : "built", mode, vid);
     }
     it = e->jit_cache.emplace(key, k).first;
   }
@@ -567,8 +570,10 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
     Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R, true);
     JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
     std::string err;
-    std::vector<char> cubin = jit::compile(jit_spec_source(H, o, Ly, cfg), err);
+    bool cached = false;
+    std::vector<char> cubin = jit::compile(jit_spec_source(H, o, Ly, cfg), err, &cached);
     if (cubin.empty()) return fail(err);
+    if (!cached) g_jit_builds++;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
   } catch (const std::exception& ex) { return fail(ex.what()); }

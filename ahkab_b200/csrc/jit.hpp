@@ -11,9 +11,14 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -89,9 +94,63 @@ inline bool load(bool compile_only, std::string& err) {
   return true;
 }
 
-// spec: text of jit_spec.h.  Returns the sm_100a cubin (empty + err on failure).
-inline std::vector<char> compile(const std::string& spec, std::string& err) {
+// ---- on-disk cache of compiled kernels ----------------------------------------------------
+// $AHK_JIT_CACHE (default ~/.cache/ahkab_b200), one <hash>.cubin per (generated constants,
+// engine sources): a second process / run with the same circuit skips NVRTC.  AHK_JIT_CACHE=off
+// disables it.  Files are written to a temporary name and renamed (atomic).
+inline unsigned long long fnv1a(const char* p, size_t n, unsigned long long h = 1469598103934665603ull) {
+  for (size_t i = 0; i < n; i++) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+  return h;
+}
+inline std::string cache_path(const std::string& spec) {
+  const char* env = getenv("AHK_JIT_CACHE");
+  if (env && std::string(env) == "off") return "";
+  std::string dir;
+  if (env && *env) dir = env;
+  else if (const char* home = getenv("HOME")) dir = std::string(home) + "/.cache/ahkab_b200";
+  else return "";
+  unsigned long long h = fnv1a(spec.data(), spec.size());
+  for (int i = 0; i < g_nsources; i++) h = fnv1a(g_sources[i].text, strlen(g_sources[i].text), h);
+  h = fnv1a("sm_100a nvrtc12 lineinfo v1", 27, h);
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx.cubin", h);
+  return dir + name;
+}
+inline bool cache_read(const std::string& path, std::vector<char>& out) {
+  if (path.empty()) return false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 64;
+  if (ok) { out.resize((size_t)n); ok = fread(out.data(), 1, (size_t)n, f) == (size_t)n; }
+  fclose(f);
+  if (ok && memcmp(out.data(), "\x7f" "ELF", 4) != 0) ok = false;   // a cubin is an ELF image
+  if (!ok) out.clear();
+  return ok;
+}
+inline void cache_write(const std::string& path, const std::vector<char>& cubin) {
+  if (path.empty() || cubin.empty()) return;
+  const size_t slash = path.rfind('/');
+  const std::string dir = path.substr(0, slash);
+  for (size_t i = 1; i <= dir.size(); i++)   // mkdir -p
+    if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+// spec: text of jit_spec.h.  Returns the sm_100a cubin (empty + err on failure); *from_cache
+// tells whether NVRTC ran.
+inline std::vector<char> compile(const std::string& spec, std::string& err, bool* from_cache = nullptr) {
   std::vector<char> cubin;
+  const std::string cpath = cache_path(spec);
+  if (from_cache) *from_cache = false;
+  if (cache_read(cpath, cubin)) { if (from_cache) *from_cache = true; return cubin; }
   if (!load(true, err)) return cubin;
   Api& a = api();
   std::vector<const char*> names, texts;
@@ -119,6 +178,7 @@ inline std::vector<char> compile(const std::string& spec, std::string& err) {
   if (sz) a.GetCUBIN(prog, cubin.data());
   a.DestroyProgram(&prog);
   if (!sz) err = "NVRTC produced no cubin";
+  else cache_write(cpath, cubin);
   return cubin;
 }
 
@@ -137,9 +197,10 @@ inline std::string cu_err(CUresult r) {
 
 // Compiles + loads `entry` of the specialised translation unit (current CUDA context =
 // the runtime's primary context of the current device).
-inline bool build(const std::string& spec, const char* entry, size_t smem, Kernel& k, std::string& err) {
+inline bool build(const std::string& spec, const char* entry, size_t smem, Kernel& k, std::string& err,
+                  bool* from_cache = nullptr) {
   if (!load(false, err)) return false;
-  std::vector<char> cubin = compile(spec, err);
+  std::vector<char> cubin = compile(spec, err, from_cache);
   if (cubin.empty()) return false;
   Api& a = api();
   CUresult r = a.ModuleLoadData(&k.mod, cubin.data());

@@ -197,7 +197,9 @@ int ahk_set_variant(ahk_engine* e, int real_id, int ac_id);
  * several times fewer instructions.  mode 0 = never, 1 = always (an NVRTC failure is an
  * error), 2 = for batches of at least min_batch instances, default (2, 4096);
  * min_batch <= 0 keeps the current threshold.  The first call with a new combination pays
- * the compilation (seconds); the kernel is cached in the engine. */
+ * the compilation (seconds); the kernel is cached in the engine and, as a cubin, on disk
+ * ($AHK_JIT_CACHE, default ~/.cache/ahkab_b200; "off" disables), so that other processes and
+ * later runs with the same circuit skip NVRTC. */
 int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);

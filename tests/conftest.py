@@ -11,6 +11,10 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests', 'hoste
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+    # compiled specialised kernels: keep the tests' cubins out of ~/.cache
+    if 'AHK_JIT_CACHE' not in os.environ:
+        import tempfile
+        os.environ['AHK_JIT_CACHE'] = tempfile.mkdtemp(prefix='ahk_jit_cache_')
     # fresh checkout: build the CUDA library (nvcc cross-compiles without a GPU), the
     # oracle and the host-emulation library once, like __graft_entry__.build() does
     import subprocess

@@ -211,3 +211,31 @@ def test_gpu_specialised_lte_transient(vid):
     xa, xb = _np(ta['x']), _np(tb['x'])
     for i in np.nonzero(same)[0][:16]:
         assert np.abs(xa[i, :ra[i]] - xb[i, :rb[i]]).max() < 1e-2
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC not installed")
+def test_disk_cache_skips_nvrtc(tmp_path, monkeypatch):
+    """The cubin of a (circuit, options, variant) is stored under $AHK_JIT_CACHE and reused."""
+    import oracle
+    lib = _abi.load_library()
+    monkeypatch.setenv('AHK_JIT_CACHE', str(tmp_path / 'cache'))
+    w = W.c2_diode_op(B=16)
+    o = oracle.Oracle(w.circuit(Circuit), w.batch(), w.opts)
+
+    def compile_once():
+        nb = C.c_int64(0)
+        rc = lib.ahk_jit_compile(C.byref(o.desc.c), C.byref(o.opts), len(o.slots),
+                                 o.slots.ctypes.data_as(C.POINTER(C.c_int32)), 0, 0, 0, 2, C.byref(nb))
+        assert rc == 0, lib.ahk_last_error().decode()[:2000]
+        return nb.value
+
+    b0 = lib.ahk_jit_build_count()
+    n1 = compile_once()
+    assert lib.ahk_jit_build_count() == b0 + 1
+    files = list((tmp_path / 'cache').glob('*.cubin'))
+    assert len(files) == 1 and files[0].stat().st_size == n1
+    n2 = compile_once()                                   # served from the file: no NVRTC run
+    assert n2 == n1 and lib.ahk_jit_build_count() == b0 + 1
+    monkeypatch.setenv('AHK_JIT_CACHE', 'off')
+    compile_once()
+    assert lib.ahk_jit_build_count() == b0 + 2
