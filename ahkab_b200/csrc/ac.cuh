@@ -153,6 +153,7 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
       const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
+#ifdef AHK_BCAST_SHFL
       if (G > 1 && R == 1) {
         // one row per lane: every element of the pivot row is fetched from the owner's
         // registers right where it is used (4 shuffles per complex element) — no pivot-row
@@ -169,6 +170,31 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
           a[0][j].re -= l.re * pre - l.im * pim;
           a[0][j].im -= l.re * pim + l.im * pre;
         }
+#else
+      if (G > 1 && R == 1) {
+        // one row per lane: the owner publishes its row in one of two shared-memory buffers
+        // (16-byte stores), one group barrier, then every lane reads each element right
+        // where it is used (one 16-byte broadcast load per complex element instead of four
+        // shuffles; no pivot-row copy in registers).  Two buffers: a lane can only reach the
+        // barrier of step k+1 after its reads of step k, so buffer k & 1 is free again at k+2.
+        cd* buf = pvb + (k & 1) * NC;
+        if (mine) {
+#pragma unroll
+          for (int j = k; j < NC; j++) buf[j] = a[0][j];
+        }
+        Grp<G>::sync(c.mask);
+        const cd pk = buf[k];
+        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
+        const cd inv = crecip(pk);
+        cd l = cmul(a[0][k], inv);
+        if (mine) l = cd{0.0, 0.0};
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) {
+          const cd pv = buf[j];
+          a[0][j].re -= l.re * pv.re - l.im * pv.im;
+          a[0][j].im -= l.re * pv.im + l.im * pv.re;
+        }
+#endif
       } else {
         cd pv[NC > 0 ? NC : 1];
         if (G > 1) {

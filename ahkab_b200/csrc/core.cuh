@@ -357,6 +357,7 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
       const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
+#ifdef AHK_BCAST_SHFL
       if (G > 1 && R == 1) {
         // one row per lane: every element of the pivot row is fetched from the owner's
         // registers right where it is used — no pivot-row copy in registers, no
@@ -366,6 +367,25 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
         const double l = mine ? 0.0 : a[0][k] * (1.0 / pk);
 #pragma unroll
         for (int j = k + 1; j < NC; j++) a[0][j] -= l * Grp<G>::bcast(a[0][j], own, c.mask);
+#else
+      if (G > 1 && R == 1) {
+        // one row per lane: the owner publishes its row in one of two shared-memory buffers,
+        // one group barrier, then every lane reads each element right where it is used (one
+        // broadcast load per element instead of two shuffles and their run-time-mask checks;
+        // no pivot-row copy in registers).  Two buffers: a lane reaches the barrier of step
+        // k+1 only after its reads of step k, so buffer k & 1 is free again at step k+2.
+        double* buf = pvb + (k & 1) * NC;
+        if (mine) {
+#pragma unroll
+          for (int j = k; j < NC; j++) buf[j] = a[0][j];
+        }
+        Grp<G>::sync(c.mask);
+        const double pk = buf[k];
+        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
+        const double l = mine ? 0.0 : a[0][k] * (1.0 / pk);
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) a[0][j] -= l * buf[j];
+#endif
       } else {
         double pv[NC > 0 ? NC : 1];
         if (G > 1) {   // the owner lane publishes its row, everybody reads it back

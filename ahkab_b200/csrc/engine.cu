@@ -453,9 +453,11 @@ int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int
     const VarInfo& v = real_variants()[vid];
     *vid_out = vid;
     *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, slim && v.NC > 0);
-    if (plan(e, B, vid, v, Ly->stride, *L, real_min_blocks(v.NC), nullptr)) return -1;
+    static const int minb_env = getenv("AHK_JIT_MINB") ? atoi(getenv("AHK_JIT_MINB")) : 0;   // tuning
+    const int rb = (jit && minb_env > 0) ? minb_env : real_min_blocks(v.NC);
+    if (plan(e, B, vid, v, Ly->stride, *L, rb, nullptr)) return -1;
     if (!jit || v.NC == 0) return 0;
-    if (get_jit(e, B, mode, vid, v, *Ly, *L, real_min_blocks(v.NC), method, usc, jk)) return -1;
+    if (get_jit(e, B, mode, vid, v, *Ly, *L, rb, method, usc, jk)) return -1;
     if (*jk) return 0;
   }
   return 0;
