@@ -11,7 +11,9 @@
 // memory for the generic fallback Var<0,0,G>.
 #pragma once
 #include "core.cuh"
+#ifndef AHK_JIT   // (specialised build: AcLayout is a set of constants from jit_spec.h)
 #include "program_build.hpp"
+#endif
 
 namespace ahk {
 
@@ -39,6 +41,7 @@ AHK_DEV cd cdivv(cd a, cd b) {   // Smith's algorithm (what C / numpy use)
   }
 }
 
+#ifndef AHK_JIT
 struct AcLayout {
   Layout L;          // real arrays shared with core.cuh (Mv, Dv, Bv, dout, dst, x=xr, bytes, Pv)
   int RS;            // complex row stride (elements) of the staging / fallback matrix
@@ -71,6 +74,8 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
   return A;
 }
 
+#endif  // AHK_JIT
+
 struct AcArgs {
   const double* x_op;      // [B][n] or null
   const double* omegas;    // device [npts]
@@ -79,6 +84,9 @@ struct AcArgs {
   double* x_out;           // [B][npts][n] complex
   int* status;
 };
+
+// kernel parameters of the circuit-specialised AC kernel (jit_kernels.cuh; filled by engine.cu)
+struct KAcJ { const double* vary; long long B; AcArgs a; int nchunks; };
 
 // generic fallback: complex LU + back-substitution on the shared-memory matrix
 template <int G>

@@ -399,7 +399,8 @@ KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
 // The specialised kernel for (analysis, variant, launch shape, options, varied slots) —
 // compiled on first use, cached in the engine.  *out = nullptr: use the interpreted kernel.
 int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, const Layout& Ly,
-            const Launch& L, int reg_blocks, int method, int usc, jit::Kernel** out) {
+            const Launch& L, int reg_blocks, int method, int usc, jit::Kernel** out,
+            const JitAc* ac = nullptr) {
   *out = nullptr;
   if (e->jit_mode == 0 || v.NC == 0) return 0;   // the generic shared-memory fallback is not specialised
   if (e->jit_mode == 2 && B < e->jit_min_batch) return 0;
@@ -410,9 +411,10 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
     jit::Kernel k;
     JitCfg cfg = {v.NC, v.R, v.G, L.threads, std::max(1, std::min(32, reg_blocks * 128 / L.threads)), mode, method, usc};
     std::string err;
-    const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg);
+    const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg, ac);
     bool cached = false;
-    if (!jit::build(spec, mode == MODE_TRAN ? "ahk_jit_tran" : "ahk_jit_dc", L.smem, k, err, &cached)) {
+    const char* entry = mode == JIT_MODE_AC ? "ahk_jit_ac" : (mode == MODE_TRAN ? "ahk_jit_tran" : "ahk_jit_dc");
+    if (!jit::build(spec, entry, L.smem, k, err, &cached)) {
       k.failed = true; k.why = err;
       if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] specialised kernel not built: %s\n", err.c_str());
     } else {
@@ -559,21 +561,32 @@ int64_t ahk_jit_launch_count(void) { return g_jit_launches.load(); }
 int64_t ahk_jit_build_count(void) { return g_jit_builds.load(); }
 
 int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary, const int32_t* vary_slots,
-                    int tran, int method, int use_step_control, int variant_id, int64_t* cubin_bytes) {
-  if (!circ || !opts || variant_id < 2 || variant_id >= AHK_N_REAL_VARIANTS) return fail("ahk_jit_compile: bad argument");
+                    int kind, int method, int use_step_control, int variant_id, int64_t* cubin_bytes) {
+  if (!circ || !opts || kind < 0 || kind > 2 || variant_id < 2 ||
+      variant_id >= (kind == 2 ? AHK_N_AC_VARIANTS : AHK_N_REAL_VARIANTS))
+    return fail("ahk_jit_compile: bad argument");
   try {
     HostProg H;
     build_program(circ, H);
     set_vary_slots(H, n_vary, vary_slots);
-    const VarInfo& v = real_variants()[variant_id];
+    const VarInfo& v = (kind == 2 ? ac_variants() : real_variants())[variant_id];
     if (!fits(v, H.hdr.n)) return fail("variant does not fit this circuit");
     Opts o; std::memcpy(&o, opts, sizeof(Opts));
-    const int mode = tran ? MODE_TRAN : MODE_OP;
-    Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R, true);
-    JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
+    std::string spec;
+    if (kind == 2) {
+      AcLayout AL = make_ac_layout(H, v.G, v.NC);
+      const JitAc ja = {AL.RS, AL.Ac, AL.xc, AL.dxc, AL.Nac, AL.pvc, AL.stride};
+      JitCfg cfg = {v.NC, v.R, v.G, 128, ac_min_blocks(v.NC), JIT_MODE_AC, 0, 0};
+      spec = jit_spec_source(H, o, AL.L, cfg, &ja);
+    } else {
+      const int mode = kind ? MODE_TRAN : MODE_OP;
+      Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R, true);
+      JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
+      spec = jit_spec_source(H, o, Ly, cfg);
+    }
     std::string err;
     bool cached = false;
-    std::vector<char> cubin = jit::compile(jit_spec_source(H, o, Ly, cfg), err, &cached);
+    std::vector<char> cubin = jit::compile(spec, err, &cached);
     if (cubin.empty()) return fail(err);
     if (!cached) g_jit_builds++;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
@@ -853,6 +866,16 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     k_fill_i32<<<(int)nb, 256, 0, s>>>(status, batch->B, AHK_ST_OK);
     CK(cudaGetLastError());
     g_launches++;
+  }
+  if (wants_jit(e, batch->B) && v.NC > 0) {   // the kernel compiled for this circuit (jit_gen.hpp)
+    const JitAc ja = {AL.RS, AL.Ac, AL.xc, AL.dxc, AL.Nac, AL.pvc, AL.stride};
+    jit::Kernel* jk = nullptr;
+    if (get_jit(e, batch->B, JIT_MODE_AC, vid, v, AL.L, L, ac_min_blocks(v.NC), 0, 0, &jk, &ja)) return -1;
+    if (jk) {
+      KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, nchunks};
+      std::string err;
+      return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
+    }
   }
   KAc k;
   k.p = e->dprog; k.o = e->o; k.AL = AL;

@@ -9,6 +9,9 @@
 #error "jit_kernels.cuh needs the generated jit_spec.h first"
 #endif
 #include "entry.cuh"
+#if AHK_JIT_MODE == 2
+#include "ac.cuh"
+#endif
 
 namespace ahk {
 
@@ -24,6 +27,21 @@ ahk_jit_dc(const __grid_constant__ KDcJ k) {
   Ctx c; long long u;
   if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
   run_dc<JitVar>(c, k.a);
+}
+#elif AHK_JIT_MODE == 2
+__device__ const AcLayout jit_aclayout{};
+extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
+ahk_jit_ac(const __grid_constant__ KAcJ k) {   // unit = (instance, frequency chunk), as k_ac.cu
+  Ctx c; long long u;
+  if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_aclayout.L, AcLayout::stride, k.vary, k.B,
+                           k.B * k.nchunks, u)) return;
+  c.inst = u / k.nchunks;
+  const int ch = (int)(u % k.nchunks);
+  AcArgs a = k.a;
+  const int per = (a.npts + k.nchunks - 1) / k.nchunks;
+  a.f0 = ch * per;
+  a.f1 = min(a.npts, a.f0 + per);
+  run_ac<JitVar>(c, jit_aclayout, a);
 }
 #else
 extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)

@@ -204,11 +204,11 @@ int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);
 int64_t ahk_jit_build_count(void);
-/* Host-only check (needs NVRTC, no GPU): compiles the specialised OP/DC (tran = 0) or
- * transient (tran = 1) kernel of this circuit for kernel variant variant_id and returns
- * the size of the sm_100a cubin. */
+/* Host-only check (needs NVRTC, no GPU): compiles the specialised OP/DC (kind = 0),
+ * transient (kind = 1) or AC (kind = 2; variant ids of the AC table) kernel of this circuit
+ * for kernel variant variant_id and returns the size of the sm_100a cubin. */
 int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary,
-                    const int32_t* vary_slots, int tran, int method,
+                    const int32_t* vary_slots, int kind, int method,
                     int use_step_control, int variant_id, int64_t* cubin_bytes);
 const char* ahk_last_error(void);
 /* Number of kernel launches issued by this library so far (all engines). */

@@ -43,7 +43,9 @@ CASES = [('c2', W.c2_diode_op, 0, 'TRAP', 0, (2, 3, 4)),
          ('c3', W.c3_colpitts, 1, 'TRAP', 0, (7,)),
          ('c3op', W.c3_colpitts, 0, 'TRAP', 0, (7,)),
          ('c4', W.c4_ring3, 1, 'GEAR2', 1, (3, 5)),
-         ('c4ie', W.c4_ring3, 1, 'IMPLICIT_EULER', 1, (5,))]
+         ('c4ie', W.c4_ring3, 1, 'IMPLICIT_EULER', 1, (5,)),
+         ('c1ac', W.c1_butterworth, 2, 'TRAP', 0, (4, 5)),       # AC table: Var<16,1,16>, Var<24,1,32>
+         ('c3ac', W.c3_colpitts, 2, 'TRAP', 0, (4,))]
 
 
 @pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC not installed")
@@ -239,3 +241,19 @@ def test_disk_cache_skips_nvrtc(tmp_path, monkeypatch):
     monkeypatch.setenv('AHK_JIT_CACHE', 'off')
     compile_once()
     assert lib.ahk_jit_build_count() == b0 + 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('vid', [-1, 4, 5])
+def test_gpu_specialised_ac(vid):
+    w = W.c1_butterworth(512)
+    e = _engine(w)
+    e.set_variant(ac=vid)
+    om = common.c1_omegas()
+    e.set_jit('off'); a = e.ac(om)
+    n0 = e.jit_launch_count()
+    e.set_jit('on'); b = e.ac(om)
+    assert e.jit_launch_count() == n0 + 1
+    xa, xb = _np(a['x']), _np(b['x'])
+    assert (_np(b['status']) & 1).all() and (_np(a['status']) == _np(b['status'])).all()
+    assert np.abs(xa - xb).max() <= 1e-10 * np.abs(xa).max()
