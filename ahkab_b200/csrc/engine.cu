@@ -452,7 +452,10 @@ int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int
                      [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, slim).stride; },
                      &vid))
       return -1;
-    const VarInfo& v = real_variants()[vid];
+    VarInfo v = real_variants()[vid];
+    // a specialised kernel is compiled for this circuit: exactly n + 1 matrix columns, no
+    // padding up to the column count of the variant table
+    if (jit && v.NC > 0) v.NC = e->n + 1;
     *vid_out = vid;
     *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, slim && v.NC > 0);
     static const int minb_env = getenv("AHK_JIT_MINB") ? atoi(getenv("AHK_JIT_MINB")) : 0;   // tuning
@@ -868,13 +871,18 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     g_launches++;
   }
   if (wants_jit(e, batch->B) && v.NC > 0) {   // the kernel compiled for this circuit (jit_gen.hpp)
-    const JitAc ja = {AL.RS, AL.Ac, AL.xc, AL.dxc, AL.Nac, AL.pvc, AL.stride};
+    VarInfo vj = v;
+    vj.NC = e->n + 1;                         // exactly n + 1 columns, no padding
+    const AcLayout ALj = make_ac_layout(e->H, vj.G, vj.NC);
+    Launch Lj;
+    if (plan(e, units, vid, vj, ALj.stride, Lj, ac_min_blocks(v.NC), nullptr)) return -1;
+    const JitAc ja = {ALj.RS, ALj.Ac, ALj.xc, ALj.dxc, ALj.Nac, ALj.pvc, ALj.stride};
     jit::Kernel* jk = nullptr;
-    if (get_jit(e, batch->B, JIT_MODE_AC, vid, v, AL.L, L, ac_min_blocks(v.NC), 0, 0, &jk, &ja)) return -1;
+    if (get_jit(e, batch->B, JIT_MODE_AC, vid, vj, ALj.L, Lj, ac_min_blocks(v.NC), 0, 0, &jk, &ja)) return -1;
     if (jk) {
       KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, nchunks};
       std::string err;
-      return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
+      return jit_launched(jit::launch(*jk, Lj.blocks, Lj.threads, Lj.smem, s, &kj, err), err);
     }
   }
   KAc k;

@@ -79,7 +79,7 @@ AC_FLOP = 4 * LU(14) + 8 * 14 ** 2            # per (instance, frequency)
 C5_FLOP = (2 * LU(257) - 2 * 2 * 257 ** 2) / 10.0 + 2 * (2 * 257 ** 2 + 2 * 257 ** 2)
 
 
-JIT_MODE = 'auto'   # --jit: circuit-specialised kernels (ahk_set_jit); auto = batches >= 4096
+JIT_MODE = 'auto'   # --jit: circuit-specialised kernels (ahk_set_jit); auto = batches >= 1024 here
 
 
 # ---------------------------------------------------------------------------------
@@ -99,7 +99,9 @@ class Runner(object):
         self.w = W.ALL[name](B=B, seed=seeds[name] + 1000 * seed_off)
         self.circ = self.w.circuit(Circuit)
         self.eng = Engine(self.circ, self.w.batch(), opts=self.w.opts)
-        self.eng.set_jit(JIT_MODE)
+        # (threshold 1024: the chunks of the pipelined end-to-end paths are sub-batches of
+        # 1024 instances and the bench repeats every call, so the compilation amortises)
+        self.eng.set_jit(JIT_MODE, min_batch=1024)
         self.B = B
         self.pipe = None
         self.vary_host = torch.empty(self.eng.vary.shape, dtype=torch.float64,
@@ -502,7 +504,7 @@ def main():
     ap.add_argument('--only', action='store_true', help='headline workload only')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--jit', default='auto', choices=['auto', 'on', 'off'],
-                    help='circuit-specialised kernels: auto (batches >= 4096), on, off (interpreted)')
+                    help='circuit-specialised kernels: auto (batches >= 1024), on, off (interpreted)')
     args = ap.parse_args()
     global JIT_MODE
     JIT_MODE = args.jit
