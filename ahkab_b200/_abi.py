@@ -65,7 +65,8 @@ EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_dc_sweep', 'ahk_tran', 'ahk_ac', 'ahk_probe_fp64',
            'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info',
            'ahk_h2d_columns', 'ahk_set_jit', 'ahk_jit_launch_count',
-           'ahk_jit_build_count', 'ahk_jit_compile', 'ahk_op_host')
+           'ahk_jit_build_count', 'ahk_jit_compile', 'ahk_op_host',
+           'ahk_set_jit_shape')
 
 
 def _dp(a):
@@ -169,6 +170,8 @@ def load_library(path=None):
     lib.ahk_op_host.restype = C.c_int
     lib.ahk_set_jit.argtypes = [vp, C.c_int, i64]
     lib.ahk_set_jit.restype = C.c_int
+    lib.ahk_set_jit_shape.argtypes = [vp, C.c_int, C.c_int]
+    lib.ahk_set_jit_shape.restype = C.c_int
     lib.ahk_jit_launch_count.argtypes = []
     lib.ahk_jit_launch_count.restype = i64
     lib.ahk_jit_build_count.argtypes = []

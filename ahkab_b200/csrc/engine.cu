@@ -89,6 +89,11 @@ struct ahk_engine {
   // NVRTC is not available
   int jit_mode = 2;
   long long jit_min_batch = 4096;
+  int jit_R = 0, jit_G = 0;   // forced (rows per lane, lanes per instance) of the specialised kernels, 0 = heuristic
+  // variant / layout / launch shape / kernel of recent small-circuit calls, so that a repeated
+  // call (the common case: same batch size again and again) goes straight to the launch
+  struct Prepared { int vid; Layout Ly; Launch L; jit::Kernel* jk; };
+  std::map<std::vector<long long>, Prepared> prepared;
   long long slots_epoch = 0, opts_epoch = 0;   // bumped when the varied slots / options change
   std::map<std::vector<long long>, jit::Kernel> jit_cache;
   // host-buffer entry points (ahk_op_host): three internal streams + two chunk workspaces
@@ -310,7 +315,7 @@ int plan(const ahk_engine* e, long long units, int vid, const VarInfo& v, int st
 // wave).  stride_of(v) = doubles per instance of the layout.
 template <typename StrideOf>
 int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, long long units,
-                 int reg_blocks_of(int), StrideOf stride_of, int* vid) {
+                 int reg_blocks_of(int), StrideOf stride_of, int* vid, bool exact_nc = false) {
   const int n = e->n;
   if (forced >= 0) {
     if (forced >= ntab || !fits(tab[forced], n)) return fail("forced kernel variant does not fit this circuit");
@@ -318,24 +323,28 @@ int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, 
     *vid = forced;
     return 0;
   }
+  // exact_nc: the choice is made for a specialised kernel, which is compiled with exactly
+  // n + 1 columns whatever the table says — every fitting (R, G) shape competes
+  auto eff = [&](int i) { VarInfo q = tab[i]; if (exact_nc && q.NC > 0) q.NC = n + 1; return q; };
   const long long per_sm = (units + e->sm_count - 1) / e->sm_count;   // instances one SM must hold
   int minNC = 1 << 30;
   for (int i = 2; i < ntab; i++)
-    if (fits(tab[i], n) && (e->group <= 0 || tab[i].G == e->group)) minNC = std::min(minNC, tab[i].NC);
+    if (fits(tab[i], n) && (e->group <= 0 || tab[i].G == e->group)) minNC = std::min(minNC, eff(i).NC);
   int best = -1, best_one_wave = -1;
   long long best_lanes = -1;
   for (int i = 2; i < ntab; i++) {
-    if (!fits(tab[i], n) || tab[i].NC != minNC) continue;
-    if (e->group > 0 && tab[i].G != e->group) continue;
+    const VarInfo q = eff(i);
+    if (!fits(tab[i], n) || q.NC != minNC) continue;
+    if (e->group > 0 && q.G != e->group) continue;
     long long res = 0;
     Launch tmp;
-    if (plan(e, units, i, tab[i], stride_of(tab[i]), tmp, reg_blocks_of(tab[i].NC), &res))
+    if (plan(e, units, i, q, stride_of(q), tmp, reg_blocks_of(q.NC), &res))
       continue;   // does not fit in shared memory
-    const long long lanes = std::min(res, per_sm) * tab[i].G;
-    if (res >= per_sm && per_sm * tab[i].G >= 128 &&
-        (best_one_wave < 0 || tab[i].G < tab[best_one_wave].G))
+    const long long lanes = std::min(res, per_sm) * q.G;
+    if (res >= per_sm && per_sm * q.G >= 128 &&
+        (best_one_wave < 0 || q.G < tab[best_one_wave].G))
       best_one_wave = i;
-    if (best < 0 || lanes > best_lanes || (lanes == best_lanes && tab[i].G < tab[best].G)) {
+    if (best < 0 || lanes > best_lanes || (lanes == best_lanes && q.G < tab[best].G)) {
       best = i; best_lanes = lanes;
     }
   }
@@ -441,18 +450,43 @@ bool wants_jit(const ahk_engine* e, long long B) {
 // call, and its specialised kernel if the policy asks for one (*jk = nullptr: launch the
 // interpreted kernel).  A specialised kernel has its own, smaller layout; if it cannot be
 // built under the automatic policy the call is planned again for the interpreted kernel.
+int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
+                           Launch* L, jit::Kernel** jk);
+
 int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
                   Launch* L, jit::Kernel** jk) {
+  const std::vector<long long> key = {B, mode, method, usc, e->slots_epoch, e->opts_epoch, e->jit_mode,
+                                      e->jit_min_batch, e->force_vid, e->group, e->jit_R, e->jit_G};
+  auto it = e->prepared.find(key);
+  if (it != e->prepared.end()) {
+    *vid_out = it->second.vid; *Ly = it->second.Ly; *L = it->second.L; *jk = it->second.jk;
+    return 0;
+  }
+  if (prepare_small_uncached(e, B, mode, method, usc, vid_out, Ly, L, jk)) return -1;
+  if (e->prepared.size() > 64) e->prepared.clear();
+  e->prepared[key] = ahk_engine::Prepared{*vid_out, *Ly, *L, *jk};
+  return 0;
+}
+
+int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
+                           Launch* L, jit::Kernel** jk) {
   *jk = nullptr;
   static const bool full_layout = getenv("AHK_JIT_FULL_LAYOUT") != nullptr;   // tuning experiments
   for (int jit = wants_jit(e, B) ? 1 : 0; jit >= 0; jit--) {
     int vid;
     const bool slim = jit != 0 && !full_layout;
-    if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, B, real_min_blocks,
-                     [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, slim).stride; },
-                     &vid))
-      return -1;
-    VarInfo v = real_variants()[vid];
+    VarInfo v;
+    if (jit && e->jit_G > 0) {
+      // a specialised kernel is not bound to the compiled variant table: any (R, G) shape
+      vid = 1000 + e->jit_R * 64 + e->jit_G;
+      v = VarInfo{e->n + 1, e->jit_R, e->jit_G};
+    } else {
+      if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, B, real_min_blocks,
+                       [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, slim).stride; },
+                       &vid, jit != 0))
+        return -1;
+      v = real_variants()[vid];
+    }
     // a specialised kernel is compiled for this circuit: exactly n + 1 matrix columns, no
     // padding up to the column count of the variant table
     if (jit && v.NC > 0) v.NC = e->n + 1;
@@ -557,6 +591,17 @@ int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch) {
   if (mode < 0 || mode > 2) return fail("ahk_set_jit: mode must be 0 (off), 1 (on) or 2 (auto)");
   e->jit_mode = mode;
   if (min_batch > 0) e->jit_min_batch = min_batch;
+  return 0;
+}
+
+int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes) {
+  if (!e) return fail("null engine");
+  if (rows_per_lane == 0 && lanes == 0) { e->jit_R = e->jit_G = 0; return 0; }
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+    return fail("ahk_set_jit_shape: lanes must be 1,2,4,8,16,32");
+  if (rows_per_lane < 1 || rows_per_lane * lanes < e->n || e->n + 1 > 32 || rows_per_lane > 16)
+    return fail("ahk_set_jit_shape: rows_per_lane * lanes must cover the n <= 31 unknowns");
+  e->jit_R = rows_per_lane; e->jit_G = lanes;
   return 0;
 }
 

@@ -113,6 +113,13 @@ class Engine(object):
             raise EngineError(self._err())
         return self
 
+    def set_jit_shape(self, rows_per_lane=0, lanes=0):
+        """Shape of the specialised OP / DC / transient kernels (ahk_set_jit_shape);
+        (0, 0) = the heuristic's variant."""
+        if self.lib.ahk_set_jit_shape(self._h, int(rows_per_lane), int(lanes)) != 0:
+            raise EngineError(self._err())
+        return self
+
     def jit_launch_count(self):
         return int(self.lib.ahk_jit_launch_count())
 

@@ -274,6 +274,11 @@ class Timer(object):
             sampler.active.set()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(steps)]
+        # ~1 ms spin kernel ahead of the first step: the host gets a head start on the stream,
+        # so that the interval between a step's two events is device time and cannot contain
+        # host launch latency (measured with tools/c2time.py: without it a 20 us kernel shows
+        # occasional 40-160 us "steps" whenever the enqueueing thread is descheduled)
+        torch.cuda._sleep(2000000)
         for a, b in ev:
             self.flush.zero_()
             a.record()

@@ -201,6 +201,10 @@ int ahk_set_variant(ahk_engine* e, int real_id, int ac_id);
  * ($AHK_JIT_CACHE, default ~/.cache/ahkab_b200; "off" disables), so that other processes and
  * later runs with the same circuit skip NVRTC. */
 int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch);
+/* Tuning: shape of the specialised OP/DC/transient kernels — rows of the matrix per lane and
+ * lanes per instance (1,2,4,8,16,32; rows_per_lane * lanes >= n).  Being compiled on demand
+ * they are not bound to the compiled variant table.  (0, 0) = the heuristic's variant. */
+int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);
 int64_t ahk_jit_build_count(void);

@@ -55,3 +55,16 @@ for vid in [-1] + _abi.fitting_variants(e.n, 'real'):
                 name, w.B, vid, table.get(vid, 'heuristic'), mode, ms, units() / ms * 1e3), flush=True)
         except EngineError as ex:
             print('%s variant %d jit %s: %s' % (name, vid, mode, str(ex)[:200]), flush=True)
+# specialised kernels of any (rows per lane, lanes per instance) shape
+e.set_variant(real=-1); e.set_jit('on')
+n = e.n
+for G in (1, 2, 4, 8, 16):
+    R = (n + G - 1) // G
+    if R > 16 or (only and -2 not in only):
+        continue
+    try:
+        e.set_jit_shape(R, G)
+        ms = timeit(fn, 2 if name != 'c2' else 5)
+        print('%s B=%d shape R=%d G=%-2d        jit on  %10.4f ms  %.4g units/s' % (name, w.B, R, G, ms, units() / ms * 1e3), flush=True)
+    except EngineError as ex:
+        print('%s shape R=%d G=%d: %s' % (name, R, G, str(ex)[:300]), flush=True)
