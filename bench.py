@@ -269,16 +269,26 @@ class Timer(object):
         r = None
         for _ in range(warmup):
             r = fn()
+        # keep the GPU busy for >= 0.3 s before timing: a 20 us kernel after W = 3 warm-up steps
+        # is otherwise measured while the SM clock is still ramping up from idle (10-step runs
+        # of C2 read 0.026-0.043 ms against 0.020 ms for 50-step runs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.3:
+            r = fn()
+            torch.cuda.synchronize()
         self.barrier()
         if sampler is not None:
             sampler.active.set()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(steps)]
-        # ~1 ms spin kernel ahead of the first step: the host gets a head start on the stream,
-        # so that the interval between a step's two events is device time and cannot contain
-        # host launch latency (measured with tools/c2time.py: without it a 20 us kernel shows
-        # occasional 40-160 us "steps" whenever the enqueueing thread is descheduled)
-        torch.cuda._sleep(2000000)
+        # one untimed step ahead of the K timed ones, in the same stream without a
+        # synchronisation in between: the first step after a barrier otherwise reads 0.10-0.20
+        # ms for a 0.018 ms kernel (per-step trace, AHK_BENCH_DEBUG=1) because the device waits
+        # for the host to enqueue it; from the second step on the host runs ahead of the stream
+        # (every step starts with an 85 us L2 flush) and the event pairs measure device time
+        self.flush.zero_()
+        r = fn()
         for a, b in ev:
             self.flush.zero_()
             a.record()
@@ -288,6 +298,8 @@ class Timer(object):
         if sampler is not None:
             sampler.active.clear()
         ms = sum(a.elapsed_time(b) for a, b in ev)
+        if os.environ.get('AHK_BENCH_DEBUG'):
+            sys.stderr.write('per-step ms: %s\n' % ' '.join('%.4f' % a.elapsed_time(b) for a, b in ev))
         if self.dist_on:
             import torch.distributed as dist
             t = torch.tensor([ms], dtype=torch.float64, device=self.flush.device)
@@ -540,7 +552,8 @@ def main():
     warmup = max(3, args.warmup)
     timer = Timer(dist_on, device)
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get('AHK_NO_SAMPLER'):
+        sampler.start()
     hbm_peak, hbm_src = peaks()
     probe = Runner('c2', B=1024)
     fp64_peak = measure_fp64_peak(probe.eng, timer)
