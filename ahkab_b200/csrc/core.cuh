@@ -63,6 +63,11 @@ struct Grp {
     for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(m, v, o));
     return v;
   }
+  static AHK_DEV double fmax_all(double v, unsigned m) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o));
+    return v;
+  }
   static AHK_DEV int all(int pred, unsigned m) { return G > 1 ? __all_sync(m, pred) : pred; }
   static AHK_DEV int any(int pred, unsigned m) { return G > 1 ? __any_sync(m, pred) : pred; }
   static AHK_DEV double bcast(double v, int src, unsigned m) { return __shfl_sync(m, v, src, G); }
@@ -92,6 +97,7 @@ template <int G>
 struct Grp {  // host emulation (tests/hostemu): G == 1 only
   static void sync(unsigned) {}
   static double fmin_all(double v, unsigned) { return v; }
+  static double fmax_all(double v, unsigned) { return v; }
   static int all(int p, unsigned) { return p; }
   static int any(int p, unsigned) { return p; }
   static double bcast(double v, int, unsigned) { return v; }
@@ -647,15 +653,18 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
     double td = 1.0;
     if (o.nr_damp_first_iters) td = it < 10 ? 1e-2 : (it < 20 ? 0.1 : 1.0);
     if (o.nl_voltages_lock && p.nlock) {
-      double t = 1.0;
+      // min over the pairs of lim / d  ==  lim / (max over the pairs of d): the quotient is
+      // monotone in d, so ONE division per iteration gives the identical value
+      double dmax = 0.0;
       AHK_LANES(k, p.nlock) {
         int n1 = p.lock[2 * k], n2 = p.lock[2 * k + 1];
         double d;
         if (n1 != 0) d = n2 != 0 ? fabs(dx[n1 - 1] - dx[n2 - 1]) : fabs(dx[n1 - 1]);
         else d = fabs(dx[n2 != 0 ? n2 - 1 : n - 1]);   // dx[-1] quirk, dc_analysis.py:941
-        if (d > lim) t = fmin(t, lim / d);
+        if (d > dmax) dmax = d;                         // (a NaN step never wins: as `d > lim` before)
       }
-      td = fmin(td, Grp<G>::fmin_all(t, c.mask));
+      dmax = Grp<G>::fmax_all(dmax, c.mask);
+      if (dmax > lim) td = fmin(td, lim / dmax);
     }
     // convergence_check (utilities.py:392-549): np.allclose(x, x + dx) per unit class and
     // |residual| <= the other class's absolute tolerance; NaN never passes

@@ -452,10 +452,13 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     r = Runner(name, seed_off=rank)
     eng = r.eng
     # kernel path, inputs resident
+    # kernels of this library per step (counted on one untimed step), times the K timed steps
+    r.step()
     l0, j0 = eng.launch_count(), eng.jit_launch_count()
+    r.step()
+    launches = (eng.launch_count() - l0) * steps
+    jit_launches = (eng.jit_launch_count() - j0) * steps
     ms, raw = timer.timed(r.step, steps, warmup, sampler)
-    launches = (eng.launch_count() - l0) // (steps + warmup) * steps
-    jit_launches = (eng.jit_launch_count() - j0) // (steps + warmup) * steps
     units = all_sum(r.units(raw), dist_on, device)
     flop, byts = r.algo(raw)
     value = units * steps / (ms * 1e-3)
