@@ -144,7 +144,7 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
   cd pd[R > 0 ? R : 1];
   int ps[R > 0 ? R : 1];
 #pragma unroll
-  for (int s = 0; s < R; s++) { pd[s] = cd{1.0, 0.0}; ps[s] = 0; }
+  for (int s = 0; s < R; s++) { pd[s] = cd{1.0, 0.0}; ps[s] = 0; }   // pd: RECIPROCAL of the row's pivot
 #pragma unroll
   for (int k = 0; k < NC - 1; k++) {
     if (k < n) {
@@ -167,8 +167,8 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
         // registers right where it is used (4 shuffles per complex element) — no pivot-row
         // copy in registers, no shared-memory round trip, no barrier
         const cd pk = cd{Grp<G>::bcast(a[0][k].re, own, c.mask), Grp<G>::bcast(a[0][k].im, own, c.mask)};
-        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
         const cd inv = crecip(pk);
+        if (mine) { usedm |= 1u; pd[0] = inv; ps[0] = k; }
         cd l = cmul(a[0][k], inv);
         if (mine) l = cd{0.0, 0.0};
 #pragma unroll
@@ -192,8 +192,8 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
         }
         Grp<G>::sync(c.mask);
         const cd pk = buf[k];
-        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
         const cd inv = crecip(pk);
+        if (mine) { usedm |= 1u; pd[0] = inv; ps[0] = k; }
         cd l = cmul(a[0][k], inv);
         if (mine) l = cd{0.0, 0.0};
 #pragma unroll
@@ -227,12 +227,12 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
             pv[j] = t;
           }
         }
+        const cd inv = crecip(pv[k]);
         if (mine) {
           usedm |= 1u << slot;
 #pragma unroll
-          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = inv; ps[s] = k; }
         }
-        const cd inv = crecip(pv[k]);
 #pragma unroll
         for (int s = 0; s < R; s++) {
           cd l = cmul(a[s][k], inv);
@@ -249,7 +249,7 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
 #pragma unroll
   for (int s = 0; s < R; s++) {
     const int r = c.sub + G * s;
-    if (r < n) dx[ps[s]] = cdivv(a[s][NC - 1], pd[s]);
+    if (r < n) dx[ps[s]] = cmul(a[s][NC - 1], pd[s]);   // (stored pivot reciprocal: no division)
   }
   Grp<G>::sync(c.mask);
   return 1;

@@ -346,7 +346,7 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
   double pd[R > 0 ? R : 1];
   int ps[R > 0 ? R : 1];
 #pragma unroll
-  for (int s = 0; s < R; s++) { pd[s] = 1.0; ps[s] = 0; }
+  for (int s = 0; s < R; s++) { pd[s] = 1.0; ps[s] = 0; }   // pd: RECIPROCAL of the row's pivot
 #pragma unroll
   for (int k = 0; k < NC - 1; k++) {
     if (k < n) {
@@ -369,8 +369,9 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
         // registers right where it is used — no pivot-row copy in registers, no
         // shared-memory round trip, no barrier
         const double pk = Grp<G>::bcast(a[0][k], own, c.mask);
-        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
-        const double l = mine ? 0.0 : a[0][k] * (1.0 / pk);
+        const double ipk = 1.0 / pk;
+        if (mine) { usedm |= 1u; pd[0] = ipk; ps[0] = k; }
+        const double l = mine ? 0.0 : a[0][k] * ipk;
 #pragma unroll
         for (int j = k + 1; j < NC; j++) a[0][j] -= l * Grp<G>::bcast(a[0][j], own, c.mask);
 #else
@@ -386,9 +387,9 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
           for (int j = k; j < NC; j++) buf[j] = a[0][j];
         }
         Grp<G>::sync(c.mask);
-        const double pk = buf[k];
-        if (mine) { usedm |= 1u; pd[0] = pk; ps[0] = k; }
-        const double l = mine ? 0.0 : a[0][k] * (1.0 / pk);
+        const double ipk = 1.0 / buf[k];
+        if (mine) { usedm |= 1u; pd[0] = ipk; ps[0] = k; }
+        const double l = mine ? 0.0 : a[0][k] * ipk;
 #pragma unroll
         for (int j = k + 1; j < NC; j++) a[0][j] -= l * buf[j];
 #endif
@@ -416,12 +417,12 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
             pv[j] = t;
           }
         }
+        const double inv = 1.0 / pv[k];
         if (mine) {
           usedm |= 1u << slot;
 #pragma unroll
-          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = pv[k]; ps[s] = k; }
+          for (int s = 0; s < R; s++) if (slot == s) { pd[s] = inv; ps[s] = k; }
         }
-        const double inv = 1.0 / pv[k];
 #pragma unroll
         for (int s = 0; s < R; s++) {
           const double l = (mine && slot == s) ? 0.0 : a[s][k] * inv;
@@ -434,7 +435,7 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
 #pragma unroll
   for (int s = 0; s < R; s++) {
     const int r = c.sub + G * s;
-    if (r < n) dx[ps[s]] = a[s][NC - 1] / pd[s];
+    if (r < n) dx[ps[s]] = a[s][NC - 1] * pd[s];   // (stored pivot reciprocal: no division)
   }
   Grp<G>::sync(c.mask);
   return 1;
