@@ -66,7 +66,7 @@ EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info',
            'ahk_h2d_columns', 'ahk_set_jit', 'ahk_jit_launch_count',
            'ahk_jit_build_count', 'ahk_jit_compile', 'ahk_op_host',
-           'ahk_set_jit_shape')
+           'ahk_set_jit_shape', 'ahk_pack_rows')
 
 
 def _dp(a):
@@ -170,6 +170,8 @@ def load_library(path=None):
     lib.ahk_op_host.restype = C.c_int
     lib.ahk_set_jit.argtypes = [vp, C.c_int, i64]
     lib.ahk_set_jit.restype = C.c_int
+    lib.ahk_pack_rows.argtypes = [vp, vp, vp, vp, i64, i64, C.c_int, vp, vp, vp]
+    lib.ahk_pack_rows.restype = C.c_int
     lib.ahk_set_jit_shape.argtypes = [vp, C.c_int, C.c_int]
     lib.ahk_set_jit_shape.restype = C.c_int
     lib.ahk_jit_launch_count.argtypes = []

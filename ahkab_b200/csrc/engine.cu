@@ -57,6 +57,24 @@ __global__ void __launch_bounds__(256) k_probe_fp64(int iters, double seed, doub
   if (s == 12345.678) out[0] = s;   // keeps the chains live, (almost) never writes
 }
 
+// Ragged transient results -> contiguous: block b copies the rows[b] accepted rows of instance
+// b (out of max_rows allocated) behind those of the instances before it.  Both copies are
+// contiguous runs of doubles (coalesced); HBM bound.
+__global__ void __launch_bounds__(256) k_pack_rows(const double* __restrict__ t_out, const double* __restrict__ x_out,
+                                                   const int* __restrict__ rows, const long long* __restrict__ offsets,
+                                                   long long B, long long max_rows, int n,
+                                                   double* __restrict__ t_packed, double* __restrict__ x_packed) {
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const long long r = rows[b], off = offsets[b];
+    const double* ts = t_out + b * max_rows;
+    const double* xs = x_out + b * max_rows * n;
+    double* td = t_packed + off;
+    double* xd = x_packed + off * n;
+    for (long long i = threadIdx.x; i < r; i += blockDim.x) td[i] = ts[i];
+    for (long long i = threadIdx.x; i < r * n; i += blockDim.x) xd[i] = xs[i];
+  }
+}
+
 __global__ void k_fill_i32(int* p, long long n, int v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -676,6 +694,22 @@ int ahk_h2d_columns(double* dst, const double* src_host, int n_rows, int64_t row
   CK(cudaMemcpy2DAsync(dst, (size_t)(hi - lo) * sizeof(double), src_host + lo, (size_t)row_len * sizeof(double),
                        (size_t)(hi - lo) * sizeof(double), (size_t)n_rows, cudaMemcpyHostToDevice,
                        (cudaStream_t)stream));
+  return 0;
+}
+
+int ahk_pack_rows(const double* t_out, const double* x_out, const int32_t* rows, const int64_t* offsets,
+                  int64_t B, int64_t max_rows, int n, double* t_packed, double* x_packed, void* stream) {
+  if (!t_out || !x_out || !rows || !offsets || !t_packed || !x_packed || B <= 0 || max_rows <= 0 || n <= 0)
+    return fail("ahk_pack_rows: bad argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = (int)std::min<int64_t>(B, (int64_t)sms * 8);   // 8 resident blocks of 256 threads per SM
+  k_pack_rows<<<blocks, 256, 0, (cudaStream_t)stream>>>(t_out, x_out, rows, (const long long*)offsets, B, max_rows, n,
+                                                        t_packed, x_packed);
+  CK(cudaGetLastError());
+  g_launches++;
   return 0;
 }
 

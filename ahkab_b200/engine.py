@@ -277,6 +277,30 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(t=t, x=x, rows=rows, counters=counters, status=status, _packed=pk['_packed'])
 
+    def pack_tran(self, raw):
+        """Ragged transient results -> contiguous (ahk_pack_rows): returns a dict with
+        t [sum rows], x [sum rows][n], offsets [B + 1] (int64, instance b owns rows
+        offsets[b]:offsets[b+1]) plus rows / counters / status.  Reads the row total back
+        (one small synchronising copy); the device->host read of the result then moves only
+        the rows that exist instead of B x max_rows."""
+        rows = raw['rows']
+        B, max_rows = raw['t'].shape
+        offs = torch.zeros(B + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(rows, 0, out=offs[1:])
+        total = int(offs[-1].item())
+        t = self._new((max(total, 1),))
+        x = self._new((max(total, 1), self.n))
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_pack_rows(_ptr(raw['t']), _ptr(raw['x']), _ptr(rows), _ptr(offs), B,
+                                        max_rows, self.n, _ptr(t), _ptr(x), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        out = dict(t=t[:total], x=x[:total], offsets=offs, rows=rows, counters=raw['counters'],
+                   status=raw['status'])
+        if 'op_iters' in raw:
+            out['op_iters'] = raw['op_iters']
+        return out
+
     @staticmethod
     def default_max_rows(tstart, tstep, tstop, use_step_control):
         nominal = int(np.ceil((tstop - tstart) / tstep)) + 2 if tstep > 0 else 16

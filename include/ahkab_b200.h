@@ -225,6 +225,15 @@ int64_t ahk_launch_count(void);
 int ahk_h2d_columns(double* dst, const double* src_host, int n_rows,
                     int64_t row_len, int64_t lo, int64_t hi, void* stream);
 
+/* Plumbing for end-to-end transients: ahk_tran writes [B][max_rows] padded rows, of which
+ * instance b used rows[b].  This packs the used rows of all instances contiguously,
+ * instance after instance (offsets[b] = rows[0] + ... + rows[b-1], device, int64), so that
+ * the device->host read moves sum(rows) rows instead of B * max_rows.
+ *   t_packed device [sum rows], x_packed device [sum rows][n] */
+int ahk_pack_rows(const double* t_out, const double* x_out, const int32_t* rows,
+                  const int64_t* offsets, int64_t B, int64_t max_rows, int n,
+                  double* t_packed, double* x_packed, void* stream);
+
 /* Diagnostics (no reference counterpart): launches an FP64-FMA-only kernel,
  * blocks x threads (<= 256) threads each running 8 independent chains of
  * `iters` DFMAs = blocks*threads*iters*16 flop.  bench.py times it with CUDA

@@ -59,6 +59,23 @@ def test_c2_diode_op(gold):
         assert (_np(r['iters']) != g['iters']).mean() < 0.004, v
 
 
+def test_pack_rows_keeps_every_accepted_row():
+    """ahk_pack_rows: the ragged [B][max_rows] transient buffers, packed, hold exactly the
+    accepted rows of every instance in instance order."""
+    w = W.c4_ring3(96)
+    e = _engine(w)
+    tr = dict(W.C4_TRAN); tr['tstop'] = 5e-9
+    raw = e.tran(None, max_rows=1024, **tr)
+    pk = e.pack_tran(raw)
+    rows, offs = _np(raw['rows']), _np(pk['offsets'])
+    t, x, tp, xp = _np(raw['t']), _np(raw['x']), _np(pk['t']), _np(pk['x'])
+    assert offs[0] == 0 and (np.diff(offs) == rows).all() and len(tp) == rows.sum() == len(xp)
+    assert rows.min() > 10 and rows.max() < 1024 and len(set(rows.tolist())) > 1     # ragged
+    for b in range(len(rows)):
+        assert np.array_equal(tp[offs[b]:offs[b + 1]], t[b, :rows[b]])
+        assert np.array_equal(xp[offs[b]:offs[b + 1]], x[b, :rows[b]])
+
+
 @pytest.mark.parametrize('B,chunks', [(4096, 4), (1000, 3), (64, 1), (5, 8), (4096, 0), (77, 0)])
 def test_op_host_matches_op(B, chunks):
     """ahk_op_host (host buffers, chunks pipelined inside the library) == ahk_op."""
