@@ -273,14 +273,6 @@ class Timer(object):
         r = None
         for _ in range(warmup):
             r = fn()
-        # keep the GPU busy for >= 0.3 s before timing: a 20 us kernel after W = 3 warm-up steps
-        # is otherwise measured while the SM clock is still ramping up from idle (10-step runs
-        # of C2 read 0.026-0.043 ms against 0.020 ms for 50-step runs)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.3:
-            r = fn()
-            torch.cuda.synchronize()
         self.barrier()
         if sampler is not None:
             sampler.active.set()
@@ -555,7 +547,10 @@ def main():
             os.environ['NCCL_DEBUG'] = 'NONE'
         else:
             os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=device)
+        # (every rank must issue the same collectives in the same order: all loop counts below are
+        # fixed numbers, never time based; a short timeout turns a mismatch into a quick failure)
+        import datetime
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
     warmup = max(3, args.warmup)
     timer = Timer(dist_on, device)
     sampler = ClockSampler(local)
