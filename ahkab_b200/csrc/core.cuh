@@ -5,8 +5,9 @@
 // compile time the number of matrix columns NC (>= n+1, the last one is the
 // right-hand side), the rows per lane R and the lanes per instance G (R*G >= n):
 // row r lives in lane r % G, slot r / G, as NC doubles IN REGISTERS for the whole
-// linear solve (Gauss-Jordan with implicit partial pivoting, fully unrolled; the
-// pivot row crosses lanes through a shared-memory broadcast).  The per-instance
+// linear solve (G > 1: Gauss-Jordan with implicit partial pivoting, fully unrolled, the
+// pivot row crossing lanes through a double-buffered shared-memory broadcast; G == 1: LU
+// with explicit register swaps).  The per-instance
 // parameters are staged once from HBM into shared memory, together with the
 // sparse values of the linear stamps, the iterate, the history ring and the
 // device outputs; HBM is touched again only to write result rows.
@@ -14,6 +15,11 @@
 // memory, LU with back-substitution.
 // Control scalars (time, step, counters) are kept redundantly in registers and
 // are group-uniform by construction.
+//
+// This source is compiled twice: ahead of time (k_dc.cu / k_tran.cu / k_ac.cu), where it
+// INTERPRETS the stamp program (`Prog`), and at run time by NVRTC with `Prog`, `Opts` and
+// `Layout` replaced by compile-time constants (AHK_JIT, jit_gen.hpp), where the loops
+// marked AHK_UNROLL / AHK_LANES unroll and the program folds into straight-line code.
 //
 // What it replaces in the reference (all per instance, pure Python there):
 //   dc_analysis.mdn_solver / _update_J_and_Tx / get_td   dc_analysis.py:690-946

@@ -257,3 +257,15 @@ def test_gpu_specialised_ac(vid):
     xa, xb = _np(a['x']), _np(b['x'])
     assert (_np(b['status']) & 1).all() and (_np(a['status']) == _np(b['status'])).all()
     assert np.abs(xa - xb).max() <= 1e-10 * np.abs(xa).max()
+
+
+def test_generated_constants_do_not_depend_on_the_batch_values():
+    """The text that keys the compiled-kernel cache must be the same for two batches that
+    vary the same parameters with different values (else every run() call recompiles)."""
+    def spec(seed):
+        w = W.c2_diode_op(B=32, seed=seed)
+        return _emu(w).jit_source(0, NC=4, R=3, G=1)
+    a, b = spec(1), spec(2)
+    assert a == b
+    w = W.c2_diode_op(B=32)
+    assert _emu(w).jit_source(0, NC=4, R=3, G=1) != _emu(w).jit_source(0, NC=4, R=1, G=4)
