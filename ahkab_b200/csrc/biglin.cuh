@@ -256,7 +256,22 @@ struct BigLin {
   double* s2Lv = nullptr; double* s2Uv = nullptr; unsigned short* s2Li = nullptr; unsigned short* s2Ui = nullptr;
   int* d_ovf = nullptr; long long ovf_cap = 0;
   int nwarps2 = 0, cap2 = 0;
+  // static-schedule kernels (biglin3.cuh): schedule blob + structure-of-arrays buffers
+  void* s3_sched = nullptr;      // device copy of the schedule arrays
+  const void* s3_ptr[9] = {};    // step, prow, cand_slot, cand_row, l_slot, l_row, u_slot, u_col, upd
+  int s3_n = 0, s3_npos = 0, s3_nslot = 0;
+  long long s3_slots_epoch = -1, s3_opts_epoch = -1;
+  bool s3_ok = false;
+  double* s3_V = nullptr; double* s3_Mv = nullptr; double* s3_bs = nullptr; double* s3_xs = nullptr;
+  int* s3_flag = nullptr;
+  size_t s3_V_cap = 0, s3_Mv_cap = 0, s3_scr_cap = 0, s3_flag_cap = 0;
+  void release3() {
+    cudaFree(s3_sched); cudaFree(s3_V); cudaFree(s3_Mv); cudaFree(s3_bs); cudaFree(s3_xs); cudaFree(s3_flag);
+    s3_sched = nullptr; s3_V = s3_Mv = s3_bs = s3_xs = nullptr; s3_flag = nullptr;
+    s3_V_cap = s3_Mv_cap = s3_scr_cap = s3_flag_cap = 0; s3_ok = false; s3_slots_epoch = s3_opts_epoch = -1;
+  }
   void release() {
+    release3();
     cudaFree(wsA); cudaFree(wsLv); cudaFree(wsUv); cudaFree(wsLi); cudaFree(wsUi); cudaFree(d_sweep);
     cudaFree(s2Lv); cudaFree(s2Uv); cudaFree(s2Li); cudaFree(s2Ui); cudaFree(d_ovf);
     wsA = wsLv = wsUv = nullptr; wsLi = wsUi = nullptr; d_sweep = nullptr; nwarps = 0;

@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "biglin2.cuh"
+#include "biglin3.cuh"
 #include "jit.hpp"
 #include "jit_gen.hpp"
 #include "kernels.cuh"
@@ -34,6 +34,15 @@ std::atomic<long long> g_jit_launches{0};   // launches of circuit-specialised k
 std::atomic<long long> g_jit_builds{0};     // NVRTC compilations
 
 int fail(const std::string& m) { g_err = m; return -1; }
+
+// appends v (16-byte aligned) to a blob that is uploaded in one piece; returns its offset
+template <typename T>
+size_t put(std::vector<unsigned char>& buf, const std::vector<T>& v) {
+  size_t off = (buf.size() + 15) & ~size_t(15);
+  buf.resize(off + v.size() * sizeof(T) + 16);
+  if (!v.empty()) std::memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
+  return off;
+}
 
 #define CK(call)                                                                     \
   do {                                                                               \
@@ -150,9 +159,80 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
   }
   CKB(cudaMemcpyAsync(d_sweep, sweep_host, npts * sizeof(double), cudaMemcpyHostToDevice, s));
 
+  // ---- 0. static elimination schedule (biglin3.cuh): one thread per instance ----------------
+  // The schedule follows the pivot sequence of the nominal instance; instances whose pivots
+  // differ are appended to the overflow list and go through the dynamic kernel below.
+  bool staged = false;
+  // (AHK_BIGLIN3_OFF / AHK_BIGLIN_DENSE / AHK_BIGLIN_SC: tests force the other paths)
+  if (!getenv("AHK_BIGLIN3_OFF") && !getenv("AHK_BIGLIN_DENSE") && !getenv("AHK_BIGLIN_SC")) {
+    if (s3_slots_epoch != e->slots_epoch || s3_opts_epoch != e->opts_epoch) {
+      Big3Sched S;
+      s3_ok = big3_build(e->H, e->o, S);
+      s3_slots_epoch = e->slots_epoch; s3_opts_epoch = e->opts_epoch;
+      if (s3_ok) {
+        std::vector<unsigned char> buf;
+        size_t off[9];
+        off[0] = put(buf, S.step); off[1] = put(buf, S.prow); off[2] = put(buf, S.cand_slot);
+        off[3] = put(buf, S.cand_row); off[4] = put(buf, S.l_slot); off[5] = put(buf, S.l_row);
+        off[6] = put(buf, S.u_slot); off[7] = put(buf, S.u_col); off[8] = put(buf, S.upd);
+        CKB(cudaStreamSynchronize(s));
+        cudaFree(s3_sched); s3_sched = nullptr;
+        CKB(cudaMalloc(&s3_sched, buf.size() + 64));
+        CKB(cudaMemcpy(s3_sched, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+        for (int i = 0; i < 9; i++) s3_ptr[i] = (const unsigned char*)s3_sched + off[i];
+        s3_n = S.n; s3_npos = S.npos; s3_nslot = S.nslot;
+      }
+    }
+    if (s3_ok) {
+      const long long B = batch->B;
+      // scratch of the solve kernel: [n][B * ptc] doubles twice, at most ~1 GB per buffer
+      int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 27) / ((long long)n * B)));
+      const size_t needV = (size_t)2 * s3_nslot * B, needM = (size_t)s3_npos * B, needS = (size_t)n * B * ptc;
+      if (needV > s3_V_cap || needM > s3_Mv_cap || needS > s3_scr_cap || (size_t)B > s3_flag_cap ||
+          batch->B + 1 > ovf_cap) {
+        CKB(cudaStreamSynchronize(s));
+        if (needV > s3_V_cap) { cudaFree(s3_V); s3_V = nullptr; CKB(cudaMalloc(&s3_V, needV * 8)); s3_V_cap = needV; }
+        if (needM > s3_Mv_cap) { cudaFree(s3_Mv); s3_Mv = nullptr; CKB(cudaMalloc(&s3_Mv, needM * 8)); s3_Mv_cap = needM; }
+        if (needS > s3_scr_cap) {
+          cudaFree(s3_bs); cudaFree(s3_xs); s3_bs = s3_xs = nullptr;
+          CKB(cudaMalloc(&s3_bs, needS * 8)); CKB(cudaMalloc(&s3_xs, needS * 8)); s3_scr_cap = needS;
+        }
+        if ((size_t)B > s3_flag_cap) { cudaFree(s3_flag); s3_flag = nullptr; CKB(cudaMalloc(&s3_flag, (size_t)B * 4)); s3_flag_cap = B; }
+        if (batch->B + 1 > ovf_cap) {
+          cudaFree(d_ovf); d_ovf = nullptr; ovf_cap = batch->B + 1;
+          CKB(cudaMalloc(&d_ovf, (size_t)ovf_cap * sizeof(int)));
+        }
+      }
+      CKB(cudaMemsetAsync(d_ovf, 0, sizeof(int), s));
+      Big3K k3;
+      k3.p = e->dprog; k3.o = e->o; k3.vary = batch->vary; k3.B = B;
+      k3.src_elem = src_elem; k3.sweep = d_sweep; k3.npts = npts; k3.pt0 = 0; k3.ptc = ptc;
+      k3.x_out = x_out; k3.iters = iters; k3.status = status; k3.resid = resid;
+      k3.n = s3_n; k3.npos = s3_npos; k3.nslot = s3_nslot;
+      k3.step = (const Big3Step*)s3_ptr[0]; k3.prow = (const int*)s3_ptr[1];
+      k3.cand_slot = (const int*)s3_ptr[2]; k3.cand_row = (const int*)s3_ptr[3];
+      k3.l_slot = (const int*)s3_ptr[4]; k3.l_row = (const int*)s3_ptr[5];
+      k3.u_slot = (const int*)s3_ptr[6]; k3.u_col = (const int*)s3_ptr[7]; k3.upd = (const int*)s3_ptr[8];
+      k3.V = s3_V; k3.Mv = s3_Mv; k3.flag = s3_flag; k3.bs = s3_bs; k3.xs = s3_xs; k3.ovf = d_ovf;
+      k_big3_factor<<<(int)((B + 127) / 128), 128, 0, s>>>(k3);
+      CKB(cudaGetLastError());
+      launches++;
+      for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
+        k3.pt0 = pt0; k3.ptc = std::min(ptc, npts - pt0);
+        const long long T = B * k3.ptc;
+        k_big3_solve<<<(int)((T + 127) / 128), 128, 0, s>>>(k3);
+        CKB(cudaGetLastError());
+        launches++;
+      }
+      if (getenv("AHK_DEBUG"))
+        fprintf(stderr, "[ahk] biglin3 n=%d slots %d, %lld instances, %d point(s) per solve launch\n", n, s3_nslot, B, ptc);
+      staged = true;
+    }
+  }
+
   // ---- 1. sparse shared-memory kernel (n <= 1024) ----------------------------------------
   const int W = (n + 31) / 32;
-  bool sparse = W <= 32 && !getenv("AHK_BIGLIN_DENSE");
+  bool sparse = !staged && W <= 32 && !getenv("AHK_BIGLIN_DENSE");
   int SC = 0, PC = 0;
   Big2Smem S2;
   if (sparse) {
@@ -210,7 +290,7 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
   BigSmem S = big_smem(n, h.npos);
   if ((size_t)S.total > e->smem_max) { err = "circuit too large for the large-n path"; return -1; }
   int per_sm = (int)std::min<size_t>(16, e->smem_max / (size_t)S.total);
-  int want = (int)std::min<long long>(batch->B, (long long)e->sm_count * (sparse ? 1 : per_sm));
+  int want = (int)std::min<long long>(batch->B, (long long)e->sm_count * ((sparse || staged) ? 1 : per_sm));
   const int capn = n * (n - 1) / 2 + n;
   if (want > nwarps || capn != cap) {
     CKB(cudaStreamSynchronize(s));
@@ -227,7 +307,7 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
   k.src_elem = src_elem; k.sweep = d_sweep; k.npts = npts; k.x0 = nullptr;
   k.x_out = x_out; k.iters = iters; k.status = status; k.resid = resid;
   k.wsA = wsA; k.wsLv = wsLv; k.wsUv = wsUv; k.wsLi = wsLi; k.wsUi = wsUi;
-  k.cap = cap; k.RS = RS; k.list = sparse ? d_ovf : nullptr;
+  k.cap = cap; k.RS = RS; k.list = (sparse || staged) ? d_ovf : nullptr;
   if (S.total > 48 * 1024)
     CKB(cudaFuncSetAttribute(k_biglin, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total));
   k_biglin<<<want, 32, S.total, s>>>(k, S);
@@ -239,13 +319,6 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
 
 namespace {
 
-template <typename T>
-size_t put(std::vector<unsigned char>& buf, const std::vector<T>& v) {
-  size_t off = (buf.size() + 15) & ~size_t(15);
-  buf.resize(off + v.size() * sizeof(T) + 16);
-  if (!v.empty()) std::memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
-  return off;
-}
 
 int upload_program(ahk_engine* e) {
   HostProg& H = e->H;

@@ -119,3 +119,17 @@ class Emu(_oracle.Oracle):
         buf = C.create_string_buffer(n + 1)
         lib().emu_jit_source(*args, buf, C.c_int64(n + 1))
         return buf.value.decode()
+
+    def big3_sweep(self, src_elem, sweep):
+        """Large linear circuits: the static-schedule path (biglin3.cuh) on the host.
+        Returns dict(x, resid, iters, status, flags, dynamic) — `dynamic` = instances whose
+        pivot sequence differs from the nominal one (-1: no schedule could be built)."""
+        B, n = self.B, self.n
+        sweep = np.ascontiguousarray(sweep, np.float64)
+        P = len(sweep)
+        x = np.zeros((B, P, n)); res = np.zeros((B, P, n))
+        it = np.zeros((B, P), np.int32); st = np.zeros((B, P), np.int32)
+        fl = np.zeros(B, np.int32)
+        dyn = lib().emu_big3_sweep(*self._common(), C.c_int(src_elem), _dp(sweep), C.c_int(P),
+                                   _dp(x), _dp(res), _ip(it), _ip(st), _ip(fl))
+        return dict(x=x, resid=res, iters=it, status=st, flags=fl, dynamic=dyn)

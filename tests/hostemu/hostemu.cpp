@@ -13,6 +13,7 @@ using std::isnan; using std::isinf; using std::isfinite;
 #include "../../ahkab_b200/csrc/program_build.hpp"
 #include "../../ahkab_b200/csrc/ac.cuh"
 #include "../../ahkab_b200/csrc/jit_gen.hpp"
+#include "../../ahkab_b200/csrc/biglin3.cuh"
 
 using namespace ahk;
 
@@ -100,6 +101,37 @@ int emu_ac(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, co
     if (nc) run_ac<Var<4, 3, 1> >(cx, AL, a); else run_ac<Var<0, 0, 1> >(cx, AL, a);
   }
   return 0;
+}
+
+// Large linear circuits: the static-schedule path (biglin3.cuh) run on the host, one loop
+// iteration per device thread.  Returns the number of instances the schedule could not serve
+// (pivot sequence differs from the nominal one: the device hands those to k_biglin), -1 if no
+// schedule could be built; flags[B] receives BIG3_OK / BIG3_SINGULAR / BIG3_DYNAMIC.
+int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, const int32_t* slots,
+                   const double* vary, int src_elem, const double* sweep, int npts, double* x_out,
+                   double* resid, int32_t* iters, int32_t* status, int32_t* flags) {
+  HostProg H;
+  build_program(c, H);
+  set_vary_slots(H, n_vary, slots);
+  Opts q; copy_opts(o, q);
+  Big3Sched S;
+  if (!big3_build(H, q, S)) return -1;
+  const int n = S.n;
+  std::vector<double> V((size_t)2 * S.nslot * B), Mv((size_t)S.npos * B), bs((size_t)n * B * npts), xs((size_t)n * B * npts);
+  std::vector<int> flag(B), ovf(B + 1, 0);
+  Big3K k;
+  k.p = H.view(); k.o = q; k.vary = vary; k.B = B; k.src_elem = src_elem; k.sweep = sweep; k.npts = npts;
+  k.pt0 = 0; k.ptc = npts;
+  k.x_out = x_out; k.iters = iters; k.status = status; k.resid = resid;
+  k.n = n; k.npos = S.npos; k.nslot = S.nslot;
+  k.step = S.step.data(); k.prow = S.prow.data(); k.cand_slot = S.cand_slot.data(); k.cand_row = S.cand_row.data();
+  k.l_slot = S.l_slot.data(); k.l_row = S.l_row.data(); k.u_slot = S.u_slot.data(); k.u_col = S.u_col.data();
+  k.upd = S.upd.data();
+  k.V = V.data(); k.Mv = Mv.data(); k.flag = flag.data(); k.bs = bs.data(); k.xs = xs.data(); k.ovf = ovf.data();
+  int dyn = 0;
+  for (int64_t b = 0; b < B; b++) { flag[b] = big3_factor_one(k, b); if (flag[b] == BIG3_DYNAMIC) dyn++; flags[b] = flag[b]; }
+  for (int64_t t = 0; t < B * npts; t++) big3_solve_one(k, t);
+  return dyn;
 }
 
 // Text of the generated jit_spec.h (jit_gen.hpp) for this circuit / batch / analysis / variant:

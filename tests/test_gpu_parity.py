@@ -256,7 +256,7 @@ def test_c5_big_linear_paths_agree(monkeypatch):
     o = _oracle(w).dc_sweep(0, sw)
     scale = np.abs(o['x']).max()
     outs = {}
-    for tag, env in (('sparse', {}), ('dense', {'AHK_BIGLIN_DENSE': '1'}),
+    for tag, env in (('static', {}), ('sparse', {'AHK_BIGLIN3_OFF': '1'}), ('dense', {'AHK_BIGLIN_DENSE': '1'}),
                      ('overflow', {'AHK_BIGLIN_SC': '3'})):
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
@@ -271,6 +271,24 @@ def test_c5_big_linear_paths_agree(monkeypatch):
         for k_ in env:
             monkeypatch.delenv(k_)
     assert np.abs(outs['sparse'] - outs['dense']).max() / scale < 1e-14
+    # the static-schedule kernels do the same operations in the same order as the sparse one
+    assert np.abs(outs['static'] - outs['sparse']).max() / scale < 1e-15
+
+
+def test_static_schedule_hands_over_instances_with_other_pivots():
+    """biglin3: an instance whose pivot sequence differs from the nominal one (a resistor
+    of 0.5 ohm where the others have 1.3 kohm) is solved by the dynamic kernel; the others by the
+    schedule; all agree with the oracle."""
+    w = W.c5_r2r(64)
+    w.params['R1h'] = w.params['R1h'].copy()
+    w.params['R1h'][5] = 0.5      # g = 2 S > the source row's 1: other pivot in column 0
+    w.params['R1h'][17] = 0.25
+    sw = common.c5_sweep()
+    o = _oracle(w).dc_sweep(0, sw)
+    r = _engine(w).dc_sweep('V1', sw)
+    scale = np.abs(o['x']).max()
+    assert (_np(r['status']) == o['status']).all()
+    assert np.abs(_np(r['x']) - o['x']).max() / scale < 1e-12
 
 
 @pytest.mark.parametrize('name', ['c2', 'c3', 'c5'])

@@ -111,3 +111,23 @@ def test_variant_that_does_not_fit_is_refused():
     circ = w.circuit(Circuit)
     with pytest.raises(ValueError):
         emu.Emu(circ, w.batch(), opts=w.opts).op()
+
+
+def test_static_schedule_path_for_large_linear_circuits():
+    """biglin3.cuh on the host: the schedule built from the nominal instance reproduces the
+    oracle's sweep of the 257-unknown ladder, and an instance with other pivots is flagged
+    for the dynamic kernel instead of being solved wrongly."""
+    import oracle
+    w = W.c5_r2r(16)
+    w.params['R1h'] = w.params['R1h'].copy()
+    w.params['R1h'][5] = 0.5                # g = 2 S > the source row's 1: this instance pivots differently
+    circ = w.circuit(Circuit)
+    sw = common.c5_sweep()
+    o = oracle.Oracle(circ, w.batch(), opts=w.opts).dc_sweep(0, sw)
+    r = emu.Emu(circ, w.batch(), w.opts).big3_sweep(0, sw)
+    assert r['dynamic'] >= 0                # a schedule was built
+    served = r['flags'] == 0
+    assert served.sum() == 15 and r['flags'][5] == 2 and r['dynamic'] == 1
+    scale = np.abs(o['x']).max()
+    assert np.abs(r['x'][served] - o['x'][served]).max() / scale < 1e-14
+    assert (r['status'][served] == o['status'][served]).all() and (r['iters'][served] == 2).all()
