@@ -56,7 +56,7 @@ C4_MAX_ROWS = 3072
 # Only throughput-bound kernels gain: a latency-bound kernel that fits the machine in one
 # or two waves takes as long for a quarter of the batch as for all of it (measured: C3
 # 28 -> 44 ms, C4 262 -> 679 ms with 4 / 8 chunks), so those run as one chunk.
-E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=4)
+E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=1)   # c5: thread-per-instance kernels are latency bound: a quarter of the batch takes as long as all of it
 # AHK_E2E_OP_HOST=<chunks>: route the c2 end-to-end step through ahk_op_host (host buffers,
 # chunk pipeline inside the library; 0 = zero-copy).  Measured on B200 (50 steps): one packed
 # D2H through the Engine 0.129 ms; op_host 1 / 2 / 4 / 8 chunks 0.143 / 0.136 / 0.215 / 0.244 ms
