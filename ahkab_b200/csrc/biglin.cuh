@@ -258,8 +258,8 @@ struct BigLin {
   int nwarps2 = 0, cap2 = 0;
   // static-schedule kernels (biglin3.cuh): schedule blob + structure-of-arrays buffers
   void* s3_sched = nullptr;      // device copy of the schedule arrays
-  const void* s3_ptr[9] = {};    // step, prow, cand_slot, cand_row, l_slot, l_row, u_slot, u_col, upd
-  int s3_n = 0, s3_npos = 0, s3_nslot = 0;
+  const void* s3_ptr[11] = {};   // step, prow, cand_slot, cand_row, l_slot, l_row, u_slot, u_col, upd, rslot, rindex
+  int s3_n = 0, s3_npos = 0, s3_nslot = 0, s3_nrec = 0;
   long long s3_slots_epoch = -1, s3_opts_epoch = -1;
   bool s3_ok = false;
   double* s3_V = nullptr; double* s3_Mv = nullptr; double* s3_bs = nullptr; double* s3_xs = nullptr;

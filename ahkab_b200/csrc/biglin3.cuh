@@ -46,6 +46,8 @@ struct Big3Sched {          // host copy
   std::vector<int> l_slot, l_row;          // multipliers (stored in place)
   std::vector<int> u_slot, u_col;          // pivot-row entries right of the pivot, ascending column
   std::vector<int> upd;                    // [nl][nu] target slots
+  std::vector<int> rslot;                  // parameter slots that enter a stamp as 1 / value (resistors)
+  std::vector<int> rindex;                 // [nparams] index into rslot, or -1
   bool ok = false;
 };
 
@@ -67,6 +69,12 @@ inline bool big3_build(const HostProg& H, const Opts& o, Big3Sched& S) {
     }
     Mv[q] = v;
   }
+  S.rindex.assign(h.nparams > 0 ? h.nparams : 1, -1);
+  for (int t = 0; t < H.term_ptr[np]; t++) {
+    const int kd = H.term_kind[t], ak = kd < 0 ? -kd : kd, sl = H.term_slot[t];
+    if (ak == 1 && S.rindex[sl] < 0) { S.rindex[sl] = (int)S.rslot.size(); S.rslot.push_back(sl); }
+  }
+  if (S.rslot.empty()) S.rslot.push_back(0);
   S.step.assign(2 * n, Big3Step());
   S.prow.assign(2 * n, 0);
   int nslot_max = np;
@@ -132,12 +140,15 @@ struct Big3K {
   Prog p; Opts o;
   const double* vary; long long B;
   int src_elem; const double* sweep; int npts;
+  int idx32;        // every [slot][instance] / [row][thread] array has < 2^31 elements
   int pt0, ptc;     // this launch solves the points pt0 .. pt0 + ptc - 1 (scratch holds ptc points)
   double* x_out; int* iters; int* status; double* resid;
   int n, npos, nslot;
   const Big3Step* step; const int* prow;
   const int* cand_slot; const int* cand_row; const int* l_slot; const int* l_row;
   const int* u_slot; const int* u_col; const int* upd;
+  const int* rslot; const int* rindex; int nrec;   // reciprocal table (see big3_factor_one)
+  double* G;        // [nrec][B]  1 / value of every resistor-like parameter, computed once
   double* V;        // [2][nslot][B]  factors (in place)
   double* Mv;       // [npos][B]      matrix values (for the residual mat-vec)
   int* flag;        // [B] 0 ok, 1 singular, 2 handed to the dynamic kernel
@@ -149,41 +160,48 @@ struct Big3K {
 enum { BIG3_OK = 0, BIG3_SINGULAR = 1, BIG3_DYNAMIC = 2 };
 
 // ---- per-instance factorisation (one thread = one instance) --------------------------------
+// IT: index type of the [slot][instance] arrays — 32-bit when they are small enough (one
+// IMAD.WIDE per address instead of a 64-bit multiply), 64-bit otherwise
+template <typename IT>
 AHK_DEV int big3_factor_one(const Big3K& k, long long inst) {
   const Prog& p = k.p;
   const long long B = k.B;
   const int n = k.n;
   auto P = [&](int slot) -> double {
     const int v = p.slot_vary[slot];
-    return v < 0 ? p.nominal[slot] : k.vary[(long long)v * B + inst];
+    return v < 0 ? p.nominal[slot] : k.vary[(IT)v * (IT)B + inst];
   };
   double* V0 = k.V + inst;
-  double* V1 = k.V + (long long)k.nslot * B + inst;
+  double* V1 = k.V + (IT)k.nslot * (IT)B + inst;
+  // a resistor enters four stamps as 1 / R: ONE division per parameter instead of one per
+  // stamp term (the same quotient, so the sums below have the same bits)
+  double* G = k.G + inst;
+  for (int i = 0; i < k.nrec; i++) G[(IT)i * (IT)B] = 1. / P(k.rslot[i]);
   for (int q = 0; q < k.npos; q++) {     // deterministic gather, as biglin2
     double v = 0.0;
     for (int t = p.term_ptr[q]; t < p.term_ptr[q + 1]; t++) {
       const int kd = p.term_kind[t];
       const double sg = kd < 0 ? -1.0 : 1.0;
       const int ak = kd < 0 ? -kd : kd;
-      if (ak == 1) v += sg * (1. / P(p.term_slot[t]));
+      if (ak == 1) v += sg * G[(IT)k.rindex[p.term_slot[t]] * (IT)B];
       else if (ak == 2) v += sg * P(p.term_slot[t]);
       else v += sg;
     }
-    k.Mv[(long long)q * B + inst] = v;
-    V0[(long long)q * B] = v + (p.pdiag[q] ? k.o.gmin : 0.0);
-    V1[(long long)q * B] = v;
+    k.Mv[(IT)q * (IT)B + inst] = v;
+    V0[(IT)q * (IT)B] = v + (p.pdiag[q] ? k.o.gmin : 0.0);
+    V1[(IT)q * (IT)B] = v;
   }
-  for (int q = k.npos; q < k.nslot; q++) { V0[(long long)q * B] = 0.0; V1[(long long)q * B] = 0.0; }
+  for (int q = k.npos; q < k.nslot; q++) { V0[(IT)q * (IT)B] = 0.0; V1[(IT)q * (IT)B] = 0.0; }
   for (int m = 0; m < 2; m++) {
     double* V = m ? V1 : V0;
     for (int kk = 0; kk < n; kk++) {
       const Big3Step st = k.step[m * n + kk];
       const int bi = k.prow[m * n + kk];
-      const double piv = V[(long long)st.piv * B], ap = fabs(piv);
+      const double piv = V[(IT)st.piv * (IT)B], ap = fabs(piv);
       // dgesv's choice for THIS instance must be the scheduled row
       bool same = true, allzero = ap == 0.0;
       for (int i = 0; i < st.ncand; i++) {
-        const double ac = fabs(V[(long long)k.cand_slot[st.cand0 + i] * B]);
+        const double ac = fabs(V[(IT)k.cand_slot[st.cand0 + i] * (IT)B]);
         const int r = k.cand_row[st.cand0 + i];
         if (r < bi ? !(ac < ap) : !(ac <= ap)) same = false;
         if (ac != 0.0) allzero = false;
@@ -192,11 +210,11 @@ AHK_DEV int big3_factor_one(const Big3K& k, long long inst) {
       if (!same || !(ap > 0.0)) return BIG3_DYNAMIC;
       const double inv = 1.0 / piv;
       for (int i = 0; i < st.nl; i++) {
-        const long long ls = (long long)k.l_slot[st.l0 + i] * B;
+        const long long ls = (IT)k.l_slot[st.l0 + i] * (IT)B;
         const double l = V[ls] * inv;
         V[ls] = l;
         const int* up = k.upd + st.upd0 + i * st.nu;
-        for (int j = 0; j < st.nu; j++) V[(long long)up[j] * B] -= l * V[(long long)k.u_slot[st.u0 + j] * B];
+        for (int j = 0; j < st.nu; j++) V[(IT)up[j] * (IT)B] -= l * V[(IT)k.u_slot[st.u0 + j] * (IT)B];
       }
     }
   }
@@ -205,6 +223,7 @@ AHK_DEV int big3_factor_one(const Big3K& k, long long inst) {
 
 // ---- per-(instance, point) solve (one thread = one right-hand side) -------------------------
 // tid = pt * B + inst: consecutive threads = consecutive instances (coalesced V / Mv / vary)
+template <typename IT>
 AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
   const Prog& p = k.p;
   const long long B = k.B, T = B * k.ptc;
@@ -220,31 +239,31 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
   }
   auto P = [&](int slot) -> double {
     const int v = p.slot_vary[slot];
-    return v < 0 ? p.nominal[slot] : k.vary[(long long)v * B + inst];
+    return v < 0 ? p.nominal[slot] : k.vary[(IT)v * (IT)B + inst];
   };
   double* b = k.bs + tid;      // b[r] = b[r * T]
   double* x = k.xs + tid;
-  for (int r = 0; r < n; r++) x[(long long)r * T] = 0.0;
+  for (int r = 0; r < n; r++) x[(IT)r * (IT)T] = 0.0;
   int bad = 0;
   for (int m = 0; m < 2; m++) {
-    const double* V = k.V + (long long)m * k.nslot * B + inst;
+    const double* V = k.V + (IT)m * k.nslot * (IT)B + inst;
     const int* pr = k.prow + m * n;
     // b = -(M x + N): N first (dc_analysis.py:1004-1040), then the mat-vec
-    for (int r = 0; r < n; r++) b[(long long)r * T] = 0.0;
+    for (int r = 0; r < n; r++) b[(IT)r * (IT)T] = 0.0;
     for (int s = 0; s < p.nsrc; s++) {
       const SrcOp& so = p.src[s];
       if (so.tf) continue;
       const double v = (so.elem == k.src_elem) ? k.sweep[pt] : P(so.pbase);
-      if (so.is_v) b[(long long)so.row0 * T] = v;      // N[row] = -V  =>  -N = V
-      else { if (so.row0 >= 0) b[(long long)so.row0 * T] -= v; if (so.row1 >= 0) b[(long long)so.row1 * T] += v; }
+      if (so.is_v) b[(IT)so.row0 * (IT)T] = v;      // N[row] = -V  =>  -N = V
+      else { if (so.row0 >= 0) b[(IT)so.row0 * (IT)T] -= v; if (so.row1 >= 0) b[(IT)so.row1 * (IT)T] += v; }
     }
     if (m == 1) {
       for (int r = 0; r < n; r++) {
         double s = 0.0;
         for (int q = p.row_ptr[r]; q < p.row_ptr[r + 1]; q++)
-          s += k.Mv[(long long)q * B + inst] * x[(long long)p.pcol[q] * T];
-        const double rr = s - b[(long long)r * T];   // residuo = M.x + N
-        b[(long long)r * T] = -rr;
+          s += k.Mv[(IT)q * (IT)B + inst] * x[(IT)p.pcol[q] * (IT)T];
+        const double rr = s - b[(IT)r * (IT)T];   // residuo = M.x + N
+        b[(IT)r * (IT)T] = -rr;
         if (k.resid) k.resid[orow * n + r] = rr;
       }
     }
@@ -252,9 +271,9 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
     for (int kk = 0; kk < n; kk++) {
       const Big3Step st = k.step[m * n + kk];
       if (st.nl) {
-        const double bp = b[(long long)pr[kk] * T];
+        const double bp = b[(IT)pr[kk] * (IT)T];
         for (int i = 0; i < st.nl; i++)
-          b[(long long)k.l_row[st.l0 + i] * T] -= V[(long long)k.l_slot[st.l0 + i] * B] * bp;
+          b[(IT)k.l_row[st.l0 + i] * (IT)T] -= V[(IT)k.l_slot[st.l0 + i] * (IT)B] * bp;
       }
     }
     // backward; dx[kk] is stored over b[pivot row of kk]
@@ -262,21 +281,21 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
       const Big3Step st = k.step[m * n + kk];
       double s = 0.0;
       for (int j = 0; j < st.nu; j++)
-        s += V[(long long)k.u_slot[st.u0 + j] * B] * b[(long long)pr[k.u_col[st.u0 + j]] * T];
-      b[(long long)pr[kk] * T] = (b[(long long)pr[kk] * T] - s) / V[(long long)st.piv * B];
+        s += V[(IT)k.u_slot[st.u0 + j] * (IT)B] * b[(IT)pr[k.u_col[st.u0 + j]] * (IT)T];
+      b[(IT)pr[kk] * (IT)T] = (b[(IT)pr[kk] * (IT)T] - s) / V[(IT)st.piv * (IT)B];
     }
     // x <- x + dx; gmin_check on pass 2 (results.py:493-523)
     for (int c = 0; c < n; c++) {
-      const double xo = x[(long long)c * T], xn = xo + b[(long long)pr[c] * T];
+      const double xo = x[(IT)c * (IT)T], xn = xo + b[(IT)pr[c] * (IT)T];
       if (m == 1) {
         const bool isv = c < p.nv1;
         const double er = isv ? k.o.ver : k.o.ier, ea = isv ? k.o.vea : k.o.iea;
         if (fabs(xn - xo) > er * fmax(fabs(xo), fabs(xn)) + ea) bad = 1;
       }
-      x[(long long)c * T] = xn;
+      x[(IT)c * (IT)T] = xn;
     }
   }
-  for (int c = 0; c < n; c++) k.x_out[orow * n + c] = x[(long long)c * T];
+  for (int c = 0; c < n; c++) k.x_out[orow * n + c] = x[(IT)c * (IT)T];
   k.iters[orow] = 2;
   k.status[orow] = AHK_ST_OK | (bad ? AHK_ST_GMIN_CHECK : 0);
 }
@@ -285,7 +304,7 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
 __global__ void __launch_bounds__(128) k_big3_factor(const __grid_constant__ Big3K k) {
   const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= k.B) return;
-  const int fl = big3_factor_one(k, inst);
+  const int fl = k.idx32 ? big3_factor_one<unsigned>(k, inst) : big3_factor_one<long long>(k, inst);
   k.flag[inst] = fl;
   if (fl == BIG3_DYNAMIC) { const int at = atomicAdd(&k.ovf[0], 1); k.ovf[1 + at] = (int)inst; }
 }
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(128) k_big3_factor(const __grid_constant__ Big
 __global__ void __launch_bounds__(128) k_big3_solve(const __grid_constant__ Big3K k) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= k.B * k.ptc) return;
-  big3_solve_one(k, tid);
+  if (k.idx32) big3_solve_one<unsigned>(k, tid); else big3_solve_one<long long>(k, tid);
 }
 #endif
 

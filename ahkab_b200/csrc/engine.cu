@@ -171,7 +171,8 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       s3_slots_epoch = e->slots_epoch; s3_opts_epoch = e->opts_epoch;
       if (s3_ok) {
         std::vector<unsigned char> buf;
-        size_t off[9];
+        size_t off[11];
+        off[9] = put(buf, S.rslot); off[10] = put(buf, S.rindex);
         off[0] = put(buf, S.step); off[1] = put(buf, S.prow); off[2] = put(buf, S.cand_slot);
         off[3] = put(buf, S.cand_row); off[4] = put(buf, S.l_slot); off[5] = put(buf, S.l_row);
         off[6] = put(buf, S.u_slot); off[7] = put(buf, S.u_col); off[8] = put(buf, S.upd);
@@ -179,15 +180,16 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         cudaFree(s3_sched); s3_sched = nullptr;
         CKB(cudaMalloc(&s3_sched, buf.size() + 64));
         CKB(cudaMemcpy(s3_sched, buf.data(), buf.size(), cudaMemcpyHostToDevice));
-        for (int i = 0; i < 9; i++) s3_ptr[i] = (const unsigned char*)s3_sched + off[i];
-        s3_n = S.n; s3_npos = S.npos; s3_nslot = S.nslot;
+        for (int i = 0; i < 11; i++) s3_ptr[i] = (const unsigned char*)s3_sched + off[i];
+        s3_n = S.n; s3_npos = S.npos; s3_nslot = S.nslot; s3_nrec = (int)S.rslot.size();
       }
     }
     if (s3_ok) {
       const long long B = batch->B;
       // scratch of the solve kernel: [n][B * ptc] doubles twice, at most ~1 GB per buffer
       int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 27) / ((long long)n * B)));
-      const size_t needV = (size_t)2 * s3_nslot * B, needM = (size_t)s3_npos * B, needS = (size_t)n * B * ptc;
+      // (the reciprocal table shares the allocation of the matrix values: Mv | G)
+      const size_t needV = (size_t)2 * s3_nslot * B, needM = (size_t)(s3_npos + s3_nrec) * B, needS = (size_t)n * B * ptc;
       if (needV > s3_V_cap || needM > s3_Mv_cap || needS > s3_scr_cap || (size_t)B > s3_flag_cap ||
           batch->B + 1 > ovf_cap) {
         CKB(cudaStreamSynchronize(s));
@@ -207,12 +209,15 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       Big3K k3;
       k3.p = e->dprog; k3.o = e->o; k3.vary = batch->vary; k3.B = B;
       k3.src_elem = src_elem; k3.sweep = d_sweep; k3.npts = npts; k3.pt0 = 0; k3.ptc = ptc;
+      k3.idx32 = (needV < (1ull << 31) && needM < (1ull << 31) && needS < (1ull << 31)) ? 1 : 0;
       k3.x_out = x_out; k3.iters = iters; k3.status = status; k3.resid = resid;
       k3.n = s3_n; k3.npos = s3_npos; k3.nslot = s3_nslot;
       k3.step = (const Big3Step*)s3_ptr[0]; k3.prow = (const int*)s3_ptr[1];
       k3.cand_slot = (const int*)s3_ptr[2]; k3.cand_row = (const int*)s3_ptr[3];
       k3.l_slot = (const int*)s3_ptr[4]; k3.l_row = (const int*)s3_ptr[5];
       k3.u_slot = (const int*)s3_ptr[6]; k3.u_col = (const int*)s3_ptr[7]; k3.upd = (const int*)s3_ptr[8];
+      k3.rslot = (const int*)s3_ptr[9]; k3.rindex = (const int*)s3_ptr[10]; k3.nrec = s3_nrec;
+      k3.G = s3_Mv + (size_t)s3_npos * B;
       k3.V = s3_V; k3.Mv = s3_Mv; k3.flag = s3_flag; k3.bs = s3_bs; k3.xs = s3_xs; k3.ovf = d_ovf;
       k_big3_factor<<<(int)((B + 127) / 128), 128, 0, s>>>(k3);
       CKB(cudaGetLastError());

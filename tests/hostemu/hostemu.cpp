@@ -119,18 +119,20 @@ int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_
   const int n = S.n;
   std::vector<double> V((size_t)2 * S.nslot * B), Mv((size_t)S.npos * B), bs((size_t)n * B * npts), xs((size_t)n * B * npts);
   std::vector<int> flag(B), ovf(B + 1, 0);
+  std::vector<double> G((size_t)S.rslot.size() * B);
   Big3K k;
   k.p = H.view(); k.o = q; k.vary = vary; k.B = B; k.src_elem = src_elem; k.sweep = sweep; k.npts = npts;
-  k.pt0 = 0; k.ptc = npts;
+  k.pt0 = 0; k.ptc = npts; k.idx32 = 0;
   k.x_out = x_out; k.iters = iters; k.status = status; k.resid = resid;
   k.n = n; k.npos = S.npos; k.nslot = S.nslot;
   k.step = S.step.data(); k.prow = S.prow.data(); k.cand_slot = S.cand_slot.data(); k.cand_row = S.cand_row.data();
   k.l_slot = S.l_slot.data(); k.l_row = S.l_row.data(); k.u_slot = S.u_slot.data(); k.u_col = S.u_col.data();
   k.upd = S.upd.data();
+  k.rslot = S.rslot.data(); k.rindex = S.rindex.data(); k.nrec = (int)S.rslot.size(); k.G = G.data();
   k.V = V.data(); k.Mv = Mv.data(); k.flag = flag.data(); k.bs = bs.data(); k.xs = xs.data(); k.ovf = ovf.data();
   int dyn = 0;
-  for (int64_t b = 0; b < B; b++) { flag[b] = big3_factor_one(k, b); if (flag[b] == BIG3_DYNAMIC) dyn++; flags[b] = flag[b]; }
-  for (int64_t t = 0; t < B * npts; t++) big3_solve_one(k, t);
+  for (int64_t b = 0; b < B; b++) { flag[b] = big3_factor_one<long long>(k, b); if (flag[b] == BIG3_DYNAMIC) dyn++; flags[b] = flag[b]; }
+  for (int64_t t = 0; t < B * npts; t++) big3_solve_one<long long>(k, t);
   return dyn;
 }
 
