@@ -141,6 +141,7 @@ struct Big3K {
   const double* vary; long long B;
   int src_elem; const double* sweep; int npts;
   int idx32;        // every [slot][instance] / [row][thread] array has < 2^31 elements
+  int b_smem;       // solve kernel: right-hand sides in shared memory (n * blockDim doubles)
   int pt0, ptc;     // this launch solves the points pt0 .. pt0 + ptc - 1 (scratch holds ptc points)
   double* x_out; int* iters; int* status; double* resid;
   int n, npos, nslot;
@@ -223,8 +224,12 @@ AHK_DEV int big3_factor_one(const Big3K& k, long long inst) {
 
 // ---- per-(instance, point) solve (one thread = one right-hand side) -------------------------
 // tid = pt * B + inst: consecutive threads = consecutive instances (coalesced V / Mv / vary)
+// b / bT: the thread's right-hand side and its stride — global scratch ([n][B*ptc], stride T)
+// or the block's shared memory ([n][blockDim], stride blockDim): every forward / backward
+// substitution step reads what the previous one wrote, so the latency of this array is the
+// latency of the kernel.
 template <typename IT>
-AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
+AHK_DEV void big3_solve_one(const Big3K& k, long long tid, double* b, IT bT) {
   const Prog& p = k.p;
   const long long B = k.B, T = B * k.ptc;
   const long long inst = tid % B;
@@ -241,7 +246,6 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
     const int v = p.slot_vary[slot];
     return v < 0 ? p.nominal[slot] : k.vary[(IT)v * (IT)B + inst];
   };
-  double* b = k.bs + tid;      // b[r] = b[r * T]
   double* x = k.xs + tid;
   for (int r = 0; r < n; r++) x[(IT)r * (IT)T] = 0.0;
   int bad = 0;
@@ -249,21 +253,21 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
     const double* V = k.V + (IT)m * k.nslot * (IT)B + inst;
     const int* pr = k.prow + m * n;
     // b = -(M x + N): N first (dc_analysis.py:1004-1040), then the mat-vec
-    for (int r = 0; r < n; r++) b[(IT)r * (IT)T] = 0.0;
+    for (int r = 0; r < n; r++) b[(IT)r * bT] = 0.0;
     for (int s = 0; s < p.nsrc; s++) {
       const SrcOp& so = p.src[s];
       if (so.tf) continue;
       const double v = (so.elem == k.src_elem) ? k.sweep[pt] : P(so.pbase);
-      if (so.is_v) b[(IT)so.row0 * (IT)T] = v;      // N[row] = -V  =>  -N = V
-      else { if (so.row0 >= 0) b[(IT)so.row0 * (IT)T] -= v; if (so.row1 >= 0) b[(IT)so.row1 * (IT)T] += v; }
+      if (so.is_v) b[(IT)so.row0 * bT] = v;      // N[row] = -V  =>  -N = V
+      else { if (so.row0 >= 0) b[(IT)so.row0 * bT] -= v; if (so.row1 >= 0) b[(IT)so.row1 * bT] += v; }
     }
     if (m == 1) {
       for (int r = 0; r < n; r++) {
         double s = 0.0;
         for (int q = p.row_ptr[r]; q < p.row_ptr[r + 1]; q++)
           s += k.Mv[(IT)q * (IT)B + inst] * x[(IT)p.pcol[q] * (IT)T];
-        const double rr = s - b[(IT)r * (IT)T];   // residuo = M.x + N
-        b[(IT)r * (IT)T] = -rr;
+        const double rr = s - b[(IT)r * bT];   // residuo = M.x + N
+        b[(IT)r * bT] = -rr;
         if (k.resid) k.resid[orow * n + r] = rr;
       }
     }
@@ -271,9 +275,9 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
     for (int kk = 0; kk < n; kk++) {
       const Big3Step st = k.step[m * n + kk];
       if (st.nl) {
-        const double bp = b[(IT)pr[kk] * (IT)T];
+        const double bp = b[(IT)pr[kk] * bT];
         for (int i = 0; i < st.nl; i++)
-          b[(IT)k.l_row[st.l0 + i] * (IT)T] -= V[(IT)k.l_slot[st.l0 + i] * (IT)B] * bp;
+          b[(IT)k.l_row[st.l0 + i] * bT] -= V[(IT)k.l_slot[st.l0 + i] * (IT)B] * bp;
       }
     }
     // backward; dx[kk] is stored over b[pivot row of kk]
@@ -281,12 +285,12 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid) {
       const Big3Step st = k.step[m * n + kk];
       double s = 0.0;
       for (int j = 0; j < st.nu; j++)
-        s += V[(IT)k.u_slot[st.u0 + j] * (IT)B] * b[(IT)pr[k.u_col[st.u0 + j]] * (IT)T];
-      b[(IT)pr[kk] * (IT)T] = (b[(IT)pr[kk] * (IT)T] - s) / V[(IT)st.piv * (IT)B];
+        s += V[(IT)k.u_slot[st.u0 + j] * (IT)B] * b[(IT)pr[k.u_col[st.u0 + j]] * bT];
+      b[(IT)pr[kk] * bT] = (b[(IT)pr[kk] * bT] - s) / V[(IT)st.piv * (IT)B];
     }
     // x <- x + dx; gmin_check on pass 2 (results.py:493-523)
     for (int c = 0; c < n; c++) {
-      const double xo = x[(IT)c * (IT)T], xn = xo + b[(IT)pr[c] * (IT)T];
+      const double xo = x[(IT)c * (IT)T], xn = xo + b[(IT)pr[c] * bT];
       if (m == 1) {
         const bool isv = c < p.nv1;
         const double er = isv ? k.o.ver : k.o.ier, ea = isv ? k.o.vea : k.o.iea;
@@ -312,7 +316,17 @@ __global__ void __launch_bounds__(128) k_big3_factor(const __grid_constant__ Big
 __global__ void __launch_bounds__(128) k_big3_solve(const __grid_constant__ Big3K k) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= k.B * k.ptc) return;
-  if (k.idx32) big3_solve_one<unsigned>(k, tid); else big3_solve_one<long long>(k, tid);
+  extern __shared__ __align__(16) double big3_sb[];
+  if (k.b_smem) {       // right-hand side in shared memory: [n][blockDim]
+    double* b = big3_sb + threadIdx.x;
+    if (k.idx32) big3_solve_one<unsigned>(k, tid, b, (unsigned)blockDim.x);
+    else big3_solve_one<long long>(k, tid, b, (long long)blockDim.x);
+  } else {
+    double* b = k.bs + tid;
+    const long long T = k.B * k.ptc;
+    if (k.idx32) big3_solve_one<unsigned>(k, tid, b, (unsigned)T);
+    else big3_solve_one<long long>(k, tid, b, T);
+  }
 }
 #endif
 

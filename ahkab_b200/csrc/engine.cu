@@ -209,6 +209,7 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       Big3K k3;
       k3.p = e->dprog; k3.o = e->o; k3.vary = batch->vary; k3.B = B;
       k3.src_elem = src_elem; k3.sweep = d_sweep; k3.npts = npts; k3.pt0 = 0; k3.ptc = ptc;
+      k3.b_smem = 0;
       k3.idx32 = (needV < (1ull << 31) && needM < (1ull << 31) && needS < (1ull << 31)) ? 1 : 0;
       k3.x_out = x_out; k3.iters = iters; k3.status = status; k3.resid = resid;
       k3.n = s3_n; k3.npos = s3_npos; k3.nslot = s3_nslot;
@@ -222,10 +223,21 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       k_big3_factor<<<(int)((B + 127) / 128), 128, 0, s>>>(k3);
       CKB(cudaGetLastError());
       launches++;
+      // right-hand sides: global scratch [n][thread].  Shared memory (AHK_BIGLIN3_SMEM_RHS=1,
+      // blocks of 64 threads x 132 KB for n = 257) was measured and is WORSE — C5 8.6 vs 3.6 ms:
+      // two warps per SM cannot hide the latency of the factor / schedule loads
+      int sthreads = 128; size_t ssmem = 0;
+      k3.b_smem = 0;
+      if (getenv("AHK_BIGLIN3_SMEM_RHS")) {
+        for (int th = 64; th >= 32; th >>= 1)
+          if ((size_t)n * th * 8 <= e->smem_max) { sthreads = th; ssmem = (size_t)n * th * 8; k3.b_smem = 1; break; }
+      }
+      if (ssmem > 48 * 1024)
+        CKB(cudaFuncSetAttribute(k_big3_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
       for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
         k3.pt0 = pt0; k3.ptc = std::min(ptc, npts - pt0);
         const long long T = B * k3.ptc;
-        k_big3_solve<<<(int)((T + 127) / 128), 128, 0, s>>>(k3);
+        k_big3_solve<<<(int)((T + sthreads - 1) / sthreads), sthreads, ssmem, s>>>(k3);
         CKB(cudaGetLastError());
         launches++;
       }

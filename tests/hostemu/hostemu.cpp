@@ -122,7 +122,7 @@ int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_
   std::vector<double> G((size_t)S.rslot.size() * B);
   Big3K k;
   k.p = H.view(); k.o = q; k.vary = vary; k.B = B; k.src_elem = src_elem; k.sweep = sweep; k.npts = npts;
-  k.pt0 = 0; k.ptc = npts; k.idx32 = 0;
+  k.pt0 = 0; k.ptc = npts; k.idx32 = 0; k.b_smem = 0;
   k.x_out = x_out; k.iters = iters; k.status = status; k.resid = resid;
   k.n = n; k.npos = S.npos; k.nslot = S.nslot;
   k.step = S.step.data(); k.prow = S.prow.data(); k.cand_slot = S.cand_slot.data(); k.cand_row = S.cand_row.data();
@@ -132,7 +132,8 @@ int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_
   k.V = V.data(); k.Mv = Mv.data(); k.flag = flag.data(); k.bs = bs.data(); k.xs = xs.data(); k.ovf = ovf.data();
   int dyn = 0;
   for (int64_t b = 0; b < B; b++) { flag[b] = big3_factor_one<long long>(k, b); if (flag[b] == BIG3_DYNAMIC) dyn++; flags[b] = flag[b]; }
-  for (int64_t t = 0; t < B * npts; t++) big3_solve_one<long long>(k, t);
+  std::vector<double> bpriv(n);
+  for (int64_t t = 0; t < B * npts; t++) big3_solve_one<long long>(k, t, bpriv.data(), 1LL);   // private right-hand side, stride 1 (the device uses shared memory)
   return dyn;
 }
 
