@@ -220,13 +220,17 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       k3.rslot = (const int*)s3_ptr[9]; k3.rindex = (const int*)s3_ptr[10]; k3.nrec = s3_nrec;
       k3.G = s3_Mv + (size_t)s3_npos * B;
       k3.V = s3_V; k3.Mv = s3_Mv; k3.flag = s3_flag; k3.bs = s3_bs; k3.xs = s3_xs; k3.ovf = d_ovf;
-      k_big3_factor<<<(int)((B + 127) / 128), 128, 0, s>>>(k3);
+      // one thread per instance: small blocks spread the few warps over all SMs
+      int fthreads = 32;
+      if (const char* f = getenv("AHK_BIGLIN3_FT")) fthreads = std::max(32, std::min(128, atoi(f)));   // tuning
+      k_big3_factor<<<(int)((B + fthreads - 1) / fthreads), fthreads, 0, s>>>(k3);
       CKB(cudaGetLastError());
       launches++;
       // right-hand sides: global scratch [n][thread].  Shared memory (AHK_BIGLIN3_SMEM_RHS=1,
       // blocks of 64 threads x 132 KB for n = 257) was measured and is WORSE — C5 8.6 vs 3.6 ms:
       // two warps per SM cannot hide the latency of the factor / schedule loads
       int sthreads = 128; size_t ssmem = 0;
+      if (const char* f = getenv("AHK_BIGLIN3_ST")) sthreads = std::max(32, std::min(128, atoi(f)));   // tuning
       k3.b_smem = 0;
       if (getenv("AHK_BIGLIN3_SMEM_RHS")) {
         for (int th = 64; th >= 32; th >>= 1)
