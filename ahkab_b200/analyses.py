@@ -84,7 +84,8 @@ def get_engine(circ, batch=None, opts=None):
         o = options.snapshot()
         if opts:
             o.update(opts)
-        eng.set_options(**o)
+        if o != eng.opts:          # unchanged options: keep the engine's cached plans / kernels
+            eng.set_options(**o)
     return eng
 
 

@@ -8,7 +8,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../lib/obj ${AHK_PTXAS_V:+-Xptxas -v} ${AHK_DEFS}"
 # sources of the circuit-specialised kernels, embedded for NVRTC (jit.hpp)
 {
-  for f in jit_kernels.cuh entry.cuh core.cuh devices.cuh ac.cuh program.h ../../include/ahkab_b200.h; do
+  for f in jit_kernels.cuh entry.cuh core.cuh devices.cuh fastmath.cuh ac.cuh program.h ../../include/ahkab_b200.h; do
     printf '{"%s", R"AHKSRC(' "$f"; cat "$f"; printf ')AHKSRC"},\n'
   done
 } > ../lib/obj/jit_sources.inc

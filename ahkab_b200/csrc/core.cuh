@@ -112,6 +112,50 @@ struct Grp {  // host emulation (tests/hostemu): G == 1 only
 };
 #endif
 
+// ---- warp-uniform ("flat") kernels ------------------------------------------------------------
+// In the flat transient kernel every lane of a warp executes the same instruction stream: the
+// groups of a warp are in different phases of their analyses, but phase-specific work is
+// predicated, never branched around cross-lane operations.  All shuffles / votes / barriers
+// therefore run with the FULL mask at warp-uniform points (no sub-warp masks: those make the
+// compiler guard every shuffle), and a group-level vote is a slice of the warp ballot.
+#ifdef __CUDACC__
+AHK_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+AHK_DEV bool warp_loop(bool p) { return __any_sync(0xffffffffu, p) != 0; }   // loop control: same vote
+template <int G>
+struct GrpW {
+  static AHK_DEV unsigned slice(unsigned ballot) {
+    if (G == 32) return ballot;
+    const unsigned lane = threadIdx.x & 31u;
+    return (ballot >> (lane & ~(unsigned)(G - 1))) & ((1u << (G & 31)) - 1u);
+  }
+  static AHK_DEV bool all(bool p) {
+    if (G == 1) return p;
+    return slice(__ballot_sync(0xffffffffu, p)) == (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
+  }
+  static AHK_DEV bool any(bool p) {
+    if (G == 1) return p;
+    return slice(__ballot_sync(0xffffffffu, p)) != 0u;
+  }
+  static AHK_DEV void sync() { if (G > 1) __syncwarp(); }
+};
+#else
+// host emulation: one lane.  AHK_EMU_ALWAYS (tests) makes every predicated section of the flat
+// loop run in every iteration, as it does on a warp whose other groups need it — a state
+// update that is not properly predicated then corrupts the lane's own state and shows up
+#ifdef AHK_EMU_ALWAYS
+AHK_DEV bool warp_any(bool) { return true; }
+#else
+AHK_DEV bool warp_any(bool p) { return p; }
+#endif
+AHK_DEV bool warp_loop(bool p) { return p; }
+template <int G>
+struct GrpW {
+  static bool all(bool p) { return p; }
+  static bool any(bool p) { return p; }
+  static void sync() {}
+};
+#endif
+
 struct Ctx {
   const Prog* p;
   const Opts* o;
@@ -251,6 +295,48 @@ AHK_DEV void build_N(Ctx& c) {
   }
 }
 
+#if defined(AHK_JIT) && defined(AHK_JIT_ALL_EKV) && AHK_JIT_ALL_EKV && AHK_JIT_ILP > 1
+#define AHK_EKV_BATCHED 1
+// Every device of this circuit is an (active) EKV transistor: a lane evaluates its devices K at
+// a time through ekv_eval_v, which interleaves the K evaluations statement by statement.
+// Rounds beyond the device list (ndev not a multiple of G*K) re-evaluate the last device and
+// drop the result.  The loop over the batches stays rolled: one copy of the device code.
+template <int K>
+AHK_DEV void eval_devices_ekv(Ctx& c, const double* x) {
+  const Prog& p = *c.p;
+  const int G = AHK_JIT_G;
+  const int rounds = (p.ndev + G - 1) / G;
+  double* dout = c.sm + c.L->dout;
+  const double* dcon = c.sm + c.L->dcon;
+#pragma unroll 1
+  for (int q0 = 0; q0 < rounds; q0 += K) {
+    const double* kk[K];
+    int NP[K], dd[K];
+    bool ok[K];
+    double vd[K], vg[K], vs[K], o0[K], o1[K], o2[K], o3[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const int d = c.sub + (q0 + j) * G;
+      ok[j] = d < p.ndev;
+      dd[j] = ok[j] ? d : p.ndev - 1;
+      const DevOp& dv = p.dev[dd[j]];
+      kk[j] = dcon + dv.con;
+      NP[j] = dv.flags;
+      const double vb = V_of(x, dv.node[3]);
+      vd[j] = V_of(x, dv.node[0]) - vb; vg[j] = V_of(x, dv.node[1]) - vb; vs[j] = V_of(x, dv.node[2]) - vb;
+    }
+    ekv_eval_v<K>(kk, NP, vd, vg, vs, c.o->gmin, o0, o1, o2, o3);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (ok[j]) {
+        double* out = dout + p.dev[dd[j]].dout;
+        out[0] = o0[j]; out[1] = o1[j]; out[2] = o2[j]; out[3] = o3[j];
+      }
+    }
+  }
+}
+#endif
+
 // ---- device evaluation: one device per lane ------------------------------------
 // Not a template: one copy of the device models per kernel, whatever the variant.
 AHK_DEV void eval_devices(Ctx& c, const double* x) {
@@ -262,6 +348,11 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
   const int G = AHK_JIT_G;
 #else
   const int G = c.G;
+#endif
+#ifdef AHK_EKV_BATCHED
+  (void)o; (void)dout; (void)dst;
+  eval_devices_ekv<AHK_JIT_ILP>(c, x);
+  return;
 #endif
   AHK_LANES(d, p.ndev) {
     const DevOp& dv = p.dev[d];
@@ -300,6 +391,7 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
     }
   }
 }
+
 
 // ---- assembly: [Bv + J | -(Bv.x + T + Tx)], row-local, no conflicts ----------------
 // residuo = mna.dot(x) + T + Tx (dc_analysis.py:816); the matrix solved is mna + J.
@@ -342,10 +434,15 @@ AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
 // back-substitution: every elimination step updates all other rows, so no lane idles
 // and there is no serial triangular solve; rows are never moved.  Results differ from
 // dgesv by rounding only.  Returns 0 if a pivot is exactly zero (LinAlgError).
-template <class V>
+// FLAT (warp-uniform kernels): a singular matrix must not leave the function early — the other
+// groups of the warp still need this group's lanes in their full-mask shuffles — so the
+// elimination runs to the end on garbage and only the return value reports it.
+template <class V, bool FLAT = false>
 AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
   const int NC = V::NC, R = V::R, G = V::G;
   const int n = c.p->n;
+  int nonsing = 1;
+  const unsigned gm = FLAT ? 0xffffffffu : c.mask;   // flat kernels: the literal full mask (unguarded shuffles)
   double* dx = c.sm + c.L->dx;
   double* pvb = c.sm + c.L->pvb;   // [2][NC] pivot-row broadcast buffers
   unsigned usedm = 0;              // bit s: local row slot s has been a pivot row
@@ -364,8 +461,10 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
         const bool cand = r < n && !((usedm >> s) & 1u);
         if (cand && kb > key) key = kb;
       }
-      key = Grp<G>::kmax(key, c.mask);
-      if ((key >> 5) == 0ull) return 0;          // every candidate is exactly zero
+      key = Grp<G>::kmax(key, gm);
+      if ((key >> 5) == 0ull) {                  // every candidate is exactly zero
+        if (FLAT) nonsing = 0; else return 0;
+      }
       const int bi = 31 - (int)(key & 31ull);
       const int own = bi & (G - 1), slot = bi / G;
       const bool mine = c.sub == own;
@@ -374,12 +473,12 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
         // one row per lane: every element of the pivot row is fetched from the owner's
         // registers right where it is used — no pivot-row copy in registers, no
         // shared-memory round trip, no barrier
-        const double pk = Grp<G>::bcast(a[0][k], own, c.mask);
-        const double ipk = 1.0 / pk;
+        const double pk = Grp<G>::bcast(a[0][k], own, gm);
+        const double ipk = fm::rcp(pk);
         if (mine) { usedm |= 1u; pd[0] = ipk; ps[0] = k; }
         const double l = mine ? 0.0 : a[0][k] * ipk;
 #pragma unroll
-        for (int j = k + 1; j < NC; j++) a[0][j] -= l * Grp<G>::bcast(a[0][j], own, c.mask);
+        for (int j = k + 1; j < NC; j++) a[0][j] -= l * Grp<G>::bcast(a[0][j], own, gm);
 #else
       if (G > 1 && R == 1) {
         // one row per lane: the owner publishes its row in one of two shared-memory buffers,
@@ -392,8 +491,8 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
 #pragma unroll
           for (int j = k; j < NC; j++) buf[j] = a[0][j];
         }
-        Grp<G>::sync(c.mask);
-        const double ipk = 1.0 / buf[k];
+        Grp<G>::sync(gm);
+        const double ipk = fm::rcp(buf[k]);
         if (mine) { usedm |= 1u; pd[0] = ipk; ps[0] = k; }
         const double l = mine ? 0.0 : a[0][k] * ipk;
 #pragma unroll
@@ -411,7 +510,7 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
                 for (int j = k; j < NC; j++) buf[j] = a[s][j];
               }
           }
-          Grp<G>::sync(c.mask);
+          Grp<G>::sync(gm);
 #pragma unroll
           for (int j = k; j < NC; j++) pv[j] = buf[j];
         } else {
@@ -423,7 +522,7 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
             pv[j] = t;
           }
         }
-        const double inv = 1.0 / pv[k];
+        const double inv = fm::rcp(pv[k]);
         if (mine) {
           usedm |= 1u << slot;
 #pragma unroll
@@ -443,8 +542,8 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
     const int r = c.sub + G * s;
     if (r < n) dx[ps[s]] = a[s][NC - 1] * pd[s];   // (stored pivot reciprocal: no division)
   }
-  Grp<G>::sync(c.mask);
-  return 1;
+  Grp<G>::sync(gm);
+  return nonsing;
 }
 
 // ---- dense solve, one lane per instance (Var<NC,R,1>): LU in registers -------------------
@@ -483,7 +582,7 @@ AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ?
 #pragma unroll
         for (int r = k + 1; r < R; r++) if (p == r) a[r][j] = t;
       }
-      const double iv = 1.0 / a[k][k];
+      const double iv = fm::rcp(a[k][k]);
       inv[k] = iv;
 #pragma unroll
       for (int r = k + 1; r < R; r++) {     // rows >= n are zero: l = 0
@@ -508,9 +607,11 @@ AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ?
 
 // ---- dense solve, generic fallback (Var<0,0,G>): matrix in shared memory ----------------
 // Gaussian elimination with implicit partial pivoting + back-substitution, run-time n.
-template <int G>
+template <int G, bool FLAT = false>
 AHK_DEV int lu_solve_smem(Ctx& c) {
   const int n = c.p->n, RS = c.L->RS;
+  int nonsing = 1;
+  const unsigned gm = FLAT ? 0xffffffffu : c.mask;
   double* A = c.A();
   double* dx = c.sm + c.L->dx;
   unsigned char* prow = c.prow();
@@ -524,8 +625,11 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
       double v = fabs(A[r * RS + k]);
       if (bi < 0 || v > best) { best = v; bi = r; }
     }
-    Grp<G>::argmax(best, bi, c.mask);
-    if (best == 0.0) return 0;
+    Grp<G>::argmax(best, bi, gm);
+    if (best == 0.0) {
+      if (!FLAT) return 0;
+      nonsing = 0;              // (flat kernels run on, on garbage, to keep the warp together)
+    }
     used |= 1ull << bi;
     if (c.sub == 0) { prow[k] = (unsigned char)bi; stepof[bi] = (unsigned char)k; }
     const double* Ap = A + bi * RS;
@@ -537,7 +641,7 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
       if (l == 0.0) continue;                       // structural zeros: skip the row
       for (int j = k + 1; j <= n; j++) Ar[j] -= l * Ap[j];
     }
-    Grp<G>::sync(c.mask);
+    Grp<G>::sync(gm);
   }
   for (int k = n - 1; k >= 0; k--) {
     int pr = prow[k];
@@ -546,9 +650,9 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
     for (int r = c.sub; r < n; r += G) {
       if ((int)stepof[r] < k) { double a = A[r * RS + k]; if (a != 0.0) A[r * RS + n] -= a * xk; }
     }
-    Grp<G>::sync(c.mask);
+    Grp<G>::sync(gm);
   }
-  return 1;
+  return nonsing;
 }
 
 #ifdef AHK_JIT
@@ -583,19 +687,28 @@ AHK_DEV double assemble_row_switch(Ctx& c, int r, double (&row)[NC]) {
 #endif
 
 // one Newton linear step: assemble at x() and solve into dx(); 0 = singular
-template <class V>
+template <class V, bool FLAT = false>
 AHK_DEV int assemble_solve(Ctx& c) {
   const int n = c.p->n, RS = c.L->RS, G = V::G;
   double* A = c.A();
   if constexpr (V::NC > 0) {
     const int NC = V::NC, R = V::R;
     double a[R > 0 ? R : 1][NC > 0 ? NC : 1];
+#ifdef AHK_JIT
+    // REPLICATED solve: several lanes per instance (they share the device evaluations), but
+    // every lane holds ALL rows and runs the one-lane LU redundantly — for a small matrix
+    // behind expensive devices that beats distributing rows (no pivot search across lanes, no
+    // pivot-row broadcast, no idle lanes when n is not a multiple of G)
+    constexpr bool REP = G > 1 && R >= Prog::n;
+#else
+    constexpr bool REP = false;
+#endif
 #pragma unroll
     for (int s = 0; s < R; s++) {
-      const int r = c.sub + G * s;
+      const int r = REP ? s : c.sub + G * s;
 #ifdef AHK_JIT
       (void)A; (void)RS;
-      if (G == 1) {   // r == s: a compile-time constant
+      if (G == 1 || REP) {   // r == s: a compile-time constant
         if (s < n) {
 #pragma unroll
           for (int j = 0; j < NC - 1; j++) a[s][j] = 0.0;
@@ -604,7 +717,7 @@ AHK_DEV int assemble_solve(Ctx& c) {
       } else if (r < n) {
         a[s][NC - 1] = assemble_row_switch<NC>(c, r, a[s]);
       }
-      if (G == 1 ? s >= n : r >= n) {
+      if ((G == 1 || REP) ? s >= n : r >= n) {
 #pragma unroll
         for (int j = 0; j < NC; j++) a[s][j] = 0.0;
       }
@@ -626,16 +739,19 @@ AHK_DEV int assemble_solve(Ctx& c) {
       }
 #endif
     }
-    if constexpr (V::G == 1) return lu_solve_thread<V>(c, a);
-    else return gj_solve<V>(c, a);
+    if constexpr (V::G == 1 || REP) {
+      const int okk = lu_solve_thread<V>(c, a);   // (REP: every lane stores the same dx)
+      Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
+      return okk;
+    } else return gj_solve<V, FLAT>(c, a);
   } else {
     for (int r = c.sub; r < n; r += G) {
       double* Ar = A + r * RS;
       for (int j = 0; j < n; j++) Ar[j] = 0.0;
       Ar[n] = assemble_row(c, r, Ar);
     }
-    Grp<G>::sync(c.mask);
-    return lu_solve_smem<G>(c);
+    Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
+    return lu_solve_smem<G, FLAT>(c);
   }
 }
 
@@ -671,7 +787,7 @@ AHK_DEV int mdn_solver(Ctx& c, int MAXIT, int* iters) {
         if (d > dmax) dmax = d;                         // (a NaN step never wins: as `d > lim` before)
       }
       dmax = Grp<G>::fmax_all(dmax, c.mask);
-      if (dmax > lim) td = fmin(td, lim / dmax);
+      if (dmax > lim) td = fmin(td, fm::div(lim, dmax));
     }
     // convergence_check (utilities.py:392-549): np.allclose(x, x + dx) per unit class and
     // |residual| <= the other class's absolute tolerance; NaN never passes
@@ -849,9 +965,19 @@ AHK_DEV int check_step(const Opts& o, double& tstep, double time, double tstop, 
 
 struct DfOut { double C1, x_lte, pred_lte; int has_pred; };
 
+// rmin ** (1 / (order + 1)) of the LTE step factor (transient.py:362)
+#ifdef __CUDACC__
+AHK_DEV double fm_pow(double b, double e) { return fm::exp(fm::log(b) * e); }
+#else
+AHK_DEV double fm_pow(double b, double e) { return pow(b, e); }
+#endif
+
 AHK_DEV double ipow(double b, int e) { double r = 1.0; for (int i = 0; i < e; i++) r *= b; return r; }
 
+// Differentiation formula of the next step: C1, C0[], the LTE coefficients and the predictor.
 // History ring: entry k (k = 0 newest) lives in slot (h0 + k) % buflen.
+// No cross-lane traffic: every lane forms the (group-uniform) coefficients itself and writes
+// the components of C0 / pred it owns; the caller synchronises the group afterwards.
 template <class V>
 AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h0, int buflen,
                     double step, bool predict, DfOut& d) {
@@ -899,43 +1025,33 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
       d.has_pred = 1;
     }
   } else {                                           // gear.py:122-208
-    // s / alpha / gamma (order + 2 entries each) live in the instance's scratch: lane 0
-    // fills them, the group reads them (keeps run-time indexed arrays out of local memory)
-    double* s = c.sm + c.L->gsc;
-    double* alpha = s + 8;
-    double* gamma = s + 16;
-    if (c.sub == 0) {
-      s[0] = 0;
+    // s / alpha / gamma: order + 2 entries each (a specialised build knows the order: the
+    // loops unroll and the arrays live in registers)
+    double s[8], alpha[8], gamma[8];
+    s[0] = 0;
+    AHK_UNROLL
+    for (int i = 1; i < order + 2; i++) s[i] = step + HT(0) - HT(i - 1);
+    AHK_UNROLL
+    for (int k = 1; k < order + 2; k++) {
+      double a = 1.0;
       AHK_UNROLL
-      for (int i = 1; i < order + 2; i++) s[i] = step + HT(0) - HT(i - 1);
-      AHK_UNROLL
-      for (int k = 1; k < order + 2; k++) {
-        double a = 1.0;
-        AHK_UNROLL
-        for (int j = 1; j < order + 2; j++) a *= (j == k) ? 1.0 : s[j] / (s[j] - s[k]);
-        alpha[k] = a;
-      }
-      double g0 = 0;
-      AHK_UNROLL
-      for (int k = 1; k < order + 1; k++) {
-        gamma[k] = alpha[k] * ((1.0 / s[order + 1]) - (1.0 / s[k]));
-        g0 -= gamma[k];
-      }
-      gamma[0] = g0;
-      double xl = 0.0, fact = 1.0;
-      AHK_UNROLL
-      for (int k = 2; k <= order + 1; k++) fact *= k;
-      AHK_UNROLL
-      for (int k = 1; k < order + 1; k++) xl += ipow(s[k], order + 1) * (-1.0 * gamma[k] / g0);
-      s[24] = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;    // x_lte
-      double pl = -1.0 / fact;
-      AHK_UNROLL
-      for (int k = 1; k < order + 2; k++) pl *= s[k];
-      s[25] = pl;                                                      // pred_lte
+      for (int j = 1; j < order + 2; j++) a *= (j == k) ? 1.0 : fm::div(s[j], s[j] - s[k]);
+      alpha[k] = a;
     }
-    Grp<G>::sync(c.mask);
-    d.C1 = gamma[0];
-    d.x_lte = s[24];
+    double g0 = 0;
+    AHK_UNROLL
+    for (int k = 1; k < order + 1; k++) {
+      gamma[k] = alpha[k] * (fm::rcp(s[order + 1]) - fm::rcp(s[k]));
+      g0 -= gamma[k];
+    }
+    gamma[0] = g0;
+    double xl = 0.0, fact = 1.0;
+    AHK_UNROLL
+    for (int k = 2; k <= order + 1; k++) fact *= k;
+    AHK_UNROLL
+    for (int k = 1; k < order + 1; k++) xl += ipow(s[k], order + 1) * fm::div(-1.0 * gamma[k], g0);
+    d.x_lte = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;
+    d.C1 = g0;
     AHK_LANES(i, n) {
       double a = 0.0;
       AHK_UNROLL
@@ -943,19 +1059,21 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
       C0[i] = a;
     }
     if (predict) {
+      double pl = -1.0 / fact;
+      AHK_UNROLL
+      for (int k = 1; k < order + 2; k++) pl *= s[k];
       AHK_LANES(i, n) {
         double a = 0.0;
         AHK_UNROLL
         for (int k = 1; k < order + 2; k++) a = a + alpha[k] * HX(k - 1)[i];
         pred[i] = a;
       }
-      d.pred_lte = s[25];
+      d.pred_lte = pl;
       d.has_pred = 1;
     }
   }
 #undef HT
 #undef HX
-  Grp<G>::sync(c.mask);
 }
 
 struct TranArgs {
@@ -966,9 +1084,24 @@ struct TranArgs {
   int* rows; int* counters;
 };
 
-// in: x() holds x(tstart).  returns status word.
+// phases of a group inside the flat transient loop
+enum { PH_STEP = 0, PH_SOLVE = 1, PH_NR = 2, PH_DSFAIL = 3, PH_DONE = 4 };
+
+// transient.transient_analysis for one instance, in WARP-UNIFORM ("flat") form.
+// in: x() holds x(tstart).  returns the status word.
+//
+// The reference nests three loops per instance — time steps (transient.py:323-405), the
+// homotopy stages of dc_solve (dc_analysis.py:258-320) and the Newton iterations of mdn_solver
+// (dc_analysis.py:796-836).  A warp carries 32 / G instances whose trip counts differ at every
+// level (Newton iterations per solve, rejected steps, step counts), so nested loops make the
+// groups of a warp wait for the slowest at EVERY loop exit.  Here the nest is one loop whose
+// body is ONE Newton iteration for every group, preceded / followed by the step and stage
+// bookkeeping of the groups that need it in this pass (predicated on the group's phase): no
+// group ever waits for another one's iteration count, only the instance with the most Newton
+// iterations in total bounds the warp.  `live` = false: padding group of a partial warp (no
+// instance): it runs along (the warp's shuffles need all lanes) and never touches HBM.
 template <class V>
-AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
+AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
   const int G = V::G;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
@@ -980,6 +1113,9 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   const int method = a.method, use_step_control = a.use_step_control;
 #endif
   double* x = c.x();
+  double* dx = c.sm + c.L->dx;
+  const double* res = c.sm + c.L->res;
+  double* xin = c.sm + c.L->xin;     // x at the entry of mdn_solver (restored if the matrix is singular)
   double* xacc = c.sm + c.L->xacc;   // last accepted x
   double* ht = c.sm + c.L->ht;
   double* hx = c.sm + c.L->hx;
@@ -987,6 +1123,9 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   double* C0 = c.sm + c.L->C0;
   double* pred = c.sm + c.L->pred;
   double* Ntr = c.sm + c.L->Ntr;
+  double* Nd = c.sm + c.L->Nd;
+  const double* Nc = c.sm + c.L->Nc;
+  double* T = c.sm + c.L->T;
   const double* Dv = c.sm + c.L->Dv;
   double* xs = c.sm + c.L->xs;       // NR start point when nothing better exists
   int order, max_x, max_dx, pmax_x;
@@ -997,12 +1136,16 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   if (max_x > 0 || max_dx >= 0) { first_iters = max_x; if (max_dx >= 0 && max_dx + 1 > first_iters) first_iters = max_dx + 1; }
   const int start_pred = pmax_x > 0 ? pmax_x : 0;
   const double HMAX = a.tstep;
+  const double lim = o.nl_voltages_lock_factor * AHK_VTH;
+  const int MAXIT = o.transient_max_nr_iter;
+  const int use = (o.use_standard_solve_method ? 1 : 0) | (o.use_gmin_stepping ? 2 : 0) |
+                  (o.use_source_stepping ? 4 : 0);
   double tstep = a.tstep;
   build_N(c);
   int h0 = 0, nh = 1;
   AHK_LANES(i, n) { hx[i] = x[i]; xs[i] = x[i]; xacc[i] = x[i]; }
   if (c.sub == 0) ht[0] = a.tstart;
-  Grp<G>::sync(c.mask);
+  GrpW<G>::sync();
   double time = a.tstart;
   if (use_step_control) tstep = fmin((a.tstop - a.tstart) / 9999.0, HMAX);
   int iter_n = 0, solved = 1, have_x = 0, status = 0;
@@ -1010,88 +1153,222 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a) {
   int n_solves = 0, n_nr = 0, n_rej = 0, n_cut = 0;
   double* t_out = a.t_out + c.inst * a.max_rows;
   double* x_out = a.x_out + c.inst * a.max_rows * n;
-  while (time < a.tstop) {
-    DfOut d;
-    bool predict = use_step_control && iter_n >= start_pred;
-    get_df<V>(c, method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
-    // NR start point (transient.py:335-338)
-    if (o.transient_prediction_as_x0 && use_step_control && d.has_pred) {
-      AHK_LANES(i, n) x[i] = pred[i];
-    } else if (have_x) {
-      AHK_LANES(i, n) x[i] = xacc[i];
-    } else {
-      AHK_LANES(i, n) x[i] = xs[i];
+  // state of the running dc_solve / mdn_solver
+  int failed = 0, enabled = -1, gidx = 0, sidx = 0, ds_iters = 0, it = 0;
+  DfOut d;
+  d.C1 = 0.0; d.x_lte = 0.0; d.pred_lte = 0.0; d.has_pred = 0;
+  int phase = (live && time < a.tstop) ? PH_STEP : PH_DONE;
+  while (warp_loop(phase != PH_DONE)) {
+    // ===== (1) a new step attempt: DF coefficients, NR start point, Ntran; dc_solve entry =====
+    if (warp_any(phase == PH_STEP)) {
+      const bool m = phase == PH_STEP;
+      if (m) {
+        const bool predict = use_step_control && iter_n >= start_pred;
+        get_df<V>(c, method, order, iter_n < first_iters, nh, h0, buflen, tstep, predict, d);
+      }
+      GrpW<G>::sync();
+      if (m) {
+        // NR start point (transient.py:335-338)
+        if (o.transient_prediction_as_x0 && use_step_control && d.has_pred) {
+          AHK_LANES(i, n) x[i] = pred[i];
+        } else if (have_x) {
+          AHK_LANES(i, n) x[i] = xacc[i];
+        } else {
+          AHK_LANES(i, n) x[i] = xs[i];
+        }
+        // Ntran = D . C0
+        AHK_LANES(r, n) {
+          double s = 0.0;
+          AHK_UNROLL
+          for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) s += Dv[k] * C0[p.pcol[k]];
+          Ntr[r] = s;
+        }
+        c.C1 = d.C1;
+        // dc_solve entry (dc_analysis.py:222-257): N + Tt(t), first enabled method
+        if (p.ntd) {
+          AHK_LANES(i, n) Nd[i] = Nc[i];
+        }
+      }
+      if (p.ntd) {   // Tt(t), dc_analysis.py:222-237
+        GrpW<G>::sync();
+        if (m && c.sub == 0) {
+          AHK_UNROLL
+          for (int k = 0; k < p.nsrc; k++) {
+            const SrcOp& sr = p.src[k];
+            if (!sr.tf) continue;
+            double v = tf_eval(sr.tf, c.sm + c.L->Pv + sr.ppb + 1, time + tstep);
+            if (sr.is_v) Nd[sr.row0] += -1 * v;
+            else { if (sr.row0 >= 0) Nd[sr.row0] += v; if (sr.row1 >= 0) Nd[sr.row1] -= v; }
+          }
+        }
+      }
+      if (m) {
+        failed = 0; gidx = 0; sidx = 0; ds_iters = 0;
+        enabled = -1;
+        for (int q = 0; q < 3; q++) if ((use >> q) & 1) { enabled = q; break; }
+        phase = enabled < 0 ? PH_DSFAIL : PH_SOLVE;
+      }
     }
-    // Ntran = D . C0
-    AHK_LANES(r, n) {
-      double s = 0.0;
-      AHK_UNROLL
-      for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) s += Dv[k] * C0[p.pcol[k]];
-      Ntr[r] = s;
+    // ===== (2) a homotopy stage of dc_solve: Gmin, source factor, T; mdn_solver entry =====
+    if (warp_any(phase == PH_SOLVE)) {
+      const bool m = phase == PH_SOLVE;
+      GrpW<G>::sync();
+      if (m) {
+        double g = o.gmin, f = 1.0;
+        if (enabled == 1) g = gmin_step_value(gidx);   // replaces Gmin (dc_analysis.py:262-269,452-455)
+        else if (enabled == 2) f = source_step_value(sidx);
+        c.gadd = g;     // Gmin and C1 D are added while assembling
+        AHK_LANES(i, n) {
+          T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + Ntr[i];
+          xin[i] = x[i];
+        }
+        it = 0;
+        phase = PH_NR;
+      }
+      GrpW<G>::sync();
     }
-    c.C1 = d.C1;
-    Grp<G>::sync(c.mask);
-    int it = 0, meth = 0;
-    int ok = dc_solve<V>(c, o.gmin, true, time + tstep, o.transient_max_nr_iter, &it, &meth);
-    n_solves++; n_nr += it;
-    if (ok) {
-      double old_step = tstep;
-      if (use_step_control && d.has_pred) {
-        // transient.py:356-365: coeff = min(2, min_i ((aerr + rerr |x_prev_i|) / lte_i)^(1/(order+1)));
-        // the power is monotone, so the minimum ratio is found first and raised once.
-        double rmin = INFINITY;
-        const double sc = d.x_lte / (d.pred_lte - d.x_lte);
+    // ===== (3) ONE Newton iteration of every group (dc_analysis.mdn_solver) =====
+    // groups that are not iterating (done / padding) compute along on their frozen state and
+    // commit nothing
+    int r = 2;   // 2 = keep iterating, 1 converged, 0 not converged, -1 singular
+    {
+      const bool m = phase == PH_NR;
+      if (m) it++;
+      if (p.ndev) { eval_devices(c, x); GrpW<G>::sync(); }
+      const int lin_ok = assemble_solve<V, true>(c);
+      // get_td (dc_analysis.py:884-946)
+      double td = 1.0;
+      if (o.nr_damp_first_iters) td = it < 10 ? 1e-2 : (it < 20 ? 0.1 : 1.0);
+      if (o.nl_voltages_lock && p.nlock) {
+        double dmax = 0.0;
+        AHK_LANES(k, p.nlock) {
+          int n1 = p.lock[2 * k], n2 = p.lock[2 * k + 1];
+          double dd;
+          if (n1 != 0) dd = n2 != 0 ? fabs(dx[n1 - 1] - dx[n2 - 1]) : fabs(dx[n1 - 1]);
+          else dd = fabs(dx[n2 != 0 ? n2 - 1 : n - 1]);   // dx[-1] quirk, dc_analysis.py:941
+          if (dd > dmax) dmax = dd;
+        }
+        dmax = Grp<G>::fmax_all(dmax, 0xffffffffu);
+        if (dmax > lim) td = fmin(td, fm::div(lim, dmax));
+      }
+      // x += td dx; convergence_check (utilities.py:392-549)
+      bool ok = true, finite = true;
+      if (m && lin_ok) {
+        AHK_LANES(i, n) {
+          const double di = dx[i];
+          const double xn = x[i] + td * di;
+          x[i] = xn;
+          if (!isfinite(xn)) finite = false;
+          const bool isv = i < p.nv1;
+          if (!(fabs(di) <= (isv ? o.vea : o.iea) + (isv ? o.ver : o.ier) * fabs(xn + di))) ok = false;
+          if (!(fabs(res[i]) <= (isv ? o.iea : o.vea))) ok = false;
+        }
+      }
+      const bool all_ok = GrpW<G>::all(ok), all_fin = GrpW<G>::all(finite);
+      if (m) {
+        if (!lin_ok) {            // LinAlgError: x as it was when mdn_solver was entered
+          c.singular = 1;
+          AHK_LANES(i, n) x[i] = xin[i];
+          r = -1;
+        } else if (!p.ndev || all_ok) r = 1;
+        else if (!all_fin) { it = MAXIT; r = 0; }   // NaN never converges
+        else if (it >= MAXIT) r = 0;
+      }
+      GrpW<G>::sync();
+    }
+    // ===== (4) mdn_solver returned: next homotopy stage, or dc_solve is finished =====
+    int ds = 2;   // dc_solve: 2 = still running, 1 = solved, 0 = failed
+    if (phase == PH_DSFAIL) ds = 0;
+    if (phase == PH_NR && r != 2) {
+      if (r >= 0) ds_iters += it;
+      if (r <= 0) {   // set_next_solve_method, dc_analysis.py:354-408
+        failed |= 1 << enabled;
+        enabled = -1;
+        for (int q = 0; q < 3; q++) if (!((failed >> q) & 1) && ((use >> q) & 1)) { enabled = q; break; }
+        if (enabled < 0) ds = 0; else phase = PH_SOLVE;
+      } else {
+        if (enabled == 2 && sidx != 9) { sidx++; phase = PH_SOLVE; }
+        else if (enabled == 1 && gidx != 9) { gidx++; phase = PH_SOLVE; }
+        else ds = 1;
+      }
+    }
+    // ===== (5) the step attempt is over: LTE step control, accept / reject / cut =====
+    if (warp_any(ds != 2)) {
+      const bool sd = ds != 2;
+      const bool lte_on = sd && ds == 1 && use_step_control && d.has_pred;
+      // transient.py:356-365: coeff = min(2, min_i ((aerr + rerr |x_prev_i|) / lte_i)^(1/(order+1)));
+      // the power is monotone, so the minimum ratio is found first and raised once.
+      double rmin = INFINITY;
+      if (lte_on) {
+        const double sc = fm::div(d.x_lte, d.pred_lte - d.x_lte);
         AHK_LANES(i, n) {
           double lte = fabs(sc * (pred[i] - x[i]));
           if (lte != 0) {
             double re = i < p.nv1 ? o.ver : o.ier;
-            double v = (o.vea + re * fabs(xacc[i])) / lte;
+            double v = fm::div(o.vea + re * fabs(xacc[i]), lte);
             if (v < rmin) rmin = v;
           }
         }
-        rmin = Grp<G>::fmin_all(rmin, c.mask);
-        double coeff = 2.0;
-        if (rmin < INFINITY) {
-          double v = pow(rmin, 1.0 / (order + 1));
-          if (v < coeff) coeff = v;
+      }
+      rmin = Grp<G>::fmin_all(rmin, 0xffffffffu);
+      bool stop = false;
+      if (sd) {
+        n_solves++; n_nr += ds_iters;
+        bool accept = false;
+        if (ds == 1) {
+          const double old_step = tstep;
+          bool reject = false;
+          if (lte_on) {
+            double coeff = 2.0;
+            if (rmin < INFINITY) {
+              double v = fm_pow(rmin, 1.0 / (order + 1));
+              if (v < coeff) coeff = v;
+            }
+            reject = o.transient_use_aposteriori_step_control &&
+                     coeff < o.transient_aposteriori_step_threshold;
+            tstep = tstep * coeff;
+            if (check_step(o, tstep, time, a.tstop, HMAX)) { status |= AHK_ST_HMIN; solved = 0; stop = true; }
+            else if (reject) n_rej++;
+          }
+          if (!stop && !reject) {
+            time = time + old_step;
+            have_x = 1;
+            iter_n++;
+            if (nrows >= a.max_rows) { status |= AHK_ST_ROWS_FULL; solved = 0; stop = true; }
+            else accept = true;
+          }
+          if (accept) {
+            // store the row, dxdt = C1*x + C0, push to the ring (transient.py:385-393)
+            h0 = (h0 + buflen - 1) % buflen;
+            double* hnew = hx + h0 * n;
+            AHK_LANES(i, n) {
+              double xi = x[i];
+              xacc[i] = xi;
+              hnew[i] = xi;
+              hdx[i] = d.C1 * xi + C0[i];
+              x_out[nrows * n + i] = xi;
+            }
+            if (c.sub == 0) { ht[h0] = time; t_out[nrows] = time; }
+            nrows++;
+            if (nh < buflen) nh++;
+            if (o.transient_max_time_iter && iter_n == o.transient_max_time_iter) { solved = 0; stop = true; }
+          }
+        } else {
+          if (use_step_control) {
+            tstep = tstep / 5.0;
+            if (check_step(o, tstep, time, a.tstop, HMAX)) { status |= AHK_ST_HMIN; solved = 0; stop = true; }
+            else n_cut++;
+          } else { status |= AHK_ST_NR_FAIL; solved = 0; stop = true; }
+          if (!stop && o.transient_max_time_iter && iter_n == o.transient_max_time_iter) { solved = 0; stop = true; }
         }
-        double new_step = tstep * coeff;
-        bool reject = o.transient_use_aposteriori_step_control &&
-                      coeff < o.transient_aposteriori_step_threshold;
-        tstep = new_step;
-        if (check_step(o, tstep, time, a.tstop, HMAX)) { status |= AHK_ST_HMIN; solved = 0; break; }
-        if (reject) { n_rej++; continue; }
+        phase = (stop || !(time < a.tstop)) ? PH_DONE : PH_STEP;
       }
-      time = time + old_step;
-      have_x = 1;
-      iter_n++;
-      if (nrows >= a.max_rows) { status |= AHK_ST_ROWS_FULL; solved = 0; break; }
-      // accept: store the row, dxdt = C1*x + C0, push to the ring (transient.py:385-393)
-      h0 = (h0 + buflen - 1) % buflen;
-      double* hnew = hx + h0 * n;
-      AHK_LANES(i, n) {
-        double xi = x[i];
-        xacc[i] = xi;
-        hnew[i] = xi;
-        hdx[i] = d.C1 * xi + C0[i];
-        x_out[nrows * n + i] = xi;
-      }
-      if (c.sub == 0) { ht[h0] = time; t_out[nrows] = time; }
-      nrows++;
-      if (nh < buflen) nh++;
-      Grp<G>::sync(c.mask);
-    } else {
-      if (use_step_control) {
-        tstep = tstep / 5.0;
-        if (check_step(o, tstep, time, a.tstop, HMAX)) { status |= AHK_ST_HMIN; solved = 0; break; }
-        n_cut++;
-      } else { status |= AHK_ST_NR_FAIL; solved = 0; break; }
+      GrpW<G>::sync();
     }
-    if (o.transient_max_time_iter && iter_n == o.transient_max_time_iter) { solved = 0; break; }
   }
   if (solved) status |= AHK_ST_OK;
   if (c.singular) status |= AHK_ST_SINGULAR;
-  if (c.sub == 0) {
+  if (live && c.sub == 0) {
     a.rows[c.inst] = (int)nrows;
     a.counters[4 * c.inst + 0] = n_solves; a.counters[4 * c.inst + 1] = n_nr;
     a.counters[4 * c.inst + 2] = n_rej; a.counters[4 * c.inst + 3] = n_cut;

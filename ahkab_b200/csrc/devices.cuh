@@ -33,6 +33,8 @@
 #define AHK_MEM inline
 #endif
 
+#include "fastmath.cuh"
+
 namespace ahk {
 
 // constants.py:30-53 — k*T/e at T = Tref = 300 K
@@ -41,7 +43,7 @@ namespace ahk {
 #define AHK_ESI 104.5e-12
 
 // ---- diode -----------------------------------------------------------------
-AHK_DEV double safe_exp(double x) { return x < 70 ? exp(x) : exp(70.0) + 10 * x; }
+AHK_DEV double safe_exp(double x) { return x < 70 ? fm::exp(x) : 2.5154386709191670e30 + 10 * x; }   // exp(70) = 2.515...e30
 
 struct DiodeP { double IS, N, NBV, ISR, NR, RS, BV, IKF, VT, AREA; };
 
@@ -166,17 +168,17 @@ AHK_DEV double ekv_q(double v) {
     E = 0.5 * v;
   } else {
     y = v < -2.0 ? v : -0.85 + v * (0.555 - 0.065 * v);
-    E = exp(y);
+    E = fm::exp(y);
   }
   {
     double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
-    double d = 2.0 * f * f1 / (2.0 * f1 * f1 - f * 2.0 * E);
+    double d = fm::div(2.0 * f * f1, 2.0 * f1 * f1 - f * 2.0 * E);
     y -= d;
-    E = exp(y);
+    E = fm::exp(y);
   }
   {
     double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
-    double d = 2.0 * f * f1 / (2.0 * f1 * f1 - f * 2.0 * E);
+    double d = fm::div(2.0 * f * f1, 2.0 * f1 * f1 - f * 2.0 * E);
     E = E * (1.0 - d * (1.0 - 0.5 * d));
   }
   return E;
@@ -188,7 +190,7 @@ AHK_DEV double ekv_vp(const double* k, double VG) {   // ekv.py:524-540
   double arg = VG - k[EK_VTO] + t * t;
   double VP = -k[EK_PHI];
   if (VGeff > 0 && arg > 0) {
-    VP = VG - k[EK_VTO] - k[EK_GAMMA] * (sqrt(arg) - t);
+    VP = VG - k[EK_VTO] - k[EK_GAMMA] * (fm::sqrt(arg) - t);
     if (isnan(VP)) VP = 0;
   }
   return VP;
@@ -203,7 +205,7 @@ AHK_DEVFN void ekv_eval(const double* k, int NP, double vd, double vg, double vs
   int CS = +1;
   if (VS > VD) { double t = VD; VD = VS; VS = t; CS = -1; }
   const double VP = ekv_vp(k, VG);
-  const double nq = 1.0 + .5 * k[EK_GAMMA] * ahk_rsqrt(k[EK_PHI] + .5 * VP);
+  const double nq = 1.0 + .5 * k[EK_GAMMA] * fm::rsqrt(k[EK_PHI] + .5 * VP);
   const double Gs = 2 * nq * Ut * k[EK_KWL];        // ekv.py:509-522
   const double Is = Gs * Ut;
   double qf = ekv_q((VP - VS) * iUt);
@@ -211,32 +213,116 @@ AHK_DEVFN void ekv_eval(const double* k, int NP, double vd, double vg, double vs
   if (!(ifn > 10 * AHK_EPS)) { ifn = 10 * AHK_EPS; qf = 10 * AHK_EPS; }   // ekv.py:726
   // get_leq_virp, ekv.py:629-670 (Vds = half the drain-source voltage: quirk 11)
   const double Vc = k[EK_VC];
-  const double sif = sqrt(ifn);
-  const double Vdss = Vc * (sqrt(.25 + k[EK_UTVC] * sif) - .5);
-  const double Vdssp = Vc * (sqrt(.25 + k[EK_UTVC] * (sif - .75 * log(ifn))) - .5) + k[EK_LVC];
+  const double sif = fm::sqrt(ifn);
+  const double Vdss = Vc * (fm::sqrt(.25 + k[EK_UTVC] * sif) - .5);
+  const double Vdssp = Vc * (fm::sqrt(.25 + k[EK_UTVC] * (sif - .75 * fm::log(ifn))) - .5) + k[EK_LVC];
   const double vser_1 = sif - Vdss * iUt;
   const double Vds = (VD - VS) * .5;
   const double dv2 = 16.0 * Ut * Ut * (k[EK_LAMBDA] * vser_1 + 1.0 / 64);
-  const double Vip = sqrt(Vdss * Vdss + dv2) - sqrt((Vds - Vdss) * (Vds - Vdss) + dv2);
-  const double delta_l = k[EK_LLC] * log(1 + (Vds - Vip) * k[EK_ILCU]);
+  const double Vip = fm::sqrt(Vdss * Vdss + dv2) - fm::sqrt((Vds - Vdss) * (Vds - Vdss) + dv2);
+  const double delta_l = k[EK_LLC] * fm::log(1 + (Vds - Vip) * k[EK_ILCU]);
   const double Lp = k[EK_NL] - delta_l + (Vds + Vip) * k[EK_IUCRIT];
-  const double Leq = .5 * (Lp + sqrt(Lp * Lp + k[EK_LMIN2]));
-  const double v_irn = (VP - Vds - VS - sqrt(Vdssp * Vdssp + dv2) +
-                        sqrt((Vds - Vdssp) * (Vds - Vdssp) + dv2)) * iUt;
+  const double Leq = .5 * (Lp + fm::sqrt(Lp * Lp + k[EK_LMIN2]));
+  const double v_irn = (VP - Vds - VS - fm::sqrt(Vdssp * Vdssp + dv2) +
+                        fm::sqrt((Vds - Vdssp) * (Vds - Vdssp) + dv2)) * iUt;
   double qr = ekv_q(v_irn);
   double irn = qr * qr + qr;
   if (!(irn > 10 * AHK_EPS)) { irn = 10 * AHK_EPS; qr = 10 * AHK_EPS; }
-  out[0] = CS * k[EK_PREF] / Leq * Is * (ifn - irn);       // ekv.py:601-602
+  out[0] = fm::div(CS * k[EK_PREF], Leq) * Is * (ifn - irn);       // ekv.py:601-602
   double gmd = CS == 1 ? Gs * qr : Gs * qf;                 // ekv.py:672-692
   double gms = CS == 1 ? -1.0 * Gs * qf : -Gs * qr;
   // get_gmg: nv from the UN-flipped vg (ekv.py:697, quirk 11)
   const double VPu = NP == 1 ? VP : ekv_vp(k, vg);
-  const double nv = 1.0 + .5 * k[EK_GAMMA] * ahk_rsqrt(k[EK_PHI] + VPu + 1e-12);
-  double gmg = CS * Gs * (qf - qr) / nv;
+  const double nv = 1.0 + .5 * k[EK_GAMMA] * fm::rsqrt(k[EK_PHI] + VPu + 1e-12);
+  double gmg = fm::div(CS * Gs * (qf - qr), nv);
   if (gmd == 0) gmd = gmin * 2.0;  // ekv.py:331-336
   if (gmg == 0) gmg = gmin * 2.0;
   if (gms == 0) gms = -gmin * 2.0;
   out[1] = gmd; out[2] = gmg; out[3] = gms;
+}
+
+// K devices at once, statement by statement ("vertical" form of ekv_eval): the K evaluations
+// are independent, so writing each step for all of them back to back hands the instruction
+// scheduler K interleaved dependency chains — the transcendental sequences of one evaluation
+// (log, sqrt, exp, reciprocals: long serial FP64 chains) hide behind those of the others.
+// One lane per instance has 1 warp per scheduler at the BASELINE batch sizes; without this
+// the FP64 pipe idles most of the time.  Same arithmetic, same order per device as ekv_eval.
+// kk[j] = constant block, NP[j] = +-1, (vd, vg, vs)[j] = port voltages w.r.t. bulk.
+template <int K>
+AHK_DEVFN void ekv_eval_v(const double* const (&kk)[K], const int (&NP)[K], const double (&vd)[K],
+                          const double (&vg)[K], const double (&vs)[K], double gmin,
+                          double (&o0)[K], double (&o1)[K], double (&o2)[K], double (&o3)[K]) {
+  const double Ut = AHK_VTH, iUt = 1.0 / AHK_VTH;
+  double VD[K], VG[K], VS[K], VP[K], VPu[K], nq[K], Gs[K], qf[K], ifn[K], sif[K], Vdss[K], Vdssp[K],
+      Vds[K], dv2[K], Vip[K], Leq[K], qr[K], irn[K];
+  int CS[K];
+#define AHK_V for (int j = 0; j < K; j++)
+#pragma unroll
+  AHK_V {
+    VD[j] = vd[j] * NP[j]; VG[j] = vg[j] * NP[j]; VS[j] = vs[j] * NP[j];
+    CS[j] = +1;
+    if (VS[j] > VD[j]) { double t = VD[j]; VD[j] = VS[j]; VS[j] = t; CS[j] = -1; }
+  }
+#pragma unroll
+  AHK_V VP[j] = ekv_vp(kk[j], VG[j]);
+#pragma unroll
+  AHK_V VPu[j] = NP[j] == 1 ? VP[j] : ekv_vp(kk[j], vg[j]);   // get_gmg: nv from the UN-flipped vg
+#pragma unroll
+  AHK_V nq[j] = 1.0 + .5 * kk[j][EK_GAMMA] * fm::rsqrt(kk[j][EK_PHI] + .5 * VP[j]);
+#pragma unroll
+  AHK_V Gs[j] = 2 * nq[j] * Ut * kk[j][EK_KWL];
+#pragma unroll
+  AHK_V qf[j] = ekv_q((VP[j] - VS[j]) * iUt);
+#pragma unroll
+  AHK_V {
+    ifn[j] = qf[j] * qf[j] + qf[j];
+    if (!(ifn[j] > 10 * AHK_EPS)) { ifn[j] = 10 * AHK_EPS; qf[j] = 10 * AHK_EPS; }
+  }
+#pragma unroll
+  AHK_V sif[j] = fm::sqrt(ifn[j]);
+#pragma unroll
+  AHK_V Vdss[j] = kk[j][EK_VC] * (fm::sqrt(.25 + kk[j][EK_UTVC] * sif[j]) - .5);
+#pragma unroll
+  AHK_V Vdssp[j] = kk[j][EK_VC] * (fm::sqrt(.25 + kk[j][EK_UTVC] * (sif[j] - .75 * fm::log(ifn[j]))) - .5) + kk[j][EK_LVC];
+#pragma unroll
+  AHK_V {
+    const double vser_1 = sif[j] - Vdss[j] * iUt;
+    Vds[j] = (VD[j] - VS[j]) * .5;
+    dv2[j] = 16.0 * Ut * Ut * (kk[j][EK_LAMBDA] * vser_1 + 1.0 / 64);
+  }
+#pragma unroll
+  AHK_V Vip[j] = fm::sqrt(Vdss[j] * Vdss[j] + dv2[j]) - fm::sqrt((Vds[j] - Vdss[j]) * (Vds[j] - Vdss[j]) + dv2[j]);
+#pragma unroll
+  AHK_V {
+    const double delta_l = kk[j][EK_LLC] * fm::log(1 + (Vds[j] - Vip[j]) * kk[j][EK_ILCU]);
+    const double Lp = kk[j][EK_NL] - delta_l + (Vds[j] + Vip[j]) * kk[j][EK_IUCRIT];
+    Leq[j] = .5 * (Lp + fm::sqrt(Lp * Lp + kk[j][EK_LMIN2]));
+  }
+#pragma unroll
+  AHK_V {
+    const double v_irn = (VP[j] - Vds[j] - VS[j] - fm::sqrt(Vdssp[j] * Vdssp[j] + dv2[j]) +
+                          fm::sqrt((Vds[j] - Vdssp[j]) * (Vds[j] - Vdssp[j]) + dv2[j])) * iUt;
+    qr[j] = ekv_q(v_irn);
+  }
+#pragma unroll
+  AHK_V {
+    irn[j] = qr[j] * qr[j] + qr[j];
+    if (!(irn[j] > 10 * AHK_EPS)) { irn[j] = 10 * AHK_EPS; qr[j] = 10 * AHK_EPS; }
+  }
+#pragma unroll
+  AHK_V {
+    const double Is = Gs[j] * Ut;
+    o0[j] = fm::div(CS[j] * kk[j][EK_PREF], Leq[j]) * Is * (ifn[j] - irn[j]);
+    double gmd = CS[j] == 1 ? Gs[j] * qr[j] : Gs[j] * qf[j];
+    double gms = CS[j] == 1 ? -1.0 * Gs[j] * qf[j] : -Gs[j] * qr[j];
+    const double nv = 1.0 + .5 * kk[j][EK_GAMMA] * fm::rsqrt(kk[j][EK_PHI] + VPu[j] + 1e-12);
+    double gmg = fm::div(CS[j] * Gs[j] * (qf[j] - qr[j]), nv);
+    if (gmd == 0) gmd = gmin * 2.0;
+    if (gmg == 0) gmg = gmin * 2.0;
+    if (gms == 0) gms = -gmin * 2.0;
+    o1[j] = gmd; o2[j] = gmg; o3[j] = gms;
+  }
+#undef AHK_V
 }
 
 // ---- square-law MOS ----------------------------------------------------------

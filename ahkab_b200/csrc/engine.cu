@@ -117,6 +117,8 @@ struct ahk_engine {
   int jit_mode = 2;
   long long jit_min_batch = 4096;
   int jit_R = 0, jit_G = 0;   // forced (rows per lane, lanes per instance) of the specialised kernels, 0 = heuristic
+  int jit_ilp = 0;            // devices a lane evaluates interleaved (0 = heuristic)
+  int jit_threads = 0, jit_minb = 0;   // forced block size / resident blocks per SM of the specialised kernels
   // variant / layout / launch shape / kernel of recent small-circuit calls, so that a repeated
   // call (the common case: same batch size again and again) goes straight to the launch
   struct Prepared { int vid; Layout Ly; Launch L; jit::Kernel* jk; };
@@ -340,6 +342,7 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
 
 namespace {
 
+void drop_stale(ahk_engine* e);
 
 int upload_program(ahk_engine* e) {
   HostProg& H = e->H;
@@ -396,6 +399,7 @@ int set_batch(ahk_engine* e, const ahk_batch* b, cudaStream_t s) {
   e->cur_slots = slots;
   e->slots_valid = true;
   e->slots_epoch++;
+  drop_stale(e);
   return 0;
 }
 
@@ -517,6 +521,19 @@ KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
   return k;
 }
 
+// Devices one lane evaluates interleaved in a specialised kernel (ekv_eval_v): as many as the
+// lane owns, at most 3 (register budget) — the interleaved chains are what keeps the FP64 pipe
+// busy at one or two warps per scheduler.  AHK_JIT_ILP / ahk_set_jit_tuning force it.
+int jit_ilp_for(const ahk_engine* e, const VarInfo& v, int mode) {
+  if (mode == JIT_MODE_AC) return 1;
+  int ilp = e->jit_ilp;
+  static const int env = getenv("AHK_JIT_ILP") ? atoi(getenv("AHK_JIT_ILP")) : 0;   // tuning
+  if (env > 0) ilp = env;
+  const int per_lane = ((int)e->H.dev.size() + v.G - 1) / std::max(1, v.G);
+  if (ilp <= 0) ilp = std::min(3, per_lane);
+  return std::max(1, std::min(std::min(ilp, 4), std::max(1, per_lane)));
+}
+
 // The specialised kernel for (analysis, variant, launch shape, options, varied slots) —
 // compiled on first use, cached in the engine.  *out = nullptr: use the interpreted kernel.
 int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, const Layout& Ly,
@@ -526,11 +543,14 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
   if (e->jit_mode == 0 || v.NC == 0) return 0;   // the generic shared-memory fallback is not specialised
   if (e->jit_mode == 2 && B < e->jit_min_batch) return 0;
   const bool must = e->jit_mode == 1;
-  std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, e->slots_epoch, e->opts_epoch};
+  const int ilp = jit_ilp_for(e, v, mode);
+  std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, ilp, e->slots_epoch, e->opts_epoch};
   auto it = e->jit_cache.find(key);
   if (it == e->jit_cache.end()) {
     jit::Kernel k;
-    JitCfg cfg = {v.NC, v.R, v.G, L.threads, std::max(1, std::min(32, reg_blocks * 128 / L.threads)), mode, method, usc};
+    // reg_blocks > 0: resident 128-thread blocks the registers are capped for; < 0: -min_blocks of this block size
+    const int minb = reg_blocks < 0 ? -reg_blocks : std::max(1, std::min(32, reg_blocks * 128 / L.threads));
+    JitCfg cfg = {v.NC, v.R, v.G, L.threads, minb, mode, method, usc, ilp};
     std::string err;
     const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg, ac);
     bool cached = false;
@@ -568,7 +588,7 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
 int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
                   Launch* L, jit::Kernel** jk) {
   const std::vector<long long> key = {B, mode, method, usc, e->slots_epoch, e->opts_epoch, e->jit_mode,
-                                      e->jit_min_batch, e->force_vid, e->group, e->jit_R, e->jit_G};
+                                      e->jit_min_batch, e->force_vid, e->group, e->jit_R, e->jit_G, e->jit_ilp, e->jit_threads, e->jit_minb};
   auto it = e->prepared.find(key);
   if (it != e->prepared.end()) {
     *vid_out = it->second.vid; *Ly = it->second.Ly; *L = it->second.L; *jk = it->second.jk;
@@ -605,7 +625,22 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
     *vid_out = vid;
     *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, slim && v.NC > 0);
     static const int minb_env = getenv("AHK_JIT_MINB") ? atoi(getenv("AHK_JIT_MINB")) : 0;   // tuning
-    const int rb = (jit && minb_env > 0) ? minb_env : real_min_blocks(v.NC);
+    int rb = (jit && minb_env > 0) ? minb_env : real_min_blocks(v.NC);
+    if (jit && (e->jit_threads > 0 || e->jit_minb > 0)) {
+      // forced launch shape (ahk_set_jit_tuning): `threads` per block, registers capped for
+      // `min_blocks` resident blocks; rb carries min_blocks * threads / 128 to get_jit
+      const int threads = e->jit_threads > 0 ? e->jit_threads : 128;
+      if (threads < v.G) return fail("ahk_set_jit_tuning: block smaller than one instance group");
+      const int ipb = threads / v.G;
+      L->vid = vid; L->G = v.G; L->threads = threads;
+      L->smem = (size_t)ipb * Ly->stride * sizeof(double);
+      L->blocks = (int)((B + ipb - 1) / ipb);
+      if (L->smem > e->smem_max) return fail("forced block size needs too much shared memory");
+      const int minb = e->jit_minb > 0 ? e->jit_minb : std::max(1, real_min_blocks(v.NC) * 128 / threads);
+      if (get_jit(e, B, mode, vid, v, *Ly, *L, -minb, method, usc, jk)) return -1;
+      if (*jk) return 0;
+      continue;
+    }
     if (plan(e, B, vid, v, Ly->stride, *L, rb, nullptr)) return -1;
     if (!jit || v.NC == 0) return 0;
     if (get_jit(e, B, mode, vid, v, *Ly, *L, rb, method, usc, jk)) return -1;
@@ -636,6 +671,28 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   k.b = make_base(e, batch, Ly);
   k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
   return launched(launch_dc(k, L, s));
+}
+
+// The varied slots or the options changed: plans and specialised kernels compiled for an older
+// epoch can never be used again — unload their modules (device memory) and forget them.
+// key layout of jit_cache: {..., slots_epoch, opts_epoch} are the last two entries.
+void drop_stale(ahk_engine* e) {
+  e->prepared.clear();
+  if (e->hp.graph_exec) {      // the captured ahk_op_host sequence launches kernels of the old modules
+    cudaDeviceSynchronize();
+    cudaGraphExecDestroy(e->hp.graph_exec);
+    e->hp.graph_exec = nullptr;
+    e->hp.graph_key.clear(); e->hp.last_key.clear();
+  }
+  for (auto it = e->jit_cache.begin(); it != e->jit_cache.end();) {
+    const std::vector<long long>& k = it->first;
+    const bool stale = k.size() < 2 || k[k.size() - 2] != e->slots_epoch || k[k.size() - 1] != e->opts_epoch;
+    if (stale) {
+      cudaDeviceSynchronize();   // a launch of the old module may still be in flight
+      jit::unload(it->second);
+      it = e->jit_cache.erase(it);
+    } else ++it;
+  }
 }
 
 }  // namespace
@@ -693,8 +750,12 @@ int ahk_size(const ahk_engine* e) { return e ? e->n : -1; }
 
 int ahk_set_options(ahk_engine* e, const ahk_options* opts) {
   if (!e || !opts) return fail("null argument");
+  // unchanged options keep every cached plan, specialised kernel, captured graph and
+  // elimination schedule valid: callers (analyses.get_engine) set them before every run
+  if (std::memcmp(&e->o, opts, sizeof(Opts)) == 0) return 0;
   std::memcpy(&e->o, opts, sizeof(Opts));
   e->opts_epoch++;
+  drop_stale(e);
   return 0;
 }
 
@@ -717,19 +778,36 @@ int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes) {
   return 0;
 }
 
+int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks) {
+  if (!e) return fail("null engine");
+  if (ilp < 0 || ilp > 4) return fail("ahk_set_jit_tuning: ilp must be 0..4");
+  if (threads < 0 || threads > 1024 || threads % 32) return fail("ahk_set_jit_tuning: threads must be a multiple of 32");
+  if (min_blocks < 0 || min_blocks > 32) return fail("ahk_set_jit_tuning: min_blocks must be 0..32");
+  e->jit_ilp = ilp; e->jit_threads = threads; e->jit_minb = min_blocks;
+  return 0;
+}
+
 int64_t ahk_jit_launch_count(void) { return g_jit_launches.load(); }
 int64_t ahk_jit_build_count(void) { return g_jit_builds.load(); }
 
 int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary, const int32_t* vary_slots,
                     int kind, int method, int use_step_control, int variant_id, int64_t* cubin_bytes) {
+  // variant_id >= 1000 (OP / transient only): free shape, 1000 + rows_per_lane * 64 + lanes, compiled
+  // with exactly n + 1 columns like the engine does for ahk_set_jit_shape
+  const bool free_shape = variant_id >= 1000 && kind != 2;
   if (!circ || !opts || kind < 0 || kind > 2 || variant_id < 2 ||
-      variant_id >= (kind == 2 ? AHK_N_AC_VARIANTS : AHK_N_REAL_VARIANTS))
+      (!free_shape && variant_id >= (kind == 2 ? AHK_N_AC_VARIANTS : AHK_N_REAL_VARIANTS)))
     return fail("ahk_jit_compile: bad argument");
   try {
     HostProg H;
     build_program(circ, H);
     set_vary_slots(H, n_vary, vary_slots);
-    const VarInfo& v = (kind == 2 ? ac_variants() : real_variants())[variant_id];
+    VarInfo v;
+    if (free_shape) {
+      v = VarInfo{H.hdr.n + 1, (variant_id - 1000) / 64, (variant_id - 1000) % 64};
+      if (v.G < 1 || (v.G & (v.G - 1)) || v.G > 32 || v.R < 1 || v.R * v.G < H.hdr.n || H.hdr.n + 1 > 32)
+        return fail("ahk_jit_compile: bad free shape");
+    } else v = (kind == 2 ? ac_variants() : real_variants())[variant_id];
     if (!fits(v, H.hdr.n)) return fail("variant does not fit this circuit");
     Opts o; std::memcpy(&o, opts, sizeof(Opts));
     std::string spec;
@@ -742,6 +820,9 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
       const int mode = kind ? MODE_TRAN : MODE_OP;
       Layout Ly = make_layout(H, mode, method, use_step_control, v.G, v.NC, v.R, true);
       JitCfg cfg = {v.NC, v.R, v.G, 128, real_min_blocks(v.NC), mode, method, use_step_control ? 1 : 0};
+      if (const char* f = getenv("AHK_JIT_ILP")) cfg.ilp = std::max(1, std::min(4, atoi(f)));        // tuning
+      if (const char* f = getenv("AHK_JIT_THREADS")) cfg.threads = std::max(32, atoi(f));            // tuning
+      if (const char* f = getenv("AHK_JIT_MINB")) cfg.min_blocks = std::max(1, atoi(f));             // tuning
       spec = jit_spec_source(H, o, Ly, cfg);
     }
     std::string err;

@@ -47,16 +47,18 @@ AHK_DEV void run_dc(Ctx& c, const DcArgs& a) {
 }
 
 // transient.transient_analysis for one instance
+// (warp-uniform: EVERY lane of the warp calls it — `live` = false for the padding groups of a
+// partial last warp, whose c.inst names some valid instance to read parameters from)
 template <class V>
-AHK_DEV void run_tran(Ctx& c, const double* x0, const TranArgs& a, int* status) {
+AHK_DEV void run_tran(Ctx& c, const double* x0, const TranArgs& a, int* status, bool live = true) {
   const int n = c.p->n, G = V::G;
   init_ctx<V>(c);
   build_values<V>(c, true);
   double* x = c.x();
   for (int i = c.sub; i < n; i += G) x[i] = x0 ? x0[c.inst * n + i] : 0.0;
   Grp<V::G>::sync(c.mask);
-  int st = tran_analysis<V>(c, a);
-  if (c.sub == 0) status[c.inst] = st;
+  int st = tran_analysis<V>(c, a, live);
+  if (live && c.sub == 0) status[c.inst] = st;
 }
 
 // kernel parameters of the circuit-specialised kernels (jit_kernels.cuh; filled by
@@ -83,6 +85,26 @@ __device__ __forceinline__ bool make_ctx(Ctx& c, const Prog* p, const Opts* o, c
   c.G = G;
   c.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   return true;
+}
+
+// Context of a WARP-UNIFORM kernel (flat transient loop): no lane leaves — the padding groups
+// of the last block run along on the last instance's parameters with *live = false — and the
+// group's lane mask is the literal full mask, so that every shuffle / barrier of the solve
+// compiles to its unguarded form.  The launch must use whole warps (blockDim % 32 == 0).
+template <int G>
+__device__ __forceinline__ void make_ctx_uniform(Ctx& c, const Prog* p, const Opts* o, const Layout* L,
+                                                 int stride, const double* vary, long long B, bool& live) {
+  extern __shared__ __align__(16) double smem[];
+  const int gi = threadIdx.x / G;
+  const int ipb = blockDim.x / G;
+  const long long unit = (long long)blockIdx.x * ipb + gi;
+  live = unit < B;
+  c.p = p; c.o = o; c.L = L;
+  c.sm = smem + (size_t)gi * stride;
+  c.vary = vary; c.B = B; c.inst = live ? unit : B - 1;
+  c.sub = threadIdx.x % G;
+  c.G = G;
+  c.mask = 0xffffffffu;
 }
 
 #endif

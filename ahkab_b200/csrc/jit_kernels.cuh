@@ -46,9 +46,9 @@ ahk_jit_ac(const __grid_constant__ KAcJ k) {   // unit = (instance, frequency ch
 #else
 extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_tran(const __grid_constant__ KTranJ k) {
-  Ctx c; long long u;
-  if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
-  run_tran<JitVar>(c, k.x0, k.a, k.status);
+  Ctx c; bool live;
+  make_ctx_uniform<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, live);
+  run_tran<JitVar>(c, k.x0, k.a, k.status, live);
 }
 #endif
 #endif

@@ -6,9 +6,9 @@ namespace ahk {
 
 template <class V>
 __global__ void __launch_bounds__(128, (V::NC <= 12) ? AHK_MINB : (V::NC <= 16 ? 3 : 2)) k_tran(const __grid_constant__ KTran k) {
-  Ctx c; long long u;
-  if (!make_ctx<V::G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, k.b.B, u)) return;
-  run_tran<V>(c, k.x0, k.a, k.status);
+  Ctx c; bool live;
+  make_ctx_uniform<V::G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, live);
+  run_tran<V>(c, k.x0, k.a, k.status, live);
 }
 
 int launch_tran(const KTran& k, const Launch& L, cudaStream_t s) {

@@ -84,7 +84,7 @@ struct Layout {     // offsets in doubles inside one instance's slice
   int Pv;           // staged parameter values [nparams]
   int dcon;         // per-device constants [ndev][EK_NCONST]
   int pvb;          // pivot-row broadcast buffers [2][NC]
-  int gsc;          // scratch of the GEAR coefficient generation [32]
+  int xin;          // x at the entry of mdn_solver [n] (restored when the matrix turns out singular)
   int buflen;
   int stride;       // doubles per instance (padded: stride % 16 == (G*RS) % 16)
 };

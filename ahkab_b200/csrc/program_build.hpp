@@ -391,7 +391,7 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   L.bytes = take(NC > 0 ? 0 : 16);
   L.Pv = take(h.npersist); L.dcon = take(H.ncon);
   L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);
-  L.gsc = take(mode == MODE_TRAN && method >= AHK_GEAR1 ? 32 : 0);
+  L.xin = take(n);
   L.buflen = 1;
   if (mode == MODE_TRAN) {
     int order, max_x, max_dx, pmax_x;

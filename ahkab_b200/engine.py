@@ -70,17 +70,31 @@ class Engine(object):
     def set_vary(self, vary, non_blocking=True):
         """Upload per-instance values [n_vary][B] (numpy, or a pinned / device
         torch tensor).  This is the H2D copy of an end-to-end step."""
+        staged = None
         if isinstance(vary, np.ndarray):
-            if self._vary_host is None or tuple(self._vary_host.shape) != vary.shape:
-                self._vary_host = torch.empty(vary.shape, dtype=torch.float64,
-                                              pin_memory=True)
-            self._vary_host.numpy()[...] = vary
-            vary = self._vary_host
+            # two pinned staging buffers used in turn, each guarded by an event recorded
+            # after its H2D copy: a buffer is rewritten only once the copy that read it
+            # last has completed (queued set_vary / op() loops stay correct)
+            st = getattr(self, '_stage', None)
+            if st is None or tuple(st[0][0].shape) != vary.shape:
+                st = [[torch.empty(vary.shape, dtype=torch.float64, pin_memory=True), None]
+                      for _ in range(2)]
+                self._stage, self._stage_i = st, 0
+            self._stage_i ^= 1
+            staged = st[self._stage_i]
+            if staged[1] is not None:
+                staged[1].synchronize()
+            staged[0].numpy()[...] = vary
+            vary = self._vary_host = staged[0]
         if vary.device.type != 'cuda':
             if self.vary is None or self.vary.shape != vary.shape:
                 self.vary = torch.empty(vary.shape, dtype=torch.float64,
                                         device=self.device)
             self.vary.copy_(vary, non_blocking=non_blocking)
+            if staged is not None:
+                with torch.cuda.device(self.device):
+                    staged[1] = torch.cuda.Event()
+                    staged[1].record(torch.cuda.current_stream(self.device))
         else:
             self.vary = vary.contiguous()
         if self.vary.numel():
@@ -117,6 +131,13 @@ class Engine(object):
         """Shape of the specialised OP / DC / transient kernels (ahk_set_jit_shape);
         (0, 0) = the heuristic's variant."""
         if self.lib.ahk_set_jit_shape(self._h, int(rows_per_lane), int(lanes)) != 0:
+            raise EngineError(self._err())
+        return self
+
+    def set_jit_tuning(self, ilp=0, threads=0, min_blocks=0):
+        """ahk_set_jit_tuning: interleaved devices per lane, block size, resident blocks per
+        SM of the specialised kernels (0 = heuristic)."""
+        if self.lib.ahk_set_jit_tuning(self._h, int(ilp), int(threads), int(min_blocks)) != 0:
             raise EngineError(self._err())
         return self
 
@@ -203,7 +224,8 @@ class Engine(object):
         flows in chunks through copy-in / kernel / copy-out streams inside the library.
         vary_host: pinned [n_vary][B] float64 tensor (default: the batch the engine was
         built with).  Returns pinned host tensors; asynchronous on the current stream —
-        synchronise before reading them."""
+        synchronise before reading them.  The output buffers are cached per batch size and
+        reused by the next call (copy what must survive it)."""
         if vary_host is None:
             if self._vary_host is None:
                 self._vary_host = torch.empty(self.vary.shape, dtype=torch.float64, pin_memory=True)
@@ -327,12 +349,23 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(x=torch.view_as_complex(xo), status=status, omegas=om, _packed=pk['_packed'])
 
-    def to_host(self, raw, keys=None):
-        """Device->host read of a result dict into cached PINNED buffers
-        (asynchronous on the current stream; synchronise before reading).
-        This is the D2H copy of an end-to-end step."""
+    def to_host(self, raw, keys=None, fresh=False):
+        """Device->host read of a result dict into PINNED buffers (asynchronous on the
+        current stream; synchronise before reading).  This is the D2H copy of an
+        end-to-end step.
+
+        ALIASING: by default the pinned buffers are cached per result shape and REUSED —
+        the tensors returned by an earlier call change under the caller at the next call
+        with the same shapes (what a benchmark loop wants).  fresh=True allocates new
+        pinned buffers that belong to the caller."""
         if not hasattr(self, '_pinned'):
             self._pinned = {}
+        if fresh:
+            saved, self._pinned = self._pinned, {}
+            try:
+                return self.to_host(raw, keys)
+            finally:
+                self._pinned = saved
         out = {}
         if keys is None and raw.get('_packed') is not None:
             base, layout = raw['_packed']             # one copy for the whole result set

@@ -205,6 +205,10 @@ int ahk_set_jit(ahk_engine* e, int mode, int64_t min_batch);
  * lanes per instance (1,2,4,8,16,32; rows_per_lane * lanes >= n).  Being compiled on demand
  * they are not bound to the compiled variant table.  (0, 0) = the heuristic's variant. */
 int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes);
+/* Tuning of the specialised OP/DC/transient kernels: ilp = devices one lane evaluates
+ * interleaved (1..4, 0 = heuristic); threads = block size (multiple of 32, 0 = heuristic);
+ * min_blocks = resident blocks per SM the register allocation is capped for (0 = heuristic). */
+int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);
 int64_t ahk_jit_build_count(void);

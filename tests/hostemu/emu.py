@@ -107,17 +107,17 @@ class Emu(_oracle.Oracle):
         return dict(x=x, status=st)
 
     def jit_source(self, mode, method='TRAP', use_step_control=False, NC=4, R=3, G=1,
-                   threads=128, min_blocks=4):
+                   threads=128, min_blocks=4, ilp=1):
         """Text of the generated jit_spec.h (ahkab_b200/csrc/jit_gen.hpp) for this batch."""
         c6 = self._common()
         args = (c6[0], c6[1], c6[3], c6[4], C.c_int(mode),
                 C.c_int(_abi.METHODS[method.upper()]), C.c_int(bool(use_step_control)),
                 C.c_int(NC), C.c_int(R), C.c_int(G), C.c_int(threads), C.c_int(min_blocks))
-        n = lib().emu_jit_source(*args, None, C.c_int64(0))
+        n = lib().emu_jit_source(*args, None, C.c_int64(0), C.c_int(ilp))
         if n < 0:
             raise RuntimeError("emu_jit_source failed")
         buf = C.create_string_buffer(n + 1)
-        lib().emu_jit_source(*args, buf, C.c_int64(n + 1))
+        lib().emu_jit_source(*args, buf, C.c_int64(n + 1), C.c_int(ilp))
         return buf.value.decode()
 
     def big3_sweep(self, src_elem, sweep):

@@ -141,14 +141,14 @@ int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_
 // returns its length (the text is truncated to cap - 1 bytes), < 0 on error.
 int emu_jit_source(const ahk_circuit* c, const ahk_options* o, int n_vary, const int32_t* slots,
                    int mode, int method, int usc, int NC, int R, int G, int threads, int min_blocks,
-                   char* buf, int64_t cap) {
+                   char* buf, int64_t cap, int ilp) {
   try {
     HostProg H;
     build_program(c, H);
     set_vary_slots(H, n_vary, slots);
     Opts q; copy_opts(o, q);
     Layout L = make_layout(H, mode, method, usc, G, NC, R, true);
-    JitCfg cfg = {NC, R, G, threads, min_blocks, mode, method, usc};
+    JitCfg cfg = {NC, R, G, threads, min_blocks, mode, method, usc, ilp > 1 ? ilp : 1};
     std::string t = jit_spec_source(H, q, L, cfg);
     if (buf && cap > 0) {
       size_t m = std::min<size_t>(t.size(), (size_t)cap - 1);

@@ -64,11 +64,11 @@ def test_specialised_source_compiles_for_sm_100a(name, mk, tran, method, usc, vi
         assert nb.value > 10000      # an sm_100a cubin came back
 
 
-def _build_host_jit(spec, tag):
+def _build_host_jit(spec, tag, defs=()):
     d = tempfile.mkdtemp(prefix='ahk_jit_%s_' % tag)
     open(os.path.join(d, 'jit_spec.h'), 'w').write(spec)
     so = os.path.join(d, 'libemuj.so')
-    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I', d,
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I', d] + list(defs) + [
                            '-I', os.path.join(ROOT, 'ahkab_b200', 'csrc'), '-o', so,
                            os.path.join(ROOT, 'tests', 'hostemu', 'hostemu_jit.cpp'), '-lm'])
     return C.CDLL(so)
@@ -102,7 +102,11 @@ def test_specialised_host_build_is_bit_identical_op():
     assert np.array_equal(x, ref['x']) and np.array_equal(res, ref['resid'])
 
 
-def test_specialised_host_build_is_bit_identical_tran():
+@pytest.mark.parametrize('ilp,always', [(1, False), (3, False), (2, True)])
+def test_specialised_host_build_is_bit_identical_tran(ilp, always):
+    """ilp > 1: the devices go through the interleaved ekv_eval_v; always: every predicated
+    section of the flat transient loop runs in every pass (AHK_EMU_ALWAYS), as on a warp whose
+    other groups are in other phases — a badly predicated state update would change results."""
     import emu
     w = W.c4_ring3(B=2)
     e = _emu(w)
@@ -114,7 +118,8 @@ def test_specialised_host_build_is_bit_identical_tran():
         ref = e.tran(x0, tr['tstart'], tr['tstep'], tr['tstop'] / 10, 'GEAR2', True, rows_cap)
     finally:
         emu.set_variant(0)
-    lib = _build_host_jit(e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1), 'c4')
+    lib = _build_host_jit(e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1, ilp=ilp),
+                          'c4', ['-DAHK_EMU_ALWAYS'] if always else [])
     B, n = e.B, e.n
     t = np.full((B, rows_cap), np.nan); x = np.full((B, rows_cap, n), np.nan)
     rows = np.zeros(B, np.int32); cnt = np.zeros((B, 4), np.int32); st = np.zeros(B, np.int32)
