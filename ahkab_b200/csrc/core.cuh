@@ -54,10 +54,28 @@
 #define AHK_LANES(i, cnt) for (int i = c.sub; i < (cnt); i += G)
 #endif
 
+// "items of a small vector" in the flat transient kernel.  REPLICATED shapes (every lane of the
+// group holds all rows, see assemble_solve) also replicate the cheap vector work: every lane
+// handles EVERY item, so that after unrolling all indices are compile-time constants (no
+// constant-table look-ups by lane, no cross-lane reductions); the lanes store identical values.
+#define AHK_ITEMS(i, cnt)                                                                      \
+  AHK_UNROLL for (int i##_q = 0; i##_q < (REP ? (cnt) : ((cnt) + G - 1) / G); i##_q++)         \
+    if (const int i = REP ? i##_q : c.sub + i##_q * G; i < (cnt))
+
 namespace ahk {
 
 template <int NC_, int R_, int G_>
 struct Var { static const int NC = NC_, R = R_, G = G_; };
+
+// replicated shape: several lanes per instance, each holding all rows (specialised builds only)
+template <class V>
+struct RepOf {
+#ifdef AHK_JIT
+  static const bool value = V::G > 1 && V::NC > 0 && V::R >= Prog::n;
+#else
+  static const bool value = false;
+#endif
+};
 
 // ---- group primitives ---------------------------------------------------------
 #ifdef __CUDACC__
@@ -694,15 +712,11 @@ AHK_DEV int assemble_solve(Ctx& c) {
   if constexpr (V::NC > 0) {
     const int NC = V::NC, R = V::R;
     double a[R > 0 ? R : 1][NC > 0 ? NC : 1];
-#ifdef AHK_JIT
     // REPLICATED solve: several lanes per instance (they share the device evaluations), but
     // every lane holds ALL rows and runs the one-lane LU redundantly — for a small matrix
     // behind expensive devices that beats distributing rows (no pivot search across lanes, no
     // pivot-row broadcast, no idle lanes when n is not a multiple of G)
-    constexpr bool REP = G > 1 && R >= Prog::n;
-#else
-    constexpr bool REP = false;
-#endif
+    constexpr bool REP = RepOf<V>::value;
 #pragma unroll
     for (int s = 0; s < R; s++) {
       const int r = REP ? s : c.sub + G * s;
@@ -982,6 +996,7 @@ template <class V>
 AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h0, int buflen,
                     double step, bool predict, DfOut& d) {
   const int G = V::G;
+  constexpr bool REP = RepOf<V>::value;
   const int n = c.p->n;
   const double* ht = c.sm + c.L->ht;
   const double* hx = c.sm + c.L->hx;
@@ -1000,23 +1015,23 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
     if (predict && avail > 1) {
       const double* xm = HX(1);
       double dt = HT(0) - HT(1);
-      AHK_LANES(i, n) pred[i] = (x0[i] - xm[i]) / dt * step + x0[i];
+      AHK_ITEMS(i, n) pred[i] = (x0[i] - xm[i]) / dt * step + x0[i];
       d.pred_lte = -0.5 * step * (HT(0) + step - HT(1));
       d.has_pred = 1;
     }
-    AHK_LANES(i, n) C0[i] = -1. / step * x0[i];
+    AHK_ITEMS(i, n) C0[i] = -1. / step * x0[i];
   } else if (method == AHK_TRAP) {                   // trap.py:98-192
     d.C1 = 2.0 / step;
     d.x_lte = 1.0 / 12 * step * step * step;
     const double* x0 = HX(0);
-    AHK_LANES(i, n) C0[i] = -1.0 * (2.0 / step * x0[i] + hdx[i]);
+    AHK_ITEMS(i, n) C0[i] = -1.0 * (2.0 / step * x0[i] + hdx[i]);
     if (predict && nh > 2) {
       // quadratic through the last three points (trap.py:171-186 solves the same
       // interpolation with inv(A)); divided differences about t_n
       const double* xa = HX(1);
       const double* xb = HX(2);
       double t1 = HT(1) - HT(0), t2 = HT(2) - HT(0);
-      AHK_LANES(i, n) {
+      AHK_ITEMS(i, n) {
         double d1 = (xa[i] - x0[i]) / t1, d2 = (xb[i] - x0[i]) / t2;
         double a2 = (d1 - d2) / (t1 - t2), a1 = d1 - a2 * t1;
         pred[i] = a2 * step * step + a1 * step + x0[i];
@@ -1052,7 +1067,7 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
     for (int k = 1; k < order + 1; k++) xl += ipow(s[k], order + 1) * fm::div(-1.0 * gamma[k], g0);
     d.x_lte = (((order + 1) & 1) ? -1.0 : 1.0) * (1.0 / fact) * xl;
     d.C1 = g0;
-    AHK_LANES(i, n) {
+    AHK_ITEMS(i, n) {
       double a = 0.0;
       AHK_UNROLL
       for (int k = 0; k < order; k++) a = a + gamma[k + 1] * HX(k)[i];
@@ -1062,7 +1077,7 @@ AHK_DEV void get_df(Ctx& c, int method, int order, bool bootstrap, int nh, int h
       double pl = -1.0 / fact;
       AHK_UNROLL
       for (int k = 1; k < order + 2; k++) pl *= s[k];
-      AHK_LANES(i, n) {
+      AHK_ITEMS(i, n) {
         double a = 0.0;
         AHK_UNROLL
         for (int k = 1; k < order + 2; k++) a = a + alpha[k] * HX(k - 1)[i];
@@ -1103,6 +1118,7 @@ enum { PH_STEP = 0, PH_SOLVE = 1, PH_NR = 2, PH_DSFAIL = 3, PH_DONE = 4 };
 template <class V>
 AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
   const int G = V::G;
+  constexpr bool REP = RepOf<V>::value;
   const Prog& p = *c.p;
   const Opts& o = *c.o;
   const int n = p.n;
@@ -1143,7 +1159,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
   double tstep = a.tstep;
   build_N(c);
   int h0 = 0, nh = 1;
-  AHK_LANES(i, n) { hx[i] = x[i]; xs[i] = x[i]; xacc[i] = x[i]; }
+  AHK_ITEMS(i, n) { hx[i] = x[i]; xs[i] = x[i]; xacc[i] = x[i]; }
   if (c.sub == 0) ht[0] = a.tstart;
   GrpW<G>::sync();
   double time = a.tstart;
@@ -1170,14 +1186,14 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
       if (m) {
         // NR start point (transient.py:335-338)
         if (o.transient_prediction_as_x0 && use_step_control && d.has_pred) {
-          AHK_LANES(i, n) x[i] = pred[i];
+          AHK_ITEMS(i, n) x[i] = pred[i];
         } else if (have_x) {
-          AHK_LANES(i, n) x[i] = xacc[i];
+          AHK_ITEMS(i, n) x[i] = xacc[i];
         } else {
-          AHK_LANES(i, n) x[i] = xs[i];
+          AHK_ITEMS(i, n) x[i] = xs[i];
         }
         // Ntran = D . C0
-        AHK_LANES(r, n) {
+        AHK_ITEMS(r, n) {
           double s = 0.0;
           AHK_UNROLL
           for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) s += Dv[k] * C0[p.pcol[k]];
@@ -1186,7 +1202,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
         c.C1 = d.C1;
         // dc_solve entry (dc_analysis.py:222-257): N + Tt(t), first enabled method
         if (p.ntd) {
-          AHK_LANES(i, n) Nd[i] = Nc[i];
+          AHK_ITEMS(i, n) Nd[i] = Nc[i];
         }
       }
       if (p.ntd) {   // Tt(t), dc_analysis.py:222-237
@@ -1218,7 +1234,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
         if (enabled == 1) g = gmin_step_value(gidx);   // replaces Gmin (dc_analysis.py:262-269,452-455)
         else if (enabled == 2) f = source_step_value(sidx);
         c.gadd = g;     // Gmin and C1 D are added while assembling
-        AHK_LANES(i, n) {
+        AHK_ITEMS(i, n) {
           T[i] = (enabled == 2 ? f * Nd[i] : Nd[i]) + Ntr[i];
           xin[i] = x[i];
         }
@@ -1241,20 +1257,20 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
       if (o.nr_damp_first_iters) td = it < 10 ? 1e-2 : (it < 20 ? 0.1 : 1.0);
       if (o.nl_voltages_lock && p.nlock) {
         double dmax = 0.0;
-        AHK_LANES(k, p.nlock) {
+        AHK_ITEMS(k, p.nlock) {
           int n1 = p.lock[2 * k], n2 = p.lock[2 * k + 1];
           double dd;
           if (n1 != 0) dd = n2 != 0 ? fabs(dx[n1 - 1] - dx[n2 - 1]) : fabs(dx[n1 - 1]);
           else dd = fabs(dx[n2 != 0 ? n2 - 1 : n - 1]);   // dx[-1] quirk, dc_analysis.py:941
           if (dd > dmax) dmax = dd;
         }
-        dmax = Grp<G>::fmax_all(dmax, 0xffffffffu);
+        if (!REP) dmax = Grp<G>::fmax_all(dmax, 0xffffffffu);
         if (dmax > lim) td = fmin(td, fm::div(lim, dmax));
       }
       // x += td dx; convergence_check (utilities.py:392-549)
       bool ok = true, finite = true;
       if (m && lin_ok) {
-        AHK_LANES(i, n) {
+        AHK_ITEMS(i, n) {
           const double di = dx[i];
           const double xn = x[i] + td * di;
           x[i] = xn;
@@ -1264,11 +1280,11 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
           if (!(fabs(res[i]) <= (isv ? o.iea : o.vea))) ok = false;
         }
       }
-      const bool all_ok = GrpW<G>::all(ok), all_fin = GrpW<G>::all(finite);
+      const bool all_ok = REP ? ok : GrpW<G>::all(ok), all_fin = REP ? finite : GrpW<G>::all(finite);
       if (m) {
         if (!lin_ok) {            // LinAlgError: x as it was when mdn_solver was entered
           c.singular = 1;
-          AHK_LANES(i, n) x[i] = xin[i];
+          AHK_ITEMS(i, n) x[i] = xin[i];
           r = -1;
         } else if (!p.ndev || all_ok) r = 1;
         else if (!all_fin) { it = MAXIT; r = 0; }   // NaN never converges
@@ -1301,7 +1317,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
       double rmin = INFINITY;
       if (lte_on) {
         const double sc = fm::div(d.x_lte, d.pred_lte - d.x_lte);
-        AHK_LANES(i, n) {
+        AHK_ITEMS(i, n) {
           double lte = fabs(sc * (pred[i] - x[i]));
           if (lte != 0) {
             double re = i < p.nv1 ? o.ver : o.ier;
@@ -1310,7 +1326,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
           }
         }
       }
-      rmin = Grp<G>::fmin_all(rmin, 0xffffffffu);
+      if (!REP) rmin = Grp<G>::fmin_all(rmin, 0xffffffffu);
       bool stop = false;
       if (sd) {
         n_solves++; n_nr += ds_iters;
@@ -1341,7 +1357,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
             // store the row, dxdt = C1*x + C0, push to the ring (transient.py:385-393)
             h0 = (h0 + buflen - 1) % buflen;
             double* hnew = hx + h0 * n;
-            AHK_LANES(i, n) {
+            AHK_ITEMS(i, n) {
               double xi = x[i];
               xacc[i] = xi;
               hnew[i] = xi;

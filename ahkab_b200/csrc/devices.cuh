@@ -157,6 +157,10 @@ AHK_DEVFN void ekv_setup(const EkvP& m, double* k) {
 // Stateless and branch-uniform: every lane does the same work.
 AHK_DEV double ekv_q(double v) {
   double y, E;
+  // below v = -100 the result (q = e^v < 4e-44) only ever meets the 10 EPS floor of its callers
+  // (ekv.py:726): clamping v there changes nothing and bounds every exponential argument below,
+  // so the range clamps of fm::exp are not needed (y <= ln(v / 2) bounds them above)
+  v = fmax(v, -100.0);
   if (v > 2.0) {
     // y0 = ln(v/2) to single precision (enough for a start: Halley is cubic), and
     // E0 = v/2 taken directly instead of exp(y0): one fast log, no exponential
@@ -168,13 +172,13 @@ AHK_DEV double ekv_q(double v) {
     E = 0.5 * v;
   } else {
     y = v < -2.0 ? v : -0.85 + v * (0.555 - 0.065 * v);
-    E = fm::exp(y);
+    E = fm::exp_nc(y);
   }
   {
     double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;
     double d = fm::div(2.0 * f * f1, 2.0 * f1 * f1 - f * 2.0 * E);
     y -= d;
-    E = fm::exp(y);
+    E = fm::exp_nc(y);
   }
   {
     double f = y + 2.0 * E - v, f1 = 1.0 + 2.0 * E;

@@ -119,6 +119,7 @@ struct ahk_engine {
   int jit_R = 0, jit_G = 0;   // forced (rows per lane, lanes per instance) of the specialised kernels, 0 = heuristic
   int jit_ilp = 0;            // devices a lane evaluates interleaved (0 = heuristic)
   int jit_threads = 0, jit_minb = 0;   // forced block size / resident blocks per SM of the specialised kernels
+  int last[8] = {-1, 0, 0, 0, 0, 0, 0, 0};   // ahk_last_launch: vid, NC, R, G, threads, blocks, specialised?, analysis
   // variant / layout / launch shape / kernel of recent small-circuit calls, so that a repeated
   // call (the common case: same batch size again and again) goes straight to the launch
   struct Prepared { int vid; Layout Ly; Launch L; jit::Kernel* jk; };
@@ -608,10 +609,30 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
     int vid;
     const bool slim = jit != 0 && !full_layout;
     VarInfo v;
+    bool flat_auto = false;
     if (jit && e->jit_G > 0) {
       // a specialised kernel is not bound to the compiled variant table: any (R, G) shape
       vid = 1000 + e->jit_R * 64 + e->jit_G;
       v = VarInfo{e->n + 1, e->jit_R, e->jit_G};
+    } else if (jit && mode == MODE_TRAN && e->force_vid < 0 && e->group <= 0 && e->n + 1 <= 32) {
+      // Specialised TRANSIENT kernel (flat warp-uniform loop, core.cuh: tran_analysis), shape
+      // measured on C4 / C3 (profiles/r2*_sweep_*.txt):
+      //  * small matrices (n <= 6) behind devices: REPLICATED — the lanes of a group split the
+      //    device evaluations, at most three per lane (evaluated interleaved), and every lane
+      //    solves the whole system redundantly on compile-time indices;
+      //  * larger matrices: rows distributed, about five per lane.
+      const int nd = (int)e->H.dev.size();
+      int G = 1, R;
+      if (e->n <= 6) {
+        while (G < 8 && (nd + G - 1) / G > 3) G *= 2;
+        R = e->n;
+      } else {
+        while (G < 32 && (e->n + G - 1) / G > 5) G *= 2;
+        R = (e->n + G - 1) / G;
+      }
+      vid = 1000 + R * 64 + G;
+      v = VarInfo{e->n + 1, R, G};
+      flat_auto = true;
     } else {
       if (pick_variant(e, real_variants(), AHK_N_REAL_VARIANTS, e->force_vid, B, real_min_blocks,
                        [&](const VarInfo& q) { return make_layout(e->H, mode, method, usc, q.G, q.NC, q.R, slim).stride; },
@@ -626,6 +647,31 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
     *Ly = make_layout(e->H, mode, method, usc, v.G, v.NC, v.R, slim && v.NC > 0);
     static const int minb_env = getenv("AHK_JIT_MINB") ? atoi(getenv("AHK_JIT_MINB")) : 0;   // tuning
     int rb = (jit && minb_env > 0) ? minb_env : real_min_blocks(v.NC);
+    if (flat_auto && e->jit_threads <= 0 && e->jit_minb <= 0) {
+      // ONE WAVE: an instance lives for the whole analysis, so every SM must hold its share of
+      // the batch at once — blocks of two warps, and the register cap that lets
+      // ceil(share / instances per block) of them be resident (255 registers when the batch
+      // leaves the SM mostly empty: the interleaved device evaluations use them)
+      const long long per_sm = (B + e->sm_count - 1) / e->sm_count;
+      int threads = 64;
+      if (threads < v.G) threads = v.G;
+      const int ipb = threads / v.G;
+      int minb = (int)((per_sm + ipb - 1) / ipb);
+      const size_t smem = (size_t)ipb * Ly->stride * sizeof(double);
+      const int smem_blocks = (int)((size_t)(228 * 1024) / (smem + 1024));
+      if (smem <= e->smem_max && smem_blocks >= 1) {
+        minb = std::max(1, std::min(minb, std::min(smem_blocks, 2048 / threads)));
+        if (65536 / (minb * threads) < 64) minb = std::max(1, 65536 / (64 * threads));   // never below 64 registers
+        L->vid = vid; L->G = v.G; L->threads = threads; L->smem = smem;
+        L->blocks = (int)((B + ipb - 1) / ipb);
+        if (getenv("AHK_DEBUG"))
+          fprintf(stderr, "[ahk] flat transient kernel: n=%d R=%d G=%d, %d thr/block, %d blocks, %zu B smem/block, "
+                  "%d resident blocks/SM\n", e->n, v.R, v.G, threads, L->blocks, smem, minb);
+        if (get_jit(e, B, mode, vid, v, *Ly, *L, -minb, method, usc, jk)) return -1;
+        if (*jk) return 0;
+      }
+      continue;
+    }
     if (jit && (e->jit_threads > 0 || e->jit_minb > 0)) {
       // forced launch shape (ahk_set_jit_tuning): `threads` per block, registers capped for
       // `min_blocks` resident blocks; rb carries min_blocks * threads / 128 to get_jit
@@ -649,6 +695,14 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
   return 0;
 }
 
+void note_launch(ahk_engine* e, int vid, const Launch& L, bool jit, int analysis, bool ac = false) {
+  VarInfo v{0, 0, L.G};
+  if (vid >= 1000) v = VarInfo{e->n + 1, (vid - 1000) / 64, (vid - 1000) % 64};
+  else if (vid >= 0) { v = (ac ? ac_variants() : real_variants())[vid]; if (jit && v.NC > 0) v.NC = e->n + 1; }
+  e->last[0] = vid; e->last[1] = v.NC; e->last[2] = v.R; e->last[3] = v.G; e->last[4] = L.threads;
+  e->last[5] = L.blocks; e->last[6] = jit ? 1 : 0; e->last[7] = analysis;
+}
+
 int jit_launched(bool ok, const std::string& err) {
   if (!ok) return fail(err);
   g_launches++;
@@ -662,6 +716,7 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   int vid; Layout Ly; Launch L;
   jit::Kernel* jk = nullptr;
   if (prepare_small(e, batch->B, MODE_OP, 0, 0, &vid, &Ly, &L, &jk)) return -1;
+  note_launch(e, vid, L, jk != nullptr, 0);
   if (jk) {
     KDcJ kj = {batch->vary, batch->B, DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status}};
     std::string err;
@@ -784,6 +839,12 @@ int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks) {
   if (threads < 0 || threads > 1024 || threads % 32) return fail("ahk_set_jit_tuning: threads must be a multiple of 32");
   if (min_blocks < 0 || min_blocks > 32) return fail("ahk_set_jit_tuning: min_blocks must be 0..32");
   e->jit_ilp = ilp; e->jit_threads = threads; e->jit_minb = min_blocks;
+  return 0;
+}
+
+int ahk_last_launch(const ahk_engine* e, int32_t* out8) {
+  if (!e || !out8) return fail("null argument");
+  for (int i = 0; i < 8; i++) out8[i] = e->last[i];
   return 0;
 }
 
@@ -1079,6 +1140,7 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   int vid; Layout Ly; Launch L;
   jit::Kernel* jk = nullptr;
   if (prepare_small(e, batch->B, MODE_TRAN, method, use_step_control ? 1 : 0, &vid, &Ly, &L, &jk)) return -1;
+  note_launch(e, vid, L, jk != nullptr, 1);
   if (jk) {
     KTranJ kj = {batch->vary, batch->B, x0,
                  TranArgs{tstart, tstep, tstop, method, use_step_control, max_rows, t_out, x_out, rows, counters},
@@ -1134,11 +1196,13 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     jit::Kernel* jk = nullptr;
     if (get_jit(e, batch->B, JIT_MODE_AC, vid, vj, ALj.L, Lj, ac_min_blocks(v.NC), 0, 0, &jk, &ja)) return -1;
     if (jk) {
+      note_launch(e, vid, Lj, true, 2, true);
       KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, nchunks};
       std::string err;
       return jit_launched(jit::launch(*jk, Lj.blocks, Lj.threads, Lj.smem, s, &kj, err), err);
     }
   }
+  note_launch(e, vid, L, false, 2, true);
   KAc k;
   k.p = e->dprog; k.o = e->o; k.AL = AL;
   k.vary = batch->vary; k.B = batch->B; k.nchunks = nchunks;

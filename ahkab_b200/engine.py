@@ -141,6 +141,13 @@ class Engine(object):
             raise EngineError(self._err())
         return self
 
+    def last_launch(self):
+        """ahk_last_launch as a dict: vid, NC, R, G, threads, blocks, jit, analysis."""
+        out = (C.c_int32 * 8)()
+        if self.lib.ahk_last_launch(self._h, out) != 0:
+            raise EngineError(self._err())
+        return dict(zip(('vid', 'NC', 'R', 'G', 'threads', 'blocks', 'jit', 'analysis'), list(out)))
+
     def jit_launch_count(self):
         return int(self.lib.ahk_jit_launch_count())
 

@@ -209,6 +209,10 @@ int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes);
  * interleaved (1..4, 0 = heuristic); threads = block size (multiple of 32, 0 = heuristic);
  * min_blocks = resident blocks per SM the register allocation is capped for (0 = heuristic). */
 int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks);
+/* Shape of the last small-circuit kernel launch of this engine (diagnostics, tests):
+ * out8 = { variant id (>= 1000: free shape), matrix columns, rows per lane, lanes per
+ * instance, threads per block, blocks, 1 if circuit-specialised, analysis 0 OP/DC 1 tran 2 AC }. */
+int ahk_last_launch(const ahk_engine* e, int32_t* out8);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);
 int64_t ahk_jit_build_count(void);

@@ -140,17 +140,17 @@ def test_c4_ring3_gear2_lte(gold, v):
     assert np.abs(rows - ot['rows']).max() <= 0.01 * ot['rows'].max()
     assert np.abs(rows[:8] - g['t_rows']).max() <= 0.01 * g['t_rows'].max()
     # waveforms on the reference's time grid, the reference test's own tolerance
-    # (tests/ring3/test_ring3.py:6: er=1e-1, ea=1e-2)
+    # (tests/ring3/test_ring3.py:6: er=1e-1, ea=1e-2) over the whole run
     t, x = _np(rt['t']), _np(rt['x'])
     for b in range(8):
         rg = int(g['t_rows'][b]); rb = int(rows[b])
-        for v in range(5):
-            xi = np.interp(g['t'][b, :rg], t[b, :rb], x[b, :rb, v])
-            ref = g['x'][b, :rg, v]
-            assert np.all(np.abs(xi - ref) <= 1e-2 + 1e-1 * np.abs(ref) + 0.35), (b, v)
-        # early window (before phase drift matters): tight
-        k = 200
-        assert common.parity_tol(x[b, :k], g['x'][b, :k], 4) < 50.0
+        tg = g['t'][b, :rg]
+        xi = np.stack([np.interp(tg, t[b, :rb], x[b, :rb, q]) for q in range(5)], -1)
+        ref = g['x'][b, :rg]
+        assert np.all(np.abs(xi - ref) <= 1e-2 + 1e-1 * np.abs(ref)), b
+        # early window: 10x the SURVEY 8(d) tolerance (different LTE-controlled grids, values
+        # compared through linear interpolation)
+        assert common.parity_tol(xi[:200], ref[:200], 4) < 10.0, b
 
 
 @pytest.mark.parametrize('v', [-1, 0, 1, 4, 5, 6])

@@ -17,6 +17,9 @@ circ = w.circuit(Circuit)
 e = Engine(circ, w.batch(), opts=w.opts)
 e.set_variant(real=G if name != 'c1' else -1, ac=G if name == 'c1' else -1)
 e.set_jit(os.environ.get('AHK_JIT', 'auto'))   # circuit-specialised kernels: auto / on / off
+if os.environ.get('AHK_SHAPE'):                # "R,G,ilp,threads,minb" of the specialised kernel
+    R_, G_, ilp_, thr_, minb_ = (int(v) for v in os.environ['AHK_SHAPE'].split(','))
+    e.set_jit_shape(R_, G_); e.set_jit_tuning(ilp_, thr_, minb_)
 for _ in range(reps):
     if name == 'c2':
         r = e.op()
