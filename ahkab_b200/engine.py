@@ -167,7 +167,7 @@ class Engine(object):
 
     _ES = {torch.float64: 8, torch.int32: 4}
 
-    def _new_packed(self, spec):
+    def _new_packed(self, spec, cache=True):
         """Result tensors of one call as views into ONE device buffer, so that the
         device->host read of an end-to-end step is a single copy.  spec: tuple of (key,
         shape, dtype); float64 first keeps every view 8-byte aligned.  The byte layout is
@@ -183,7 +183,8 @@ class Engine(object):
                 items.append((k, tuple(shape), dtype, off, n_el * self._ES[dtype], nb))
                 off += nb
             lay = (off, items)
-            self._layouts[spec] = lay
+            if cache:
+                self._layouts[spec] = lay
         total, items = lay
         base = torch.empty(total, dtype=torch.uint8, device=self.device)
         out = {}
@@ -311,23 +312,33 @@ class Engine(object):
         t [sum rows], x [sum rows][n], offsets [B + 1] (int64, instance b owns rows
         offsets[b]:offsets[b+1]) plus rows / counters / status.  Reads the row total back
         (one small synchronising copy); the device->host read of the result then moves only
-        the rows that exist instead of B x max_rows."""
+        the rows that exist instead of B x max_rows.  Everything but `offsets` (= cumsum of
+        rows) lives in ONE device buffer (`_packed`): one D2H copy, one message of the
+        multi-GPU result gather."""
         rows = raw['rows']
         B, max_rows = raw['t'].shape
         offs = torch.zeros(B + 1, dtype=torch.int64, device=self.device)
         torch.cumsum(rows, 0, out=offs[1:])
         total = int(offs[-1].item())
-        t = self._new((max(total, 1),))
-        x = self._new((max(total, 1), self.n))
+        spec = (('t', (max(total, 1),), torch.float64), ('x', (max(total, 1), self.n), torch.float64),
+                ('rows', (B,), torch.int32), ('counters', (B, 4), torch.int32),
+                ('status', (B,), torch.int32))
+        if 'op_iters' in raw:
+            spec += (('op_iters', (B,), torch.int32),)
+        pk = self._new_packed(spec, cache=False)
+        t, x = pk['t'], pk['x']
         with torch.cuda.device(self.device):
             rc = self.lib.ahk_pack_rows(_ptr(raw['t']), _ptr(raw['x']), _ptr(rows), _ptr(offs), B,
                                         max_rows, self.n, _ptr(t), _ptr(x), self._stream())
         if rc != 0:
             raise EngineError(self._err())
-        out = dict(t=t[:total], x=x[:total], offsets=offs, rows=rows, counters=raw['counters'],
-                   status=raw['status'])
-        if 'op_iters' in raw:
-            out['op_iters'] = raw['op_iters']
+        for k in ('rows', 'counters', 'status', 'op_iters'):
+            if k in pk:
+                pk[k].copy_(raw[k])
+        out = dict(t=t[:total], x=x[:total], offsets=offs, rows=pk['rows'], counters=pk['counters'],
+                   status=pk['status'], _packed=pk['_packed'])
+        if 'op_iters' in pk:
+            out['op_iters'] = pk['op_iters']
         return out
 
     @staticmethod
@@ -376,11 +387,7 @@ class Engine(object):
         out = {}
         if keys is None and raw.get('_packed') is not None:
             base, layout = raw['_packed']             # one copy for the whole result set
-            key = ('_packed', base.numel())
-            hb = self._pinned.get(key)
-            if hb is None:
-                hb = torch.empty(base.numel(), dtype=torch.uint8, pin_memory=True)
-                self._pinned[key] = hb
+            hb = self.pinned_bytes(base.numel())
             hb.copy_(base, non_blocking=True)
             for k, shape, dtype, off, nbytes, _nb in layout:
                 out[k] = hb[off:off + nbytes].view(dtype).view(shape)
@@ -400,6 +407,17 @@ class Engine(object):
             buf.copy_(src, non_blocking=True)
             out[k] = buf
         return out
+
+    def pinned_bytes(self, nbytes):
+        """A pinned host buffer of nbytes (uint8) out of ONE cached, grow-only allocation
+        (pinning memory costs milliseconds: never per call)."""
+        if not hasattr(self, '_pinned'):
+            self._pinned = {}
+        hb = self._pinned.get('_bytes')
+        if hb is None or hb.numel() < nbytes:
+            hb = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+            self._pinned['_bytes'] = hb
+        return hb[:nbytes]
 
     def probe_fp64(self, iters=4096, blocks=None, threads=256):
         """Launch the FP64-FMA probe kernel (diagnostics); returns its flop count."""

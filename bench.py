@@ -18,9 +18,17 @@ synthetic batch:
           CUDA events on the launching stream, L2 flushed between timed steps.
 `e2e`     the same step through the Engine API with HOST buffers: pinned
           H2D of the parameters, the analysis, pinned D2H of every result.
-N > 1     one process per GPU (torchrun), weak scaling: every rank runs its own
-          full-size batch (seed + rank), no data-path collective; the e2e step
-          ends with the NCCL gather of the per-instance iters/status words.
+N > 1     one process per GPU (torchrun), STRONG scaling: the fixed BASELINE batch is
+          cut into contiguous shards (ahkab_b200/dist.py: shard_range), one per rank;
+          `value` = units of the whole batch / max-over-ranks kernel time.  The e2e
+          step of every rank is pinned H2D of its shard, the analysis, then the ONE
+          result collective — every rank's packed result buffer (x / resid / iters /
+          status, packed transient rows) to rank 0 over NCCL (grouped send/recv) —
+          and rank 0's pinned D2H of the gathered batch.  `e2e.hbm_resident` stops
+          the clock when the results sit in rank 0's HBM; `e2e.breakdown_ms` splits a
+          step into H2D / kernels / gather / D2H with CUDA events; `weak` is the old
+          weak-scaling figure (every rank its own full-size batch), kept as a
+          secondary key.
 --impl reference   the reference's algorithm on the host cores: the C
           restatement in oracle/ (the reference itself is pure Python and does
           not travel to the GPU box), OpenMP over all cores, rank 0 only.
@@ -65,6 +73,12 @@ E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=1)   # c5: thread-per-instance kern
 OP_HOST = os.environ.get('AHK_E2E_OP_HOST')
 
 
+def config_of(name):
+    """The workload description — identical in both arms (ours / --impl reference)."""
+    return {"workload": NAMES[name], "instances": FULL_B[name],
+            "l2": "GPU arm: flushed (512 MiB write) before every timed step; CPU arm: not applicable"}
+
+
 def LU(n):
     return 2.0 / 3.0 * n ** 3 + 2.0 * n ** 2
 
@@ -86,19 +100,26 @@ JIT_MODE = 'auto'   # --jit: circuit-specialised kernels (ahk_set_jit); auto = b
 class Runner(object):
     """One workload on one GPU: `step()` with inputs resident, `e2e()` from host."""
 
-    def __init__(self, name, seed_off=0, B=None):
+    def __init__(self, name, seed_off=0, B=None, rank=0, world=1):
+        """world > 1: this rank's contiguous shard of the one seeded batch of B instances
+        (strong scaling); seed_off: a different full batch per rank (weak scaling)."""
         import torch
         import common
         from ahkab_b200 import workloads as W
+        from ahkab_b200 import dist as ahk_dist
         from ahkab_b200.circuit import Circuit
         from ahkab_b200.engine import Engine
-        self.torch, self.common, self.W = torch, common, W
+        self.torch, self.common, self.W, self.ahk_dist = torch, common, W, ahk_dist
         self.name = name
         B = B or FULL_B[name]
         seeds = dict(c1=0, c2=1, c3=2, c4=3, c5=4)
         self.w = W.ALL[name](B=B, seed=seeds[name] + 1000 * seed_off)
         self.circ = self.w.circuit(Circuit)
-        self.eng = Engine(self.circ, self.w.batch(), opts=self.w.opts)
+        self.rank, self.world, self.B_total = rank, world, B
+        lo, hi = ahk_dist.shard_range(B, world, rank)
+        self.lo, self.hi = lo, hi
+        B = hi - lo
+        self.eng = Engine(self.circ, self.w.batch(lo, hi), opts=self.w.opts)
         # (threshold 1024: the chunks of the pipelined end-to-end paths are sub-batches of
         # 1024 instances and the bench repeats every call, so the compilation amortises)
         self.eng.set_jit(JIT_MODE, min_batch=1024)
@@ -113,6 +134,7 @@ class Runner(object):
             self.om = common.c1_omegas()
         if name == 'c5':
             self.sw = common.c5_sweep()
+        self.gbuf = None      # rank 0: destination of the result gather (grow-only)
         if name == 'c4':
             self.x0_host = torch.as_tensor(common.c4_x0(self.circ, B)).pin_memory()
             self.x0 = self.x0_host.cuda()
@@ -162,6 +184,36 @@ class Runner(object):
         host = self.pipe.run(lambda sub, lo, hi, x: self.step(sub, x.get('x0')),
                              self.vary_host, extra)
         return host, host
+
+    def e2e_dist(self, d2h=True, ev=None):
+        """One end-to-end step of a sharded run: pinned H2D of this rank's shard, the
+        analysis, the single result collective (every rank's packed result buffer to rank
+        0, NCCL), and rank 0's pinned D2H of the gathered batch.  ev: optional list that
+        receives CUDA events at the phase boundaries (H2D | kernels | gather | D2H)."""
+        torch = self.torch
+        def mark():
+            if ev is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); ev.append(e)
+        mark()
+        self.eng.set_vary(self.vary_host)
+        if self.name == 'c4':
+            self.x0.copy_(self.x0_host, non_blocking=True)
+        mark()
+        raw = self.step()
+        tran = self.name in ('c3', 'c4')
+        pk = self.eng.pack_tran(raw) if tran else raw
+        mark()
+        big, views = self.ahk_dist.gather_result(pk, ragged=tran, out=self.gbuf)
+        mark()
+        host = None
+        if self.rank == 0:
+            self.gbuf = big if (self.gbuf is None or big.numel() > self.gbuf.numel()) else self.gbuf
+            self.gathered_bytes = int(big.numel())
+            if d2h:
+                host = self.eng.pinned_bytes(big.numel())
+                host.copy_(big, non_blocking=True)
+        mark()
+        return raw, host
 
     def d2h_bytes(self, host):
         return int(sum(v.numel() * v.element_size() for v in host.values()))
@@ -428,13 +480,13 @@ def run_reference(args, rank):
                 "cpu_baseline": cb,
                 "e2e": {"value": cb['value'], "unit": UNITS[name], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
-                "config": {"workload": NAMES[name], "sample": cb['sample']}}
+                "config": config_of(name)}
         if i == 0:
             out = line
         else:
             cfgs[name] = line
     out.update({"impl": "reference", "n_gpus": args.gpus, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "gpu_launches": 0})
     if cfgs:
         out["configs"] = cfgs
@@ -445,7 +497,7 @@ def run_reference(args, rank):
 def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_src, fp64_peak,
               dist_on, device, want_cpu):
     import torch
-    r = Runner(name, seed_off=rank)
+    r = Runner(name, rank=rank, world=world)
     eng = r.eng
     # kernel path, inputs resident
     # kernels of this library per step (counted on one untimed step), times the K timed steps
@@ -454,60 +506,93 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     r.step()
     launches = (eng.launch_count() - l0) * steps
     jit_launches = (eng.jit_launch_count() - j0) * steps
+    shape = eng.last_launch() if name != 'c5' else None
     ms, raw = timer.timed(r.step, steps, warmup, sampler)
     units = all_sum(r.units(raw), dist_on, device)
     flop, byts = r.algo(raw)
     value = units * steps / (ms * 1e-3)
     # end to end, host buffers
-    e2e_fn = r.e2e
+    hbm_resident = breakdown = None
     if dist_on:
-        # the single result collective: gather the per-instance words to rank 0
-        from ahkab_b200 import dist as ahk_dist
-
-        def e2e_fn():
-            rr, hh = r.e2e()
-            st = rr['status'] if rr['status'].is_cuda else rr['status'].to(device, non_blocking=True)
-            ahk_dist.gather_rows(st.reshape(r.B, -1), r.B * world)
-            return rr, hh
-    ms_e, (raw_e, host) = timer.timed(e2e_fn, steps, warmup)
+        ms_a, _ = timer.timed(lambda: r.e2e_dist(d2h=False), steps, warmup)
+        hbm_resident = {"value": units * steps / (ms_a * 1e-3), "ms_per_step": ms_a / steps,
+                        "what": "same step, clock stopped when the gathered results are in rank 0's HBM"}
+        ms_e, (raw_e, host) = timer.timed(r.e2e_dist, steps, warmup)
+        # phase breakdown of one step on rank 0 (CUDA events on the stream between the phases)
+        evs = []
+        timer.barrier()
+        r.e2e_dist(ev=evs)
+        timer.barrier()
+        ph = [evs[i].elapsed_time(evs[i + 1]) for i in range(4)]
+        breakdown = {"h2d": ph[0], "kernels_and_pack": ph[1], "nccl_gather": ph[2], "d2h_rank0": ph[3],
+                     "what": "rank 0, one step, CUDA events between the phases (the gather includes "
+                             "waiting for the slowest rank)"}
+        d2h_bytes = int(all_sum(getattr(r, 'gathered_bytes', 0), dist_on, device))
+        h2d_bytes = int(all_sum(r.h2d, dist_on, device))
+    else:
+        ms_e, (raw_e, host) = timer.timed(r.e2e, steps, warmup)
+        d2h_bytes, h2d_bytes = r.d2h_bytes(host), r.h2d
     units_e = all_sum(r.units(raw_e), dist_on, device)
     e2e_value = units_e * steps / (ms_e * 1e-3)
     ok = int((raw['status'] & 1).sum().item()) if 'status' in raw else None
     step_s = ms * 1e-3 / steps
+    par = ("single GPU" if world == 1 else
+           "fixed batch of %d instances in %d contiguous shards (one rank per GPU); one NCCL "
+           "result collective per step: every rank's packed results to rank 0 (grouped send/recv)"
+           % (r.B_total, world))
     line = {
         "metric": UNITS[name].replace('/s', '/sec'), "value": value,
         "unit": UNITS[name], "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f64" if name != 'c1' else "complex128",
         "data": "synthetic",
-        "config": {"workload": NAMES[name], "instances_per_gpu": r.B,
-                   "units_per_step_rank0": r.units(raw), "n_unknowns": eng.n,
-                   "l2": "flushed (512 MiB write) before every timed step",
-                   "parallelism": "batch sharded, %d rank(s), no data-path collective" % world,
-                   "status_ok_rank0": ok,
-                   "kernels": ("%d of %d launches per run are circuit-specialised kernels "
-                               "(NVRTC, sm_100a; --jit %s)" % (jit_launches, launches, JIT_MODE))},
+        "config": config_of(name),
+        "details": {"instances_per_gpu": r.B, "units_per_step": units, "n_unknowns": eng.n,
+                    "parallelism": par, "status_ok_rank0": ok, "kernel_shape_rank0": shape,
+                    "kernels": ("%d of %d launches per run are circuit-specialised kernels "
+                                "(NVRTC, sm_100a; --jit %s)" % (jit_launches, launches, JIT_MODE))},
         "e2e": {"value": e2e_value, "unit": UNITS[name], "ms_per_step": ms_e / steps,
-                "chunks": E2E_CHUNKS[name],
-                "h2d_bytes_per_step": r.h2d, "d2h_bytes_per_step": r.d2h_bytes(host)},
+                "chunks": E2E_CHUNKS[name] if world == 1 else 1,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "fp64", "achieved": flop / step_s / 1e12, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": flop / step_s / 1e12 / fp64_peak if fp64_peak else None,
             "peak_source": "measured in this run: DFMA probe kernel (ahk_probe_fp64), best of 5",
             "algorithmic_flop_per_step": flop,
+            "scope": "rank 0's kernels on its shard" if world > 1 else "the whole batch",
             "traffic": (measured_traffic(name) or {}).get("bytes"),
             "traffic_source": measured_traffic(name),
             "hbm": {"bound": "hbm", "achieved": byts / step_s / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},
     }
+    if hbm_resident:
+        line["e2e"]["hbm_resident"] = hbm_resident
+        line["e2e"]["breakdown_ms"] = breakdown
+    if name == 'c5':
+        line["roofline"].update(c5_roofline_extra(eng, r, step_s, fp64_peak))
     if want_cpu and rank == 0 and world == 1:
         cb, _ms = cpu_measure(name, 2 if name in ('c3', 'c4') else 3, 1)
         line["cpu_baseline"] = cb
     del r
     torch.cuda.empty_cache()
+    if dist_on:
+        # secondary: the weak-scaling figure (every rank its own full-size batch, kernel path)
+        rw = Runner(name, seed_off=rank)
+        ms_w, raw_w = timer.timed(rw.step, min(steps, 3), 3)
+        units_w = all_sum(rw.units(raw_w), dist_on, device)
+        line["weak"] = {"value": units_w * min(steps, 3) / (ms_w * 1e-3), "ms_per_step": ms_w / min(steps, 3),
+                        "instances_per_gpu": rw.B, "scaling": "weak",
+                        "what": "kernel path, every rank its own full-size batch, no collective"}
+        del rw
+        torch.cuda.empty_cache()
     return line
+
+
+def c5_roofline_extra(eng, r, step_s, fp64_peak):
+    return {}
 
 
 def main():

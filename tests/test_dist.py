@@ -81,6 +81,51 @@ def test_gather_rows_two_gloo_ranks(B):
     assert (gs[:half] == 1).all() and (gs[half:] == 2).all()
 
 
+def _worker_packed(rank, world, port, q):
+    """ragged messages (what LTE-controlled transients produce) + a packed result set"""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n = 5 + 3 * rank                                   # ragged: 5 and 8 elements
+        buf = torch.arange(n, dtype=torch.float64) + 100 * rank
+        big, views = ahk_dist.gather_packed(buf)           # sizes exchanged (one small all_gather)
+        # a packed result set like Engine._new_packed builds it: x [B][2] f64 | status [B] i32
+        B = 3 + rank
+        base = torch.zeros(B * 16 + ((B * 4 + 7) & ~7), dtype=torch.uint8)
+        layout = [('x', (B, 2), torch.float64, 0, B * 16, B * 16),
+                  ('status', (B,), torch.int32, B * 16, B * 4, (B * 4 + 7) & ~7)]
+        loc = ahk_dist.unpack(base, layout)
+        loc['x'][:] = rank + torch.arange(B * 2, dtype=torch.float64).reshape(B, 2) / 10
+        loc['status'][:] = 7 + rank
+        gb, gv = ahk_dist.gather_result({'_packed': (base, layout)}, ragged=True)
+        if rank == 0:
+            lay1 = [('x', (4, 2), torch.float64, 0, 64, 64), ('status', (4,), torch.int32, 64, 16, 16)]
+            r1 = ahk_dist.unpack(gv[1], lay1)
+            q.put((big.numpy(), [v.numpy().copy() for v in views], r1['x'].numpy().copy(),
+                   r1['status'].numpy().copy()))
+        else:
+            assert big is None and views is None and gb is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_packed_ragged_two_gloo_ranks():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    big, views, x1, st1 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(big, np.concatenate([np.arange(5.), np.arange(8.) + 100]))
+    assert np.array_equal(views[0], np.arange(5.)) and np.array_equal(views[1], np.arange(8.) + 100)
+    assert np.array_equal(x1, 1 + np.arange(8.).reshape(4, 2) / 10) and (st1 == 8).all()
+
+
 def test_gather_rows_single_process_is_identity():
     x = torch.arange(6.).reshape(3, 2)
     assert ahk_dist.gather_rows(x, 3) is x
