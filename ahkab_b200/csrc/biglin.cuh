@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(32) k_biglin(const __grid_constant__ BigK k, c
 #ifdef __CUDACC__
 struct ahk_engine;
 // host driver state of the large-n path (owned by ahk_engine)
+namespace ahk { struct Big3Sched; }   // biglin3.cuh
 struct BigLin {
   // dense-workspace kernel (biglin.cuh): fallback for instances whose rows outgrow the
   // shared-memory slots of the sparse kernel, and for n > 1024
@@ -265,11 +266,15 @@ struct BigLin {
   double* s3_V = nullptr; double* s3_Mv = nullptr; double* s3_bs = nullptr; double* s3_xs = nullptr;
   int* s3_flag = nullptr;
   size_t s3_V_cap = 0, s3_Mv_cap = 0, s3_scr_cap = 0, s3_flag_cap = 0;
-  void release3() {
-    cudaFree(s3_sched); cudaFree(s3_V); cudaFree(s3_Mv); cudaFree(s3_bs); cudaFree(s3_xs); cudaFree(s3_flag);
-    s3_sched = nullptr; s3_V = s3_Mv = s3_bs = s3_xs = nullptr; s3_flag = nullptr;
-    s3_V_cap = s3_Mv_cap = s3_scr_cap = s3_flag_cap = 0; s3_ok = false; s3_slots_epoch = s3_opts_epoch = -1;
-  }
+  // the schedule COMPILED (biglin3_gen.hpp): module, factor-value count, buffers
+  void* c3_mod[2] = {nullptr, nullptr};   // jit::Kernel objects (factor, solve), owned here as opaque pointers
+  int c3_state = 0;                       // 0 not tried for this epoch, 1 ready, -1 unavailable
+  int c3_nf = 0, c3_npos = 0;
+  double* c3_F = nullptr; double* c3_Mv = nullptr; int* c3_flagm = nullptr;
+  size_t c3_F_cap = 0, c3_Mv_cap = 0, c3_flag_cap = 0;
+  void release_c3();
+  ahk::Big3Sched* s3_S = nullptr;         // host copy of the schedule (source of the generated code), owned
+  void release3();
   void release() {
     release3();
     cudaFree(wsA); cudaFree(wsLv); cudaFree(wsUv); cudaFree(wsLi); cudaFree(wsUi); cudaFree(d_sweep);

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "biglin3.cuh"
+#include "biglin3_gen.hpp"
 #include "jit.hpp"
 #include "jit_gen.hpp"
 #include "kernels.cuh"
@@ -143,6 +144,24 @@ struct ahk_engine {
   } hp;
 };
 
+void BigLin::release_c3() {
+  for (int i = 0; i < 2; i++) {
+    jit::Kernel* k = (jit::Kernel*)c3_mod[i];
+    if (k) { if (i == 0) jit::unload(*k); delete k; }
+    c3_mod[i] = nullptr;
+  }
+  cudaFree(c3_F); cudaFree(c3_Mv); cudaFree(c3_flagm);
+  c3_F = c3_Mv = nullptr; c3_flagm = nullptr;
+  c3_F_cap = c3_Mv_cap = c3_flag_cap = 0; c3_state = 0;
+}
+void BigLin::release3() {
+  release_c3();
+  delete s3_S; s3_S = nullptr;
+  cudaFree(s3_sched); cudaFree(s3_V); cudaFree(s3_Mv); cudaFree(s3_bs); cudaFree(s3_xs); cudaFree(s3_flag);
+  s3_sched = nullptr; s3_V = s3_Mv = s3_bs = s3_xs = nullptr; s3_flag = nullptr;
+  s3_V_cap = s3_Mv_cap = s3_scr_cap = s3_flag_cap = 0; s3_ok = false; s3_slots_epoch = s3_opts_epoch = -1;
+}
+
 int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* sweep_host,
                 int npts, double* x_out, int32_t* iters, int32_t* status, double* resid,
                 cudaStream_t s, std::string& err, std::atomic<long long>& launches) {
@@ -172,6 +191,12 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       Big3Sched S;
       s3_ok = big3_build(e->H, e->o, S);
       s3_slots_epoch = e->slots_epoch; s3_opts_epoch = e->opts_epoch;
+      // the schedule as straight-line code (biglin3_gen.hpp), under the engine's JIT policy;
+      // built lazily below, when a batch that the policy wants specialised arrives
+      CKB(cudaStreamSynchronize(s));
+      release_c3();
+      delete s3_S; s3_S = nullptr;
+      if (s3_ok && big3_codegen_fits(S)) s3_S = new Big3Sched(S); else c3_state = -1;
       if (s3_ok) {
         std::vector<unsigned char> buf;
         size_t off[11];
@@ -187,7 +212,64 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         s3_n = S.n; s3_npos = S.npos; s3_nslot = S.nslot; s3_nrec = (int)S.rslot.size();
       }
     }
-    if (s3_ok) {
+    // ---- 0a. the schedule compiled for this circuit (NVRTC) ----------------------------------
+    if (s3_ok && c3_state >= 0 && (e->jit_mode == 1 || (e->jit_mode == 2 && batch->B >= e->jit_min_batch))) {
+      if (c3_state == 0) {
+        Big3Gen G;
+        std::string jerr;
+        bool cached = false;
+        jit::Kernel* kf = new jit::Kernel(); jit::Kernel* ks = new jit::Kernel();
+        if (s3_S && big3_codegen(e->H, e->o, *s3_S, G) &&
+            jit::build_text2(G.src, "ahk_big3c_factor", "ahk_big3c_solve", *kf, *ks, jerr, &cached)) {
+          c3_mod[0] = kf; c3_mod[1] = ks; c3_nf = G.nf; c3_npos = s3_S->npos; c3_state = 1;
+          if (!cached) g_jit_builds++;
+          if (getenv("AHK_DEBUG"))
+            fprintf(stderr, "[ahk] compiled elimination schedule %s: %zu statements, %d factor values per matrix\n",
+                    cached ? "loaded from the disk cache" : "built", G.statements, G.nf);
+        } else {
+          delete kf; delete ks; c3_state = -1;
+          if (e->jit_mode == 1) { err = "compiled elimination schedule: " + jerr; return -1; }
+          if (getenv("AHK_DEBUG")) fprintf(stderr, "[ahk] compiled schedule not built: %s\n", jerr.c_str());
+        }
+      }
+      if (c3_state == 1) {
+        const long long B = batch->B;
+        const size_t needF = (size_t)2 * c3_nf * B, needM = (size_t)c3_npos * B;
+        if (needF > c3_F_cap || needM > c3_Mv_cap || (size_t)2 * B > c3_flag_cap || B + 1 > ovf_cap) {
+          CKB(cudaStreamSynchronize(s));
+          if (needF > c3_F_cap) { cudaFree(c3_F); c3_F = nullptr; CKB(cudaMalloc(&c3_F, needF * 8)); c3_F_cap = needF; }
+          if (needM > c3_Mv_cap) { cudaFree(c3_Mv); c3_Mv = nullptr; CKB(cudaMalloc(&c3_Mv, needM * 8)); c3_Mv_cap = needM; }
+          if ((size_t)2 * B > c3_flag_cap) { cudaFree(c3_flagm); c3_flagm = nullptr; CKB(cudaMalloc(&c3_flagm, (size_t)2 * B * 4)); c3_flag_cap = 2 * B; }
+          if (B + 1 > ovf_cap) {
+            cudaFree(d_ovf); d_ovf = nullptr; ovf_cap = B + 1;
+            CKB(cudaMalloc(&d_ovf, (size_t)ovf_cap * sizeof(int)));
+          }
+        }
+        CKB(cudaMemsetAsync(d_ovf, 0, sizeof(int), s));
+        Big3CK ck;
+        ck.vary = batch->vary; ck.B = B; ck.src_elem = src_elem; ck.sweep = d_sweep; ck.npts = npts;
+        ck.pt0 = 0; ck.ptc = npts;
+        ck.x_out = x_out; ck.iters = iters; ck.status = status; ck.resid = resid;
+        ck.F = c3_F; ck.Mv = c3_Mv; ck.flagm = c3_flagm; ck.ovf = d_ovf;
+        std::string lerr;
+        const int T = 64;
+        if (!jit::launch(*(jit::Kernel*)c3_mod[0], (int)((2 * B + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
+        launches++; g_jit_launches++;
+        // one launch for all sweep points unless the grid would be enormous: measured on C5
+        // (gpurun_out/r2i_ptc.txt) 1 / 2 / 3 / 5 / 10 points per launch = 6.9 / 3.6 / 3.0 / 1.7 /
+        // 1.15 ms — the solve is a serial chain per thread, more threads in flight hide it
+        int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 22) / std::max<long long>(1, B)));
+        if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
+        for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
+          ck.pt0 = pt0; ck.ptc = std::min(ptc, npts - pt0);
+          const long long TT = B * ck.ptc;
+          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)((TT + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
+          launches++; g_jit_launches++;
+        }
+        staged = true;
+      }
+    }
+    if (s3_ok && !staged) {
       const long long B = batch->B;
       // scratch of the solve kernel: [n][B * ptc] doubles twice, at most ~1 GB per buffer
       int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 27) / ((long long)n * B)));

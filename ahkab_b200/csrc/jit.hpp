@@ -182,6 +182,54 @@ inline std::vector<char> compile(const std::string& spec, std::string& err, bool
   return cubin;
 }
 
+// A self-contained translation unit (no engine headers): biglin3_gen.hpp's compiled schedules.
+// Cached on disk by the hash of its text.
+inline std::vector<char> compile_text(const std::string& tu, std::string& err, bool* from_cache = nullptr) {
+  std::vector<char> cubin;
+  std::string cpath;
+  {
+    const char* env = getenv("AHK_JIT_CACHE");
+    if (!(env && std::string(env) == "off")) {
+      std::string dir;
+      if (env && *env) dir = env;
+      else if (const char* home = getenv("HOME")) dir = std::string(home) + "/.cache/ahkab_b200";
+      if (!dir.empty()) {
+        unsigned long long h = fnv1a(tu.data(), tu.size());
+        h = fnv1a("sm_100a nvrtc12 text v1", 23, h);
+        char name[64];
+        snprintf(name, sizeof name, "/%016llx.cubin", h);
+        cpath = dir + name;
+      }
+    }
+  }
+  if (from_cache) *from_cache = false;
+  if (cache_read(cpath, cubin)) { if (from_cache) *from_cache = true; return cubin; }
+  if (!load(true, err)) return cubin;
+  Api& a = api();
+  nvrtcProgram prog;
+  nvrtcResult r = a.CreateProgram(&prog, tu.c_str(), "ahk_gen.cu", 0, nullptr, nullptr);
+  if (r != NVRTC_SUCCESS) { err = std::string("nvrtcCreateProgram: ") + a.GetErrorString(r); return cubin; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  r = a.CompileProgram(prog, 3, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t ls = 0;
+    a.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) a.GetProgramLog(prog, &log[0]);
+    err = std::string("NVRTC: ") + a.GetErrorString(r) + "\n" + log.substr(0, 4000);
+    a.DestroyProgram(&prog);
+    return cubin;
+  }
+  size_t sz = 0;
+  a.GetCUBINSize(prog, &sz);
+  cubin.resize(sz);
+  if (sz) a.GetCUBIN(prog, cubin.data());
+  a.DestroyProgram(&prog);
+  if (!sz) err = "NVRTC produced no cubin";
+  else cache_write(cpath, cubin);
+  return cubin;
+}
+
 struct Kernel {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
@@ -211,6 +259,24 @@ inline bool build(const std::string& spec, const char* entry, size_t smem, Kerne
     r = a.FuncSetAttribute(k.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
     if (r != CUDA_SUCCESS) { err = "cuFuncSetAttribute(smem): " + cu_err(r); return false; }
   }
+  return true;
+}
+
+// Compiles + loads a self-contained translation unit and resolves two entry points of it
+// (k2 shares k1's module: unload k1 only).
+inline bool build_text2(const std::string& tu, const char* entry1, const char* entry2, Kernel& k1, Kernel& k2,
+                        std::string& err, bool* from_cache = nullptr) {
+  if (!load(false, err)) return false;
+  std::vector<char> cubin = compile_text(tu, err, from_cache);
+  if (cubin.empty()) return false;
+  Api& a = api();
+  CUresult r = a.ModuleLoadData(&k1.mod, cubin.data());
+  if (r != CUDA_SUCCESS) { err = "cuModuleLoadData: " + cu_err(r); return false; }
+  r = a.ModuleGetFunction(&k1.fn, k1.mod, entry1);
+  if (r != CUDA_SUCCESS) { err = std::string("cuModuleGetFunction(") + entry1 + "): " + cu_err(r); return false; }
+  r = a.ModuleGetFunction(&k2.fn, k1.mod, entry2);
+  if (r != CUDA_SUCCESS) { err = std::string("cuModuleGetFunction(") + entry2 + "): " + cu_err(r); return false; }
+  k2.mod = nullptr;
   return true;
 }
 

@@ -14,6 +14,7 @@ using std::isnan; using std::isinf; using std::isfinite;
 #include "../../ahkab_b200/csrc/ac.cuh"
 #include "../../ahkab_b200/csrc/jit_gen.hpp"
 #include "../../ahkab_b200/csrc/biglin3.cuh"
+#include "../../ahkab_b200/csrc/biglin3_gen.hpp"
 
 using namespace ahk;
 
@@ -135,6 +136,30 @@ int emu_big3_sweep(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_
   std::vector<double> bpriv(n);
   for (int64_t t = 0; t < B * npts; t++) big3_solve_one<long long>(k, t, bpriv.data(), 1LL);   // private right-hand side, stride 1 (the device uses shared memory)
   return dyn;
+}
+
+// Text of the COMPILED static schedule (biglin3_gen.hpp) for this circuit / batch: returns its
+// length (truncated to cap - 1 bytes), -1 if no schedule / too large; *nf = factor values per
+// matrix, *npos = matrix positions (sizes of the F / Mv buffers the caller must provide).
+int emu_big3_gen_source(const ahk_circuit* c, const ahk_options* o, int n_vary, const int32_t* slots,
+                        char* buf, int64_t cap, int32_t* nf, int32_t* npos) {
+  try {
+    HostProg H;
+    build_program(c, H);
+    set_vary_slots(H, n_vary, slots);
+    Opts q; copy_opts(o, q);
+    Big3Sched S;
+    if (!big3_build(H, q, S)) return -1;
+    Big3Gen G;
+    if (!big3_codegen(H, q, S, G)) return -1;
+    if (nf) *nf = G.nf;
+    if (npos) *npos = S.npos;
+    if (buf && cap > 0) {
+      size_t m = std::min<size_t>(G.src.size(), (size_t)cap - 1);
+      std::memcpy(buf, G.src.data(), m); buf[m] = 0;
+    }
+    return (int)G.src.size();
+  } catch (...) { return -1; }
 }
 
 // Text of the generated jit_spec.h (jit_gen.hpp) for this circuit / batch / analysis / variant:

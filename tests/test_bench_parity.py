@@ -190,3 +190,22 @@ def test_c4_full_batch(gold, jit):
     assert (_np(rg['status']) & 1).all()
     assert np.abs(rws - g['t_rows']).max() <= 0.01 * g['t_rows'].max()
     _c4_waveform_check(_np(rg['t']), _np(rg['x']), rws, g, int(g['K']))
+
+
+@pytest.mark.parametrize('jit', [False, True], ids=['interpreted', 'compiled'])
+def test_c5_full_batch(gold, jit):
+    w = W.c5_r2r()                            # 4096 instances x 10 sweep points, n = 257
+    e = _engine(w, jit)
+    sw = common.c5_sweep()
+    n0 = e.jit_launch_count()
+    r = e.dc_sweep('V1', sw)
+    assert (e.jit_launch_count() > n0) == jit  # the compiled elimination schedule ran iff asked for
+    x = _np(r['x'])
+    assert (_np(r['status']) == 1).all() and (_np(r['iters']) == 2).all()
+    K = 64
+    o = _oracle(w, K).dc_sweep(0, sw, threads=0)
+    assert np.abs(x[:K] - o['x']).max() / np.abs(o['x']).max() < 1e-13
+    g = gold('c5')
+    eg = _engine(W.c5_r2r(int(g['K'])), jit)
+    xg = _np(eg.dc_sweep('V1', sw)['x'])
+    assert common.parity_tol(xg, g['x'], 256) < 1e-6

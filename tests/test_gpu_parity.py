@@ -256,23 +256,28 @@ def test_c5_big_linear_paths_agree(monkeypatch):
     o = _oracle(w).dc_sweep(0, sw)
     scale = np.abs(o['x']).max()
     outs = {}
-    for tag, env in (('static', {}), ('sparse', {'AHK_BIGLIN3_OFF': '1'}), ('dense', {'AHK_BIGLIN_DENSE': '1'}),
-                     ('overflow', {'AHK_BIGLIN_SC': '3'})):
+    for tag, env in (('static', {}), ('compiled', {}), ('sparse', {'AHK_BIGLIN3_OFF': '1'}),
+                     ('dense', {'AHK_BIGLIN_DENSE': '1'}), ('overflow', {'AHK_BIGLIN_SC': '3'})):
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
         e = _engine(w)
+        j0 = e.jit_launch_count()
+        e.set_jit('on' if tag == 'compiled' else 'off')   # compiled: the schedule as NVRTC-built code
         r = e.dc_sweep('V1', sw)
         x = _np(r['x'])
         assert (_np(r['status']) == 1).all() and (_np(r['iters']) == 2).all(), tag
         assert np.abs(x - o['x']).max() / scale < 1e-13, tag
         outs[tag] = x
+        assert (e.jit_launch_count() > j0) == (tag == 'compiled'), tag
         rop = e.op()
         assert np.abs(_np(rop['x']) - _oracle(w).op()['x']).max() / scale < 1e-13, tag
         for k_ in env:
             monkeypatch.delenv(k_)
     assert np.abs(outs['sparse'] - outs['dense']).max() / scale < 1e-14
-    # the static-schedule kernels do the same operations in the same order as the sparse one
+    # the static-schedule kernels do the same operations in the same order as the sparse one,
+    # interpreted or compiled
     assert np.abs(outs['static'] - outs['sparse']).max() / scale < 1e-15
+    assert np.abs(outs['compiled'] - outs['static']).max() / scale < 1e-15
 
 
 def test_static_schedule_hands_over_instances_with_other_pivots():
@@ -285,10 +290,13 @@ def test_static_schedule_hands_over_instances_with_other_pivots():
     w.params['R1h'][17] = 0.25
     sw = common.c5_sweep()
     o = _oracle(w).dc_sweep(0, sw)
-    r = _engine(w).dc_sweep('V1', sw)
     scale = np.abs(o['x']).max()
-    assert (_np(r['status']) == o['status']).all()
-    assert np.abs(_np(r['x']) - o['x']).max() / scale < 1e-12
+    for jit in ('off', 'on'):                      # interpreted / compiled schedule
+        e = _engine(w)
+        e.set_jit(jit)
+        r = e.dc_sweep('V1', sw)
+        assert (_np(r['status']) == o['status']).all(), jit
+        assert np.abs(_np(r['x']) - o['x']).max() / scale < 1e-12, jit
 
 
 @pytest.mark.parametrize('name', ['c2', 'c3', 'c5'])

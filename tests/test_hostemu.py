@@ -131,3 +131,55 @@ def test_static_schedule_path_for_large_linear_circuits():
     scale = np.abs(o['x']).max()
     assert np.abs(r['x'][served] - o['x'][served]).max() / scale < 1e-14
     assert (r['status'][served] == o['status'][served]).all() and (r['iters'][served] == 2).all()
+
+
+class _Big3CK(__import__('ctypes').Structure):
+    import ctypes as _C
+    _fields_ = [('vary', _C.c_void_p), ('B', _C.c_longlong), ('src_elem', _C.c_int), ('sweep', _C.c_void_p),
+                ('npts', _C.c_int), ('pt0', _C.c_int), ('ptc', _C.c_int), ('x_out', _C.c_void_p),
+                ('iters', _C.c_void_p), ('status', _C.c_void_p), ('resid', _C.c_void_p), ('F', _C.c_void_p),
+                ('Mv', _C.c_void_p), ('flagm', _C.c_void_p), ('ovf', _C.c_void_p)]
+
+
+@pytest.mark.parametrize('nodes', [256, 40])
+def test_compiled_schedule_host_build_matches_interpreted(nodes):
+    """biglin3_gen.hpp: the static elimination schedule emitted as straight-line source (what
+    NVRTC compiles for the GPU), built here for the host, gives the bits of the interpreted
+    schedule — incl. the hand-over of an instance whose pivots differ from the nominal ones."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    w = W.c5_r2r(6, nodes=nodes)
+    w.params['R1h'] = w.params['R1h'].copy()
+    w.params['R1h'][3] = 0.5                              # other pivot in column 0 -> dynamic kernel
+    e = emu.Emu(w.circuit(Circuit), w.batch(), w.opts)
+    lib = emu.lib()
+    c6 = e._common()
+    nf, npos = C.c_int32(0), C.c_int32(0)
+    args = (c6[0], c6[1], c6[3], c6[4])
+    n = lib.emu_big3_gen_source(*args, None, C.c_int64(0), C.byref(nf), C.byref(npos))
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    lib.emu_big3_gen_source(*args, buf, C.c_int64(n + 1), C.byref(nf), C.byref(npos))
+    d = tempfile.mkdtemp(prefix='ahk_b3gen_')
+    open(d + '/b3.cpp', 'wb').write(buf.value)
+    subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-DAHK_B3_HOST',
+                           '-o', d + '/b3.so', d + '/b3.cpp'])
+    so = C.CDLL(d + '/b3.so')
+    sw = common.c5_sweep()
+    B, nn, P = e.B, e.n, len(sw)
+    x = np.zeros((B, P, nn)); res = np.zeros((B, P, nn))
+    it = np.zeros((B, P), np.int32); st = np.zeros((B, P), np.int32)
+    F = np.zeros((2, nf.value, B)); Mv = np.zeros((npos.value, B))
+    fl = np.zeros((2, B), np.int32); ovf = np.zeros(B + 1, np.int32)
+    vary = np.ascontiguousarray(e.vary)
+    k = _Big3CK(vary.ctypes.data, B, 0, sw.ctypes.data, P, 0, P, x.ctypes.data, it.ctypes.data,
+                st.ctypes.data, res.ctypes.data, F.ctypes.data, Mv.ctypes.data, fl.ctypes.data,
+                ovf.ctypes.data)
+    so.b3_host_run(C.byref(k))
+    ref = e.big3_sweep(0, sw)
+    ok = ref['flags'] == 0
+    assert ok.sum() == B - 1 and (fl[0] == ref['flags']).all()
+    assert ovf[0] == 1 and ovf[1] == 3                    # handed to the dynamic kernel
+    for key, got in (('x', x), ('resid', res), ('iters', it), ('status', st)):
+        assert np.array_equal(got[ok], ref[key][ok]), key
