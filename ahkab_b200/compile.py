@@ -35,7 +35,9 @@ def _src_block(elem, ov, B):
     """[dc, |ac|, arg(ac), tf0..tf7] for a V/I source."""
     dc = ov.get('dc_value', elem.dc_value)
     if dc is None:
-        dc = 0.0
+        # VSource.V / ISource.I at time None (OP, DC): dc_value if there is one, else the
+        # waveform, which reads None as t = 0 (VSource.py:92-97, time_functions.py:441-442)
+        dc = float(elem._time_function(0.)) if elem.is_timedependent else 0.0
     flags = 0
     if 'ac_value' in ov:
         ac = ov['ac_value']

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32) k_biglin(const __grid_constant__ BigK k, c
       if (lane == 0) {
         for (int s = 0; s < p.nsrc; s++) {
           const SrcOp& so = p.src[s];
-          if (so.tf) continue;
+          // (a source with a waveform enters OP / DC with its dc_value: time is None, VSource.py:92-95)
           double v = (so.elem == k.src_elem) ? k.sweep[kp] : P(so.pbase);
           if (so.is_v) N[so.row0] = -1.0 * v;
           else { if (so.row0 >= 0) N[so.row0] += v; if (so.row1 >= 0) N[so.row1] -= v; }
@@ -269,6 +269,7 @@ struct BigLin {
   // the schedule COMPILED (biglin3_gen.hpp): module, factor-value count, buffers
   void* c3_mod[2] = {nullptr, nullptr};   // jit::Kernel objects (factor, solve), owned here as opaque pointers
   int c3_state = 0;                       // 0 not tried for this epoch, 1 ready, -1 unavailable
+  int last_path = -1;                     // ahk_big_stats: 0 dense workspace, 1 sparse dynamic, 2 static schedule, 3 compiled schedule
   int c3_nf = 0, c3_npos = 0;
   double* c3_F = nullptr; double* c3_Mv = nullptr; int* c3_flagm = nullptr;
   size_t c3_F_cap = 0, c3_Mv_cap = 0, c3_flag_cap = 0;

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(32) k_biglin2(const __grid_constant__ Big2K k,
           for (int r = 0; r < n; r++) bb[r * PC + j] = 0.0;
           for (int s = 0; s < p.nsrc; s++) {
             const SrcOp& so = p.src[s];
-            if (so.tf) continue;
+            // (a source with a waveform enters OP / DC with its dc_value: time is None, VSource.py:92-95)
             const double v = (so.elem == k.src_elem) ? k.sweep[k0 + j] : P(so.pbase);
             if (so.is_v) bb[so.row0 * PC + j] = v;      // N[row] = -V  =>  -N = V
             else { if (so.row0 >= 0) bb[so.row0 * PC + j] -= v; if (so.row1 >= 0) bb[so.row1 * PC + j] += v; }

@@ -256,7 +256,7 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid, double* b, IT bT) {
     for (int r = 0; r < n; r++) b[(IT)r * bT] = 0.0;
     for (int s = 0; s < p.nsrc; s++) {
       const SrcOp& so = p.src[s];
-      if (so.tf) continue;
+      // (a source with a waveform enters OP / DC with its dc_value: time is None, VSource.py:92-95)
       const double v = (so.elem == k.src_elem) ? k.sweep[pt] : P(so.pbase);
       if (so.is_v) b[(IT)so.row0 * bT] = v;      // N[row] = -V  =>  -N = V
       else { if (so.row0 >= 0) b[(IT)so.row0 * bT] -= v; if (so.row1 >= 0) b[(IT)so.row1 * bT] += v; }

@@ -859,7 +859,10 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
       for (int k = 0; k < p.nsrc; k++) {
         const SrcOp& s = p.src[k];
         if (!s.tf) continue;
-        double v = tf_eval(s.tf, c.sm + c.L->Pv + s.ppb + 1, time);
+        // time None (OP / DC sweep, with_tran false): VSource.V / ISource.I return dc_value
+        // (VSource.py:92-95; a missing dc_value is staged as the waveform at t = 0)
+        double v = with_tran ? tf_eval(s.tf, c.sm + c.L->Pv + s.ppb + 1, time)
+                             : ((s.elem == c.dc_src) ? c.dc_val : c.PP(s.ppb));
         if (s.is_v) Nd[s.row0] += -1 * v;
         else { if (s.row0 >= 0) Nd[s.row0] += v; if (s.row1 >= 0) Nd[s.row1] -= v; }
       }

@@ -262,11 +262,14 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
         for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
           ck.pt0 = pt0; ck.ptc = std::min(ptc, npts - pt0);
-          const long long TT = B * ck.ptc;
-          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)((TT + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
+          // 32 instances x pw points per block (pw <= 8 warps, as even a split of the chunk as possible)
+          int pw = (ck.ptc + (ck.ptc + 7) / 8 - 1) / ((ck.ptc + 7) / 8);
+          if (const char* f = getenv("AHK_BIGLIN3C_PW")) pw = std::max(1, std::min(8, atoi(f)));   // tuning
+          const long long nbi = (B + 31) / 32, nby = (ck.ptc + pw - 1) / pw;
+          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)(nbi * nby), 32 * pw, 0, s, &ck, lerr)) { err = lerr; return -1; }
           launches++; g_jit_launches++;
         }
-        staged = true;
+        staged = true; last_path = 3;
       }
     }
     if (s3_ok && !staged) {
@@ -332,13 +335,14 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       }
       if (getenv("AHK_DEBUG"))
         fprintf(stderr, "[ahk] biglin3 n=%d slots %d, %lld instances, %d point(s) per solve launch\n", n, s3_nslot, B, ptc);
-      staged = true;
+      staged = true; last_path = 2;
     }
   }
 
   // ---- 1. sparse shared-memory kernel (n <= 1024) ----------------------------------------
   const int W = (n + 31) / 32;
   bool sparse = !staged && W <= 32 && !getenv("AHK_BIGLIN_DENSE");
+  if (!staged) last_path = sparse ? 1 : 0;
   int SC = 0, PC = 0;
   Big2Smem S2;
   if (sparse) {
@@ -927,6 +931,32 @@ int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks) {
 int ahk_last_launch(const ahk_engine* e, int32_t* out8) {
   if (!e || !out8) return fail("null argument");
   for (int i = 0; i < 8; i++) out8[i] = e->last[i];
+  return 0;
+}
+
+int ahk_big_stats(const ahk_engine* e, int64_t* out8) {
+  if (!e || !out8) return fail("null argument");
+  for (int i = 0; i < 8; i++) out8[i] = 0;
+  const BigLin& b = e->big;
+  out8[0] = b.last_path;
+  if (const Big3Sched* S = b.s3_S) {
+    // flop the schedule executes: per pivot step nl divisions-as-multiplies + 1 reciprocal,
+    // nl * nu multiply-subtracts (2 flop); substitutions: 2 flop per stored multiplier / row entry
+    long long ff = 0, fs = 0, nf[2] = {0, 0};
+    for (int m = 0; m < 2; m++)
+      for (int kk = 0; kk < S->n; kk++) {
+        const Big3Step& st = S->step[m * S->n + kk];
+        ff += 1 + st.nl + 2ll * st.nl * st.nu;
+        fs += 2ll * st.nl + 2ll * st.nu + 1;
+        nf[m] += 1 + st.nl + st.nu;
+      }
+    out8[1] = ff;                                   // factorisation flop per instance (both matrices)
+    out8[2] = fs + 2ll * e->H.hdr.npos + 2ll * S->n;   // flop per (instance, point): substitutions + residual mat-vec + update
+    out8[3] = nf[0] > nf[1] ? nf[0] : nf[1];        // factor values stored per matrix
+    out8[4] = S->npos;
+    out8[5] = S->nslot;
+    out8[6] = S->n;
+  }
   return 0;
 }
 

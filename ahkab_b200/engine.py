@@ -148,6 +148,17 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(zip(('vid', 'NC', 'R', 'G', 'threads', 'blocks', 'jit', 'analysis'), list(out)))
 
+    def big_stats(self):
+        """ahk_big_stats as a dict (n > 64 linear circuits: path taken, executed flop counts)."""
+        out = (C.c_int64 * 8)()
+        if self.lib.ahk_big_stats(self._h, out) != 0:
+            raise EngineError(self._err())
+        d = dict(zip(('path', 'factor_flop', 'point_flop', 'nf', 'npos', 'nslot', 'n', '_'), list(out)))
+        d['path'] = {-1: None, 0: 'dense workspace', 1: 'sparse dynamic', 2: 'static schedule',
+                     3: 'static schedule, compiled'}[d['path']]
+        del d['_']
+        return d
+
     def jit_launch_count(self):
         return int(self.lib.ahk_jit_launch_count())
 

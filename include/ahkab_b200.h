@@ -213,6 +213,13 @@ int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks);
  * out8 = { variant id (>= 1000: free shape), matrix columns, rows per lane, lanes per
  * instance, threads per block, blocks, 1 if circuit-specialised, analysis 0 OP/DC 1 tran 2 AC }. */
 int ahk_last_launch(const ahk_engine* e, int32_t* out8);
+/* Large linear circuits (n > 64): which kernels served the last call and what the static
+ * elimination schedule executes (diagnostics; bench.py's roofline): out8 = { path (0 dense
+ * workspace, 1 sparse dynamic, 2 static schedule, 3 static schedule compiled by NVRTC; -1 none
+ * yet), factorisation flop per instance (both matrices), flop per (instance, sweep point),
+ * factor values stored per matrix, structural matrix entries, value slots incl. fill-in,
+ * unknowns, 0 }. */
+int ahk_big_stats(const ahk_engine* e, int64_t* out8);
 /* Launches through specialised kernels / NVRTC compilations so far (all engines). */
 int64_t ahk_jit_launch_count(void);
 int64_t ahk_jit_build_count(void);

@@ -31,7 +31,14 @@ def run_one(ahkab, name, spec):
         out['sweep'], out['x'] = a[0], a[1:].T
         out['keys'] = np.array(r.keys())
     elif kind == 'ac':
-        opr = None
+        # x0='op' (non-linear circuits): the reference computes the linearisation point itself
+        # when none is given (ac.py:237-262)
+        # when none is given (ac.py:237-262).  The EKV device objects carry the warm start of
+        # their inner solve from call to call (ekv.py:575-586), so the AC run gets a circuit
+        # whose devices have seen nothing but that one op_analysis.
+        if an.pop('x0', None) == 'op':
+            out['op'] = ahkab.run(circ, ahkab.new_op(verbose=0))['op'].asarray().ravel()
+            circ = spec['build'](ahkab.Circuit, tf)
         r = ahkab.run(circ, ahkab.new_ac(x0=None, verbose=0, **an))['ac']
         a = r.asarray()
         out['f'], out['x'] = a[0].real, a[1:].T

@@ -108,13 +108,20 @@ class Oracle(object):
                         C.c_int(threads))
         return dict(t=t, x=x, rows=rows, counters=cnt, status=st)
 
-    def ac(self, omegas, x_op=None, threads=0):
+    def ac(self, omegas, x_op=None, threads=0, op_first=False, settle=0):
+        """op_first: the reference's flow when no linearisation point is given (OP inside, the
+        device state of that Newton run carries into J); settle: extra device evaluations at
+        the linearisation point before J is taken (see ahko_ac2)."""
         B, n = self.B, self.n
         om = np.ascontiguousarray(omegas, np.float64)
         x = np.zeros((B, len(om), n), np.complex128)
         st = np.zeros(B, np.int32)
         x_op = None if x_op is None else np.ascontiguousarray(x_op, np.float64)
-        lib().ahko_ac(*self._common(), _dp(x_op), _dp(om), C.c_int(len(om)),
-                      x.ctypes.data_as(C.POINTER(C.c_double)), _ip(st),
-                      C.c_int(threads))
-        return dict(x=x, status=st)
+        xo = np.zeros((B, n))
+        lib().ahko_ac2(*self._common(), _dp(x_op), _dp(om), C.c_int(len(om)),
+                       x.ctypes.data_as(C.POINTER(C.c_double)), _ip(st),
+                       C.c_int(threads), C.c_int(int(op_first)), C.c_int(int(settle)), _dp(xo))
+        return dict(x=x, status=st, op=xo)
+
+    def ac_op_first(self, omegas, threads=0):
+        return self.ac(omegas, threads=threads, op_first=True)

@@ -56,6 +56,7 @@ def _check(rc):
 
 class Emu(_oracle.Oracle):
     """Same constructor as Oracle; methods run the emulated engine instead."""
+    ac_op_first = None     # (the engine's AC takes the linearisation point from its own OP call)
 
     def _common6(self):
         return self._common()

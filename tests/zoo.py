@@ -101,6 +101,68 @@ def pwl_rc(Circuit, tf):
     return c
 
 
+def acnl(Circuit, tf):
+    """tests/acnl/test_acnl.py: common-source EKV amplifier — AC linearised around the
+    operating point (ac.py:417-443 _generate_J)."""
+    c = Circuit('CS amplifier')
+    c.add_vsource('vin', '1', '0', dc_value=3, ac_value=1)
+    c.add_vsource('vdd', '3', '0', dc_value=30)
+    c.add_resistor('Rd', '3', '2', 10e3)
+    c.add_capacitor('Cd', '3', '2', 40e-12)
+    c.add_resistor('Rs', '4', '0', 1e3)
+    c.add_capacitor('Cs', '4', '0', 4e-6)
+    c.add_model('ekv', 'ekv0', {'TYPE': 'n', 'VTO': .4, 'KP': 1e-2})
+    c.add_mos('m1', '2', '1', '4', '0', w=100e-6, l=1e-6, model_label='ekv0')
+    return c
+
+
+def diode_ac(Circuit, tf):
+    """diode + series resistance biased through a resistor: small-signal AC of a diode
+    (diode.py:get_drive_ports / g), second non-linear AC case."""
+    c = Circuit('diode ac')
+    c.add_model('diode', 'dm', dict(IS=1e-14, N=1.5, RS=2.))
+    c.add_vsource('V1', 'a', c.gnd, dc_value=1.2, ac_value=1.)
+    c.add_resistor('R1', 'a', 'b', 1e3)
+    c.add_diode('D1', 'b', 'c', 'dm')
+    c.add_resistor('R2', 'c', c.gnd, 100.)
+    c.add_capacitor('C1', 'c', c.gnd, 1e-9)
+    return c
+
+
+def am_src(Circuit, tf):
+    """tests/amckt: AM voltage / current sources into resistors (time_functions.py:672-728)."""
+    c = Circuit('am')
+    c.add_vsource('V1', '1', c.gnd, dc_value=0., function=tf.am(sa=10, oc=1, fm=100, fc=1e3, td=1e-3))
+    c.add_resistor('R1', '1', c.gnd, 1.)
+    c.add_vsource('V2', '2', c.gnd, dc_value=0., function=tf.am(sa=2.5, oc=4, fm=100, fc=1e3, td=1e-3))
+    c.add_resistor('R2', '2', c.gnd, 1.)
+    c.add_isource('I3', '3', c.gnd, dc_value=0., function=tf.am(sa=10, oc=1, fm=1e3, fc=100, td=1e-3))
+    c.add_resistor('R3', '3', c.gnd, 1.)
+    c.add_capacitor('C3', '3', c.gnd, 1e-5)
+    return c
+
+
+def sffm_src(Circuit, tf):
+    """tests/sffmckt: single-frequency FM sources (time_functions.py:610-670)."""
+    c = Circuit('sffm')
+    c.add_vsource('V1', '1', c.gnd, dc_value=0., function=tf.sffm(vo=0, va=1e-3, fc=20e3, mdi=10, fs=5e3, td=2e-5))
+    c.add_resistor('R1', '1', '1b', 1.)
+    c.add_capacitor('C1', '1b', c.gnd, 1e-6)
+    c.add_isource('I2', '2', c.gnd, dc_value=0., function=tf.sffm(vo=0, va=1, fc=20e3, mdi=10, fs=5e3, td=0.))
+    c.add_resistor('R2', '2', c.gnd, 1.)
+    return c
+
+
+def exp_src(Circuit, tf):
+    """tests/time_functions: exponential source (time_functions.py:534-608) into an RC."""
+    c = Circuit('exp')
+    c.add_vsource('V3', 'in', c.gnd, dc_value=0.,
+                  function=tf.exp(v1=.5, v2=-.05, td1=10e-6, tau1=20e-6, td2=400e-6, tau2=30e-6))
+    c.add_resistor('R1', 'in', 'out', 1e3)
+    c.add_capacitor('C1', 'out', c.gnd, 1e-8)
+    return c
+
+
 ZOO = {
     'rectifier': dict(build=rectifier, an=dict(kind='tran', tstart=0., tstop=2e-3, tstep=1e-5,
                                                method='TRAP', use_step_control=True, x0='op')),
@@ -117,6 +179,20 @@ ZOO = {
                                              method='GEAR5', use_step_control=True, x0='op')),
     'pwl_rc': dict(build=pwl_rc, an=dict(kind='tran', tstart=0., tstop=10e-6, tstep=1e-7,
                                          method='GEAR2', use_step_control=True, x0='op')),
+    'rc_gear1': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                             method='GEAR1', use_step_control=True, x0='op')),
+    'rc_gear4': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                             method='GEAR4', use_step_control=True, x0='op')),
+    'rc_gear6': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
+                                             method='GEAR6', use_step_control=True, x0='op')),
+    'acnl': dict(build=acnl, an=dict(kind='ac', start=1., stop=100e6, points=65, x0='op')),
+    'diode_ac': dict(build=diode_ac, an=dict(kind='ac', start=1e3, stop=1e9, points=31, x0='op')),
+    'am_src': dict(build=am_src, an=dict(kind='tran', tstart=0., tstop=6e-3, tstep=1e-5,
+                                         method='TRAP', use_step_control=True, x0='op')),
+    'sffm_src': dict(build=sffm_src, an=dict(kind='tran', tstart=0., tstop=.5e-3, tstep=.5e-6,
+                                             method='TRAP', use_step_control=True, x0='op')),
+    'exp_src': dict(build=exp_src, an=dict(kind='tran', tstart=0., tstop=6e-4, tstep=1e-6,
+                                           method='GEAR2', use_step_control=True, x0='op')),
     'rc_ie': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
                                           method='IMPLICIT_EULER', use_step_control=True, x0='op')),
 }
