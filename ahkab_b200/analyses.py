@@ -80,7 +80,7 @@ def get_engine(circ, batch=None, opts=None):
     else:
         eng.circ = circ
         eng.flat = flat
-        eng.set_vary(flat.vary)
+        eng.set_vary_flat(flat)
         o = options.snapshot()
         if opts:
             o.update(opts)
@@ -171,7 +171,7 @@ def _run_op(circ, eng, guess=True, x0=None, outfile=None, verbose=0):
     if not options.dc_use_guess:
         guess = False
     raw = eng.op(x0=_resolve_x0(x0, eng), use_guess=guess)
-    return results.op_solution(circ, raw)
+    return results.op_solution(circ, raw, engine=eng)
 
 
 def _run_dc(circ, eng, start, stop, step, source, sweep_type='LINEAR',
@@ -204,7 +204,7 @@ def _run_dc(circ, eng, start, stop, step, source, sweep_type='LINEAR',
         raise ValueError(".DC: source %s was not found." % source)
     sweep = np.array(list(it), dtype=np.float64)
     raw = eng.dc_sweep(src, sweep, x0=_resolve_x0(x0, eng), use_guess=guess)
-    return results.dc_solution(circ, raw, sweepvar=sweep_label, stype=stype)
+    return results.dc_solution(circ, raw, sweepvar=sweep_label, stype=stype, engine=eng)
 
 
 def _run_tran(circ, eng, tstart, tstep, tstop, method=None,
@@ -253,7 +253,7 @@ def _run_ac(circ, eng, start, points, stop, sweep_type=None, x0=None,
                                "available.")
         x_op = op.raw['x']
     raw = eng.ac(omegas, x_op=x_op if circ.is_nonlinear() else None)
-    return results.ac_solution(circ, raw, stype)
+    return results.ac_solution(circ, raw, stype, engine=eng)
 
 
 _analysis = {'op': _run_op, 'dc': _run_dc, 'tran': _run_tran, 'ac': _run_ac}
@@ -278,11 +278,16 @@ def run(circ, an_list=None, batch=None):
         an_item = an_list.pop(0)
         an_type = an_item.pop('type')
         if 'x0' in an_item and isinstance(an_item['x0'], str):
-            an_item['x0'] = x0s.get(an_item['x0'])
+            label = an_item['x0']
+            if label == 'op+ic' and 'op' in x0s and 'op+ic' not in x0s:
+                # (built when first asked for: a clone + scatter on the device per OP otherwise)
+                x0s['op+ic'] = icmodified_x0(circ, x0s['op'], batch)
+                _x0s.update(x0s)
+            an_item['x0'] = x0s.get(label)
         r = _analysis[an_type](circ, eng, **an_item)
         res.update({an_type: r})
         if an_type == 'op':
-            x0s['op'] = r
-            x0s['op+ic'] = icmodified_x0(circ, r, batch)
+            x0s = {'op': r}
+            _x0s.pop('op+ic', None)
             _x0s.update(x0s)
     return res

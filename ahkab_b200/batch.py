@@ -14,6 +14,8 @@ class ParamBatch(object):
     def __init__(self, B):
         self.B = int(B)
         self._ov = {}
+        self._version = 0        # bumped by set(): compile.flatten caches per (circuit, version)
+        self._flat_cache = None
 
     def set(self, owner, attr, values):
         """owner: element part_id or model label (case-insensitive);
@@ -25,6 +27,8 @@ class ParamBatch(object):
         if not np.iscomplexobj(v):
             v = v.astype(np.float64)
         self._ov[(owner.lower(), attr)] = v
+        self._version += 1
+        self._flat_cache = None
         return self
 
     def __setitem__(self, key, values):

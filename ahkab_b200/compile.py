@@ -59,8 +59,59 @@ def _src_block(elem, ov, B):
     return [dc, abs_ac, arg_ac] + tfp, flags, tfk
 
 
+_SCALARS = (int, float, bool, str, type(None), complex)
+
+
+def _scalars(o):
+    """The plain-valued attributes of an element / model / device / waveform object."""
+    out = []
+    for k, v in vars(o).items():
+        if type(v) in _SCALARS or isinstance(v, (np.floating, np.integer)):
+            out.append((k, v))
+        elif isinstance(v, np.ndarray):
+            out.append((k, v.tobytes()))
+        elif type(v) in (list, tuple) and all(type(t) in _SCALARS for t in v):
+            out.append((k, tuple(v)))
+    return tuple(out)
+
+
+def circuit_signature(circ):
+    """Everything `flatten` reads from the circuit, as a hashable value: the elements (in
+    order) with their nodes / values, their device blocks, waveforms and models.  Elements
+    are plain mutable objects (`r.value = ...` is legal, as in the reference), so a cached
+    flattening is only reused while this signature is unchanged."""
+    sig = [circ.get_nodes_number()]
+    for e in circ:
+        item = [type(e).__name__, _scalars(e)]
+        for sub in ('device', '_time_function'):
+            so = getattr(e, sub, None)
+            if so is not None and hasattr(so, '__dict__'):
+                item.append(_scalars(so))
+        m = getattr(e, 'model', None)
+        if m is not None:
+            item.append(id(m))
+        sig.append(tuple(item))
+    for label, m in circ.models.items():
+        sig.append((label, id(m), _scalars(m)))
+    return tuple(sig)
+
+
 def flatten(circ, batch=None):
-    """Flatten `circ`; with `batch` also build the vary tables."""
+    """Flatten `circ`; with `batch` also build the vary tables.  The result is cached on the
+    batch (keyed by the circuit's signature and the batch's version), so `run()` on the same
+    circuit and batch — analysis after analysis — flattens once."""
+    if batch is None:
+        return _flatten(circ, None)
+    sig = circuit_signature(circ)
+    hit = getattr(batch, '_flat_cache', None)
+    if hit is not None and hit[0] == batch._version and hit[1] == sig:
+        return hit[2]
+    flat = _flatten(circ, batch)
+    batch._flat_cache = (batch._version, sig, flat)
+    return flat
+
+
+def _flatten(circ, batch=None):
     B = batch.B if batch is not None else None
     vals = []      # per slot: float or (B,) array
     names = []     # per slot: (owner, name)
@@ -83,7 +134,7 @@ def flatten(circ, batch=None):
             if _is_arr(v):
                 if B is None or v.shape != (B,):
                     raise ValueError("bad batch array for %s.%s" % (owner, nm))
-                v = v.astype(np.float64)
+                v = np.asarray(v, dtype=np.float64)     # (no copy: ParamBatch stores float64)
             else:
                 v = float(v)
             vals.append(v)
@@ -280,6 +331,7 @@ def flatten(circ, batch=None):
     out.vary = (np.ascontiguousarray(np.stack(vary_rows))
                 if vary_rows else np.zeros((0, B or 0)))
     out.B = B
+    out.vary_pinned = None      # pinned torch copy of `vary`, made by the engine on first upload
     if G is None:
         out.n_guess = 0
         out.guess_G = np.zeros((out.n, 0))
@@ -299,7 +351,13 @@ def flatten(circ, batch=None):
 
 
 def topology_key(flat):
-    """Hashable identity of the topology + nominal values + vary slot set
+    """Hashable identity of the topology + nominal values of the fixed slots + vary slot set
     (what an engine handle is specific to)."""
-    return (flat.elems.tobytes(), flat.nominal.tobytes(),
+    nom = flat.nominal
+    if len(flat.vary_slots):
+        # a varied slot's nominal is just the first instance's value (every instance overrides
+        # it): it must not make a new batch of the same sweep look like a new circuit
+        nom = nom.copy()
+        nom[flat.vary_slots] = 0.0
+    return (flat.elems.tobytes(), nom.tobytes(),
             flat.vary_slots.tobytes(), flat.guess_G.tobytes())

@@ -262,11 +262,8 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
         for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
           ck.pt0 = pt0; ck.ptc = std::min(ptc, npts - pt0);
-          // 32 instances x pw points per block (pw <= 8 warps, as even a split of the chunk as possible)
-          int pw = (ck.ptc + (ck.ptc + 7) / 8 - 1) / ((ck.ptc + 7) / 8);
-          if (const char* f = getenv("AHK_BIGLIN3C_PW")) pw = std::max(1, std::min(8, atoi(f)));   // tuning
-          const long long nbi = (B + 31) / 32, nby = (ck.ptc + pw - 1) / pw;
-          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)(nbi * nby), 32 * pw, 0, s, &ck, lerr)) { err = lerr; return -1; }
+          const long long TT = B * ck.ptc;
+          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)((TT + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
           launches++; g_jit_launches++;
         }
         staged = true; last_path = 3;

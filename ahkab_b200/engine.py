@@ -52,7 +52,7 @@ class Engine(object):
         self._slots = np.ascontiguousarray(self.flat.vary_slots, np.int32)
         self._vary_host = None
         self.vary = None
-        self.set_vary(self.flat.vary)
+        self.set_vary_flat(self.flat)
 
     # -- plumbing ---------------------------------------------------------------
     def _err(self):
@@ -100,6 +100,17 @@ class Engine(object):
         if self.vary.numel():
             self.B = self.vary.shape[1]
         return self
+
+    def set_vary_flat(self, flat):
+        """Upload the per-instance values of a flattened (circuit, batch).  The flattening is
+        cached on the batch (compile.flatten) and keeps a PINNED copy of its value matrix,
+        made here on first use: repeated runs on the same batch copy host->device straight
+        from it, with no staging copy on the host."""
+        if flat.vary.size == 0:
+            return self.set_vary(flat.vary)
+        if getattr(flat, 'vary_pinned', None) is None:
+            flat.vary_pinned = torch.from_numpy(flat.vary).pin_memory()
+        return self.set_vary(flat.vary_pinned)
 
     def set_options(self, **kw):
         self.opts.update(kw)
@@ -417,6 +428,40 @@ class Engine(object):
                 self._pinned[key] = buf
             buf.copy_(src, non_blocking=True)
             out[k] = buf
+        return out
+
+    def to_host_owned(self, raw):
+        """The whole packed result set of one call in ONE device->host copy, returned as
+        numpy arrays that OWN their pinned buffer: it comes from a per-engine pool and goes
+        back to it when the last array / view of this result set is garbage collected, so
+        results of earlier calls never change under the caller (unlike `to_host`, whose
+        cached buffers suit a benchmark loop) and no memory is pinned per call.
+        Synchronous: the arrays are valid on return."""
+        import weakref
+        base, layout = raw['_packed']
+        nbytes = int(base.numel())
+        pool = self.__dict__.setdefault('_host_pool', [])
+        hb = None
+        for i, t in enumerate(pool):            # smallest free buffer that fits
+            if t.numel() >= nbytes and (hb is None or t.numel() < hb.numel()):
+                hb, at = t, i
+        if hb is not None:
+            pool.pop(at)
+        else:
+            hb = torch.empty(max(4096, int(nbytes * 1.125)), dtype=torch.uint8, pin_memory=True)
+        with torch.cuda.device(self.device):
+            hb[:nbytes].copy_(base, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        arr = hb.numpy()                        # every view below keeps `arr` alive as its base
+
+        def give_back(pool=pool, hb=hb):
+            if len(pool) < 8:
+                pool.append(hb)
+        weakref.finalize(arr, give_back)
+        npd = {torch.float64: np.float64, torch.int32: np.int32}
+        out = {}
+        for k, shape, dtype, off, nb, _nb in layout:
+            out[k] = arr[off:off + nb].view(npd[dtype]).reshape(shape)
         return out
 
     def pinned_bytes(self, nbytes):

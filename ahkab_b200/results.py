@@ -46,16 +46,29 @@ class solution(object):
     """Base: dict-like access by variable name (results.py:127-243)."""
     sol_type = None
 
-    def __init__(self, circ, raw):
+    def __init__(self, circ, raw, engine=None):
         self.netlist_title = circ.title
         self.raw = raw          # dict of (device) tensors from the engine
+        self._engine = engine   # (for the one-copy host read of the packed result set)
         self._np = {}
         self.variables = []
         self.units = {}
 
     def _get(self, key):
         if key not in self._np:
-            self._np[key] = _host(self.raw[key])
+            pk = self.raw.get('_packed') if isinstance(self.raw, dict) else None
+            if self._engine is not None and pk is not None and not self._np.get('_fetched'):
+                # first host access: every tensor of the call in one device->host copy
+                # (Engine.to_host_owned; the arrays own their pinned buffer)
+                host = self._engine.to_host_owned(self.raw)
+                self._np['_fetched'] = True
+                for k, v in host.items():
+                    rv = self.raw.get(k)
+                    if rv is not None and hasattr(rv, 'is_complex') and rv.is_complex():
+                        v = v.view(np.complex128).reshape(tuple(rv.shape))
+                    self._np.setdefault(k, v)
+            if key not in self._np:
+                self._np[key] = _host(self.raw[key])
         return self._np[key]
 
     def _index(self, name):
@@ -126,8 +139,8 @@ class op_solution(solution):
     """results.py:245-551 with a batch axis: sol['VN1'] -> (B,)."""
     sol_type = "OP"
 
-    def __init__(self, circ, raw):
-        solution.__init__(self, circ, raw)
+    def __init__(self, circ, raw, engine=None):
+        solution.__init__(self, circ, raw, engine)
         self.variables, self.units = _varnames(circ, upper=True)
 
     @property
@@ -158,8 +171,8 @@ class dc_solution(solution):
     """results.py:714-782: variables[0] is the sweep variable."""
     sol_type = "DC"
 
-    def __init__(self, circ, raw, sweepvar, stype):
-        solution.__init__(self, circ, raw)
+    def __init__(self, circ, raw, sweepvar, stype, engine=None):
+        solution.__init__(self, circ, raw, engine)
         names, units = _varnames(circ, upper=False)
         self.variables = [sweepvar] + names
         self.units = dict(units)
@@ -190,8 +203,8 @@ class tran_solution(solution):
     """results.py:784-853: 'T' then the unknowns; no row for tstart."""
     sol_type = "TRAN"
 
-    def __init__(self, circ, raw, tstart, tstop, method):
-        solution.__init__(self, circ, raw)
+    def __init__(self, circ, raw, tstart, tstop, method, engine=None):
+        solution.__init__(self, circ, raw, engine)
         names, units = _varnames(circ, upper=True)
         self.variables = ["T"] + names
         self.units = dict(units)
@@ -240,8 +253,8 @@ class ac_solution(solution):
     """results.py:554-712: 'f' [Hz] then complex unknowns."""
     sol_type = "AC"
 
-    def __init__(self, circ, raw, stype):
-        solution.__init__(self, circ, raw)
+    def __init__(self, circ, raw, stype, engine=None):
+        solution.__init__(self, circ, raw, engine)
         names, units = _varnames(circ, upper=False)
         self.variables = ["f"] + names
         self.units = dict(units)

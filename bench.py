@@ -93,6 +93,7 @@ AC_FLOP = 4 * LU(14) + 8 * 14 ** 2            # per (instance, frequency)
 C5_FLOP = (2 * LU(257) - 2 * 2 * 257 ** 2) / 10.0 + 2 * (2 * 257 ** 2 + 2 * 257 ** 2)
 
 
+HEADLINE = 'c2'     # --workload
 JIT_MODE = 'auto'   # --jit: circuit-specialised kernels (ahk_set_jit); auto = batches >= 1024 here
 
 
@@ -184,6 +185,25 @@ class Runner(object):
         host = self.pipe.run(lambda sub, lo, hi, x: self.step(sub, x.get('x0')),
                              self.vary_host, extra)
         return host, host
+
+    def api(self, fresh=False):
+        """The drop-in call a user of the reference makes: `ahkab.run(circ, analysis,
+        batch=ParamBatch)` from host numpy parameters to host numpy results (every result
+        array of the analysis), through ahkab_b200.analyses.run and the results objects."""
+        import ahkab_b200 as ahkab
+        W, n = self.W, self.name
+        if fresh or not hasattr(self, 'api_batch'):
+            self.api_batch = self.w.batch(self.lo, self.hi)     # ParamBatch of host numpy arrays
+        if n == 'c2':
+            r = ahkab.run(self.circ, ahkab.new_op(), batch=self.api_batch)['op']
+            return r.x, r.iterations, r.status
+        if n == 'c1':
+            r = ahkab.run(self.circ, ahkab.new_ac(x0=None, **W.C1_AC), batch=self.api_batch)['ac']
+            return r._get('x'), r.status
+        if n == 'c5':
+            r = ahkab.run(self.circ, ahkab.new_dc(**W.C5_DC), batch=self.api_batch)['dc']
+            return r._get('x'), r.status
+        return None
 
     def e2e_dist(self, d2h=True, ev=None):
         """One end-to-end step of a sharded run: pinned H2D of this rank's shard, the
@@ -462,6 +482,42 @@ def cpu_measure(name, steps, warmup):
         dt / steps * 1e3
 
 
+# instances per host core of the Python-reference sample (one ahkab.run per instance:
+# ~3 ms c2, 20 ms c1, 0.35 s c3 / c5, 16 s c4 per instance on one core)
+PY_SAMPLE_PER_CORE = dict(c2=256, c1=64, c3=4, c4=1, c5=4)
+
+
+def python_reference(name, quick=False):
+    """The reference itself — ahkab v0.18's pure-Python `ahkab.run`, one Circuit per instance,
+    BASELINE.md §3 — on a bounded sample of the same seeded batch: one process, and a pool
+    over all host cores.  None when the package is not on this machine (baseline/_ref is the
+    offline pip install recorded in DESIGN.md §7; it travels to the GPU box)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    try:
+        import ref_loop
+        if ref_loop.reference_path() is None:
+            return None
+        cores = host_threads()
+        per = PY_SAMPLE_PER_CORE[name]
+        if quick:
+            per = max(1, per // 4)
+        n1 = max(1, per // 2) if name != 'c4' else 0          # (c4: 16 s per instance, pool only)
+        out = {"kind": "reference", "unit": UNITS[name],
+               "what": "ahkab.run loop (pure Python, unmodified reference via oracle/refshim.py), "
+                       "one Circuit per instance", "path": ref_loop.reference_path()}
+        if n1:
+            u, dt = ref_loop.timed_loop(name, n1, FULL_B[name], 1)
+            out["one_core"] = {"value": u / dt, "instances": n1, "seconds": dt}
+        cnt = per * cores
+        u, dt = ref_loop.timed_loop(name, cnt, FULL_B[name], cores)
+        out.update({"value": u / dt, "cores": cores, "instances": cnt, "seconds": dt,
+                    "sample": "%d of %d instances of the same seeded batch, multiprocessing pool "
+                              "over %d processes" % (cnt, FULL_B[name], cores)})
+        return out
+    except Exception as ex:      # the Python reference is a secondary figure: never fail the arm
+        return {"kind": "reference", "unavailable": repr(ex)[:200]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -481,6 +537,10 @@ def run_reference(args, rank):
                 "e2e": {"value": cb['value'], "unit": UNITS[name], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "config": config_of(name)}
+        # beside the C port: the real Python reference on a (smaller) sample
+        py = python_reference(name, quick=(i != 0))
+        if py is not None:
+            line["python_reference"] = py
         if i == 0:
             out = line
         else:
@@ -534,6 +594,32 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
         d2h_bytes, h2d_bytes = r.d2h_bytes(host), r.h2d
     units_e = all_sum(r.units(raw_e), dist_on, device)
     e2e_value = units_e * steps / (ms_e * 1e-3)
+    e2e_api = None
+    if world == 1 and name in ('c2', 'c1', 'c5'):
+        # the same step through the drop-in API (host numpy in, host numpy out), host wall clock
+        for _ in range(3):
+            out_api = r.api()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out_api = r.api()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out_api = r.api(fresh=True)
+        torch.cuda.synchronize()
+        dt_fresh = (time.perf_counter() - t0) / steps
+        e2e_api = {"value": units_e / dt, "unit": UNITS[name], "ms_per_step": dt * 1e3,
+                   "vs_e2e": (dt * 1e3) / (ms_e / steps),
+                   "what": "ahkab_b200.run(circ, analysis, batch=ParamBatch) -> every result array as "
+                           "host numpy, host wall clock; the ParamBatch is built once from host numpy "
+                           "arrays, every call copies its (pinned) value matrix host->device",
+                   "fresh_batch_ms_per_step": dt_fresh * 1e3,
+                   "fresh_batch": "the same with a NEW ParamBatch built from the numpy arrays inside "
+                                  "every step (re-flattening, new pinned staging)",
+                   "result_bytes": int(sum(a.nbytes for a in out_api))}
+        del out_api
     ok = int((raw['status'] & 1).sum().item()) if 'status' in raw else None
     step_s = ms * 1e-3 / steps
     par = ("single GPU" if world == 1 else
@@ -568,6 +654,8 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
                     "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},
     }
+    if e2e_api:
+        line["e2e_api"] = e2e_api
     if hbm_resident:
         line["e2e"]["hbm_resident"] = hbm_resident
         line["e2e"]["breakdown_ms"] = breakdown
@@ -576,6 +664,10 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     if want_cpu and rank == 0 and world == 1:
         cb, _ms = cpu_measure(name, 2 if name in ('c3', 'c4') else 3, 1)
         line["cpu_baseline"] = cb
+        if name == HEADLINE:
+            py = python_reference(name)
+            if py is not None:
+                line["python_reference"] = py
     del r
     torch.cuda.empty_cache()
     if dist_on:
@@ -632,8 +724,9 @@ def main():
     ap.add_argument('--jit', default='auto', choices=['auto', 'on', 'off'],
                     help='circuit-specialised kernels: auto (batches >= 1024), on, off (interpreted)')
     args = ap.parse_args()
-    global JIT_MODE
+    global JIT_MODE, HEADLINE
     JIT_MODE = args.jit
+    HEADLINE = args.workload
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))

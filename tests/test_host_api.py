@@ -153,3 +153,78 @@ def test_write_csv_uses_the_reference_file_format(tmp_path):
     op.write_csv(str(tmp_path / 'a.op'), b=1)
     back = np.loadtxt(tmp_path / 'a.op', delimiter='\t', comments='#')
     assert np.array_equal(back, x[1, 0])
+
+
+def test_flatten_is_cached_per_circuit_signature_and_batch_version():
+    """run() flattens once per (circuit, batch): the cache lives on the batch and is dropped by
+    ParamBatch.set() and by any change to the circuit's elements (plain mutable objects)."""
+    w = W.c2_diode_op(8)
+    circ, pb = w.circuit(Circuit), w.batch()
+    f1 = cp.flatten(circ, pb)
+    assert cp.flatten(circ, pb) is f1
+    # the same circuit built again has the same signature (models are distinct objects -> new flattening)
+    r = [e for e in circ if e.part_id.lower().startswith('v')][0]
+    old = r.dc_value
+    r.dc_value = old * 2
+    f2 = cp.flatten(circ, pb)
+    assert f2 is not f1 and not np.array_equal(f2.nominal, f1.nominal)
+    r.dc_value = old
+    f3 = cp.flatten(circ, pb)
+    assert np.array_equal(f3.nominal, f1.nominal) and np.array_equal(f3.vary, f1.vary)
+    # new values in the batch: new flattening with the new rows
+    (owner, attr), v = next(iter(pb.items()))
+    pb.set(owner, attr, v * 1.5)
+    f4 = cp.flatten(circ, pb)
+    assert f4 is not f3 and not np.array_equal(f4.vary, f3.vary)
+    assert cp.topology_key(f4) == cp.topology_key(f3)       # same engine serves both
+
+
+def test_sources_with_a_waveform_enter_op_with_their_dc_value():
+    """VSource.V(time=None) returns dc_value when there is one, else the waveform at t = 0
+    (VSource.py:92-97): the staged dc slot holds exactly that."""
+    for dc, want in ((0.25, 0.25), (None, 0.5)):
+        c = Circuit('exp')
+        c.add_vsource('V1', 'a', c.gnd, dc_value=dc, function=TF.exp(.5, -.05, 0., 2e-5, 4e-4, 2e-5))
+        c.add_resistor('R1', 'a', c.gnd, 1e3)
+        flat = cp.flatten(c)
+        assert flat.nominal[int(flat.elems[0]['pbase'])] == want
+        x = oracle.Oracle(c).op()['x'][0]
+        assert abs(x[0] - want) < 1e-12
+
+
+def test_csv_files_load_with_the_reference_loader(tmp_path):
+    """The optional exporter's files read back bit-exactly through the REFERENCE's own
+    csvlib.load_csv (ahkab/csvlib.py:213-290) — skipped where the reference package is absent."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'oracle'))
+    import ref_loop
+    if ref_loop.reference_path() is None:
+        pytest.skip("reference package not on this machine")
+    ref = ref_loop._load()
+    from ahkab import csvlib
+    c3 = W.c3_colpitts(2).circuit(Circuit)
+    rng = np.random.default_rng(1)
+    t = np.cumsum(rng.uniform(1e-10, 2e-10, (2, 6)), axis=1)
+    x = rng.standard_normal((2, 6, 9))
+    sol = results.tran_solution(c3, dict(t=t, x=x, rows=np.array([6, 4]),
+                                         status=np.ones(2, np.int32)), 0, 1, 'TRAP')
+    f = str(tmp_path / 'b.tran')
+    sol.write_csv(f, b=1)
+    data, headers, pos, eof = csvlib.load_csv(f, load_headers=[], verbose=0)
+    assert [h.upper() for h in headers] == [k.upper() for k in sol.keys()]
+    assert data.shape == (10, 4)
+    assert np.array_equal(data[0], t[1, :4]) and np.array_equal(data[1:], x[1, :4].T)
+    # AC: |x| and arg(x) columns (results.py:640-682)
+    c1 = W.c1_butterworth(2).circuit(Circuit)
+    n = c1.get_nodes_number() - 1 + sum(1 for e in c1 if getattr(e, '_ahk_type', 0) in (3, 5, 7, 9))
+    xa = rng.standard_normal((2, 5, n)) + 1j * rng.standard_normal((2, 5, n))
+    om = 2 * np.pi * np.logspace(2, 3, 5)
+    ac = results.ac_solution(c1, dict(x=xa, omegas=om, status=np.ones(2, np.int32)), 'LOG')
+    f = str(tmp_path / 'b.ac')
+    ac.write_csv(f, b=0)
+    data, headers, pos, eof = csvlib.load_csv(f, load_headers=[], verbose=0)
+    assert headers[0].lower() in ('f', '#f') and len(headers) == 1 + 2 * n
+    assert np.allclose(data[0], om / 2 / np.pi, rtol=1e-15)
+    assert np.array_equal(data[1::2], np.abs(xa[0]).T) and np.array_equal(data[2::2], np.angle(xa[0]).T)
+    del ref
