@@ -209,4 +209,4 @@ def variants(kind='real', lib=None):
 def fitting_variants(n, kind='real', lib=None):
     """ids of the variants that can run a circuit with n unknowns."""
     return [i for i, NC, R, G in variants(kind, lib)
-            if (NC == 0 and n <= 64) or (NC - 1 >= n and R * G >= n)]
+            if (NC == 0 and (n <= 64 or (G == 32 and n <= 512))) or (NC - 1 >= n and R * G >= n)]

@@ -49,22 +49,29 @@ struct AcLayout {
   int stride;
 };
 
-inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0) {
+// big: n beyond AHK_SMALL_NMAX — the complex matrix lives in the global workspace (Ctx::Ag,
+// n x RS complex elements), its right-hand side column in shared memory (L.brhs)
+inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0, bool big = false) {
   AcLayout A; std::memset(&A, 0, sizeof A);
   const Prog& h = H.hdr;
   const int n = h.n;
-  A.RS = NC > 0 ? NC : n + 1;
+  A.RS = NC > 0 ? NC : (big ? ((n + 1) & ~1) : n + 1);   // big: rows start on 32-byte sectors
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
   auto take2 = [&](int cnt) { off += off & 1; return take(cnt); };   // 16-byte aligned
-  A.Ac = take2(2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
+  A.Ac = take2(big ? 0 : 2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
+  A.L.big = big ? 1 : 0;
+  A.L.brhs = take2(big ? 2 * n : 0);
   A.xc = take2(2 * n); A.dxc = take2(2 * n); A.Nac = take2(2 * n);
   A.pvc = take2(NC > 0 && G > 1 ? 4 * NC : 0);
   A.L.RS = A.RS;
-  A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos);
+  // (many matrix positions — dense patterns — do not fit next to the vectors: global workspace)
+  A.L.vglob = big && h.npos > AHK_VGLOB_NPOS ? 1 : 0;
+  if (A.L.vglob) { A.L.Bv = 0; A.L.Mv = h.npos; A.L.Dv = 2 * h.npos; A.L.vlen = 3 * h.npos; }
+  else { A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos); }
   A.L.x = take(n);
   A.L.dout = take(h.ndout); A.L.dst = take(H.nst);
-  A.L.bytes = take(16);
+  A.L.bytes = take(big ? (6 * n + 7) / 8 + 1 : 16);
   A.L.Pv = take(h.npersist); A.L.dcon = take(H.ncon);
   A.L.buflen = 1;
   // complex elements are 16-byte aligned: even stride, 2 mod 4 to spread the groups
@@ -128,6 +135,79 @@ AHK_DEV int zlu_solve_smem(Ctx& c, const AcLayout& AL) {
     if (c.sub == 0) dx[k] = xk;
     for (int r = c.sub; r < n; r += G)
       if ((int)stepof[r] < k) A[r * RS + n] = csub(A[r * RS + n], cmul(A[r * RS + k], xk));
+    Grp<G>::sync(c.mask);
+  }
+  return 1;
+}
+
+// large n: the complex matrix in global memory — the scheme of lu_solve_glob (core.cuh): lanes
+// along the columns of a row, only the rows with a non-zero multiplier are visited
+template <int G>
+AHK_DEV int zlu_solve_glob(Ctx& c, const AcLayout& AL) {
+  const int n = c.p->n, RS = AL.RS;
+  cd* A = (cd*)c.Ag;
+  cd* dx = (cd*)(c.sm + AL.dxc);        // column k / multipliers while eliminating, then the solution
+  cd* b = (cd*)(c.sm + AL.L.brhs);
+  unsigned short* prow = (unsigned short*)(c.sm + AL.L.bytes);
+  unsigned short* stepof = prow + n;
+  unsigned short* list = stepof + n;
+  for (int r = c.sub; r < n; r += G) stepof[r] = 0xffff;
+  Grp<G>::sync(c.mask);
+  for (int k = 0; k < n; k++) {
+    double best = -1.0;
+    int bi = -1;
+    for (int r = c.sub; r < n; r += G) {
+      if (stepof[r] != 0xffff) continue;
+      const cd a = A[(size_t)r * RS + k];
+      dx[r] = a;
+      const double v = fabs(a.re) + fabs(a.im);
+      if (bi < 0 || v > best) { best = v; bi = r; }
+    }
+    Grp<G>::argmax(best, bi, c.mask);
+    if (best == 0.0) return 0;
+    if (c.sub == 0) { prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k; }
+    Grp<G>::sync(c.mask);
+    const cd one = {1.0, 0.0};
+    const cd inv = cdivv(one, dx[bi]);
+    int cnt = 0;
+    for (int r0 = 0; r0 < n; r0 += G) {
+      const int r = r0 + c.sub;
+      bool nz = false;
+      if (r < n && stepof[r] == 0xffff) {
+        const cd l = cmul(dx[r], inv);
+        nz = !(l.re == 0.0 && l.im == 0.0);
+        if (nz) dx[r] = l;
+      }
+#ifdef __CUDACC__
+      if (G == 32) {
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (nz) list[cnt + __popc(bal & ((1u << c.sub) - 1u))] = (unsigned short)r;
+        cnt += __popc(bal);
+      } else
+#endif
+      { if (nz) list[cnt++] = (unsigned short)r; }
+    }
+    Grp<G>::sync(c.mask);
+    const cd* Ap = A + (size_t)bi * RS;
+    const cd bp = b[bi];
+    for (int t = 0; t < cnt; t++) {
+      const int r = list[t];
+      const cd l = dx[r];
+      cd* Ar = A + (size_t)r * RS;
+#pragma unroll 2
+      for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] = csub(Ar[j], cmul(l, Ap[j]));
+      if (c.sub == 0) b[r] = csub(b[r], cmul(l, bp));
+    }
+    Grp<G>::sync(c.mask);
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    const int pr = prow[k];
+    const cd* Ap = A + (size_t)pr * RS;
+    cd s = {0.0, 0.0};
+    for (int j = k + 1 + c.sub; j < n; j += G) s = cadd(s, cmul(Ap[j], dx[j]));
+    s.re = Grp<G>::sum_all(s.re, c.mask);
+    s.im = Grp<G>::sum_all(s.im, c.mask);
+    if (c.sub == 0) dx[k] = cdivv(csub(b[pr], s), Ap[k]);
     Grp<G>::sync(c.mask);
   }
   return 1;
@@ -264,9 +344,9 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
   c.L = &AL.L;
   c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0; c.gadd = 0.0; c.G = G;
   build_values<Var<0, 0, V::G> >(c, true);   // parameters, Mv, Dv, device constants
-  double* Bv = c.sm + AL.L.Bv;
-  const double* Mv = c.sm + AL.L.Mv;
-  const double* Dv = c.sm + AL.L.Dv;
+  double* Bv = c.vb() + AL.L.Bv;
+  const double* Mv = c.vb() + AL.L.Mv;
+  const double* Dv = c.vb() + AL.L.Dv;
   double* xr = c.sm + AL.L.x;
   cd* x = (cd*)(c.sm + AL.xc);
   cd* dx = (cd*)(c.sm + AL.dxc);
@@ -338,6 +418,24 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
         }
       }
       ok = zgj_solve<V>(c, AL, m);
+    } else if (AL.L.big) {     // large n: matrix in the global workspace
+      cd* A = (cd*)c.Ag;
+      cd* b = (cd*)(c.sm + AL.L.brhs);
+      for (size_t i = c.sub; i < (size_t)n * RS; i += G) A[i] = cd{0.0, 0.0};
+      Grp<G>::sync(c.mask);
+      for (int r = c.sub; r < n; r += G) {
+        cd* Ar = A + (size_t)r * RS;
+        cd s = Nac[r];
+        for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
+          int col = p.pcol[k];
+          cd v = {Bv[k], om * Dv[k]};
+          Ar[col] = v;
+          s = cadd(s, cmul(v, x[col]));
+        }
+        b[r] = cd{-s.re, -s.im};
+      }
+      Grp<G>::sync(c.mask);
+      ok = zlu_solve_glob<G>(c, AL);
     } else {
       cd* A = (cd*)(c.sm + AL.Ac);
       for (int r = c.sub; r < n; r += G) {

@@ -92,6 +92,11 @@ struct Grp {
     for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m, v, o));
     return v;
   }
+  static AHK_DEV double sum_all(double v, unsigned m) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    return v;
+  }
   static AHK_DEV int all(int pred, unsigned m) { return G > 1 ? __all_sync(m, pred) : pred; }
   static AHK_DEV int any(int pred, unsigned m) { return G > 1 ? __any_sync(m, pred) : pred; }
   static AHK_DEV double bcast(double v, int src, unsigned m) { return __shfl_sync(m, v, src, G); }
@@ -122,6 +127,7 @@ struct Grp {  // host emulation (tests/hostemu): G == 1 only
   static void sync(unsigned) {}
   static double fmin_all(double v, unsigned) { return v; }
   static double fmax_all(double v, unsigned) { return v; }
+  static double sum_all(double v, unsigned) { return v; }
   static int all(int p, unsigned) { return p; }
   static int any(int p, unsigned) { return p; }
   static double bcast(double v, int, unsigned) { return v; }
@@ -189,6 +195,7 @@ struct Ctx {
   double dc_val;
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
   double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
+  double* Ag = nullptr;  // large-n layout (Layout::big): this instance's n x RS matrix in the global workspace
 
   // persistent parameter (staged in shared memory; index = SrcOp/DevOp ppb/pmb + k)
   AHK_MEM double PP(int pslot) const { return sm[L->Pv + pslot]; }
@@ -197,7 +204,9 @@ struct Ctx {
     int v = p->slot_vary[slot];
     return v < 0 ? p->nominal[slot] : vary[(long long)v * B + inst];
   }
-  AHK_MEM double* A() const { return sm + L->A; }
+  AHK_MEM double* A() const { return Ag ? Ag : sm + L->A; }
+  double* Vg = nullptr;  // Layout::vglob: base of this instance's Mv / Dv / Bv block in the global workspace
+  AHK_MEM double* vb() const { return Vg ? Vg : sm; }   // base the offsets Layout::Mv / Dv / Bv refer to
   AHK_MEM double* x() const { return sm + L->x; }
   AHK_MEM unsigned char* prow() const { return (unsigned char*)(sm + L->bytes); }
   AHK_MEM unsigned char* stepof() const { return (unsigned char*)(sm + L->bytes) + 64; }
@@ -235,8 +244,8 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   }
 #endif
   Grp<V::G>::sync(c.mask);
-  double* Mv = c.sm + c.L->Mv;
-  double* Dv = c.sm + c.L->Dv;
+  double* Mv = c.vb() + c.L->Mv;
+  double* Dv = c.vb() + c.L->Dv;
   if (c.sub == 0) {
     AHK_UNROLL
     for (int k = 0; k < p.npos; k++) { Mv[k] = 0.0; if (with_D) Dv[k] = 0.0; }
@@ -417,9 +426,9 @@ AHK_DEV void eval_devices(Ctx& c, const double* x) {
 AHK_DEV double assemble_row(Ctx& c, int r, double* Ar) {
   const Prog& p = *c.p;
   const double* x = c.x();
-  const double* Bv = c.sm + c.L->Bv;
+  const double* Bv = c.vb() + c.L->Bv;
   const double* dout = c.sm + c.L->dout;
-  const double* Dv = c.sm + c.L->Dv;
+  const double* Dv = c.vb() + c.L->Dv;
   const bool tran = Dv != Bv;          // transient layout: the matrix is Mv + C1 D (+ Gmin)
   const double C1 = c.C1;
   double s = 0.0;
@@ -673,6 +682,91 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
   return nonsing;
 }
 
+// ---- dense solve, large n (AHK_SMALL_NMAX < n <= AHK_BIG_NMAX): matrix in global memory ------
+// numpy.linalg.solve at dc_analysis.py:822 for circuits of any size.  The same elimination as
+// lu_solve_smem / dgesv (partial pivoting: largest magnitude among the rows not yet used, ties
+// to the lowest row; rows are never moved), organised for a matrix that lives in L2 / HBM: the
+// lanes run along the COLUMNS of a row (coalesced), the rows of a step are visited one after
+// the other — and only those whose multiplier is not zero (their list is compacted per step:
+// circuit matrices are sparse, and a - 0*b == a keeps the result identical to the dense
+// algorithm's).  The multiplier column, the right-hand side and the pivot bookkeeping stay in
+// shared memory.  One warp per instance on the device (G == 32), one lane on the host (tests).
+template <int G, bool FLAT = false>
+AHK_DEV int lu_solve_glob(Ctx& c) {
+  const int n = c.p->n, RS = c.L->RS;
+  const unsigned gm = FLAT ? 0xffffffffu : c.mask;
+  int nonsing = 1;
+  double* A = c.Ag;
+  double* dx = c.sm + c.L->dx;          // column k / multipliers while eliminating, then the solution
+  double* b = c.sm + c.L->brhs;
+  unsigned short* prow = (unsigned short*)(c.sm + c.L->bytes);
+  unsigned short* stepof = prow + n;    // 0xffff: row not used as a pivot row yet
+  unsigned short* list = stepof + n;
+  for (int r = c.sub; r < n; r += G) stepof[r] = 0xffff;
+  Grp<G>::sync(gm);
+  for (int k = 0; k < n; k++) {
+    double best = -1.0;
+    int bi = -1;
+    for (int r = c.sub; r < n; r += G) {
+      if (stepof[r] != 0xffff) continue;
+      const double a = A[(size_t)r * RS + k];
+      dx[r] = a;
+      const double v = fabs(a);
+      if (bi < 0 || v > best) { best = v; bi = r; }
+    }
+    Grp<G>::argmax(best, bi, gm);
+    if (best == 0.0) {
+      if (!FLAT) return 0;
+      nonsing = 0;
+    }
+    if (c.sub == 0) { prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k; }
+    Grp<G>::sync(gm);
+    const double inv = 1.0 / dx[bi];
+    // rows of this step: not yet used, multiplier not zero
+    int cnt = 0;
+    for (int r0 = 0; r0 < n; r0 += G) {
+      const int r = r0 + c.sub;
+      bool nz = false;
+      if (r < n && stepof[r] == 0xffff) {
+        const double l = dx[r] * inv;
+        nz = l != 0.0;
+        if (nz) dx[r] = l;
+      }
+#ifdef __CUDACC__
+      if (G == 32) {
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (nz) list[cnt + __popc(bal & ((1u << c.sub) - 1u))] = (unsigned short)r;
+        cnt += __popc(bal);
+      } else
+#endif
+      { if (nz) list[cnt++] = (unsigned short)r; }     // one lane per instance
+    }
+    Grp<G>::sync(gm);
+    const double* Ap = A + (size_t)bi * RS;
+    const double bp = b[bi];
+    for (int t = 0; t < cnt; t++) {
+      const int r = list[t];
+      const double l = dx[r];
+      double* Ar = A + (size_t)r * RS;
+#pragma unroll 4
+      for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] -= l * Ap[j];
+      if (c.sub == 0) b[r] -= l * bp;
+    }
+    Grp<G>::sync(gm);
+  }
+  // back-substitution, row-wise: dx[k] = (b[p] - sum_{j > k} U[p][j] dx[j]) / U[p][k]
+  for (int k = n - 1; k >= 0; k--) {
+    const int pr = prow[k];
+    const double* Ap = A + (size_t)pr * RS;
+    double s = 0.0;
+    for (int j = k + 1 + c.sub; j < n; j += G) s += Ap[j] * dx[j];
+    s = Grp<G>::sum_all(s, gm);
+    if (c.sub == 0) dx[k] = (b[pr] - s) / Ap[k];
+    Grp<G>::sync(gm);
+  }
+  return nonsing;
+}
+
 #ifdef AHK_JIT
 // Specialised build: the row is a COMPILE-TIME constant, so its column indices, gather
 // lists and signs fold into straight-line code that writes the matrix row directly into
@@ -759,6 +853,14 @@ AHK_DEV int assemble_solve(Ctx& c) {
       return okk;
     } else return gj_solve<V, FLAT>(c, a);
   } else {
+    if (c.L->big) {       // large n: matrix in the global workspace, right-hand side in shared memory
+      for (size_t i = c.sub; i < (size_t)n * RS; i += G) A[i] = 0.0;
+      Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
+      double* b = c.sm + c.L->brhs;
+      for (int r = c.sub; r < n; r += G) b[r] = assemble_row(c, r, A + (size_t)r * RS);
+      Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
+      return lu_solve_glob<G, FLAT>(c);
+    }
     for (int r = c.sub; r < n; r += G) {
       double* Ar = A + r * RS;
       for (int j = 0; j < n; j++) Ar[j] = 0.0;
@@ -848,9 +950,9 @@ AHK_DEV int dc_solve(Ctx& c, double gmin, bool with_tran, double time, int MAXIT
   const double* Nc = c.sm + c.L->Nc;
   const double* Ntr = c.sm + c.L->Ntr;
   double* T = c.sm + c.L->T;
-  double* Bv = c.sm + c.L->Bv;
-  const double* Mv = c.sm + c.L->Mv;
-  const double* Dv = c.sm + c.L->Dv;
+  double* Bv = c.vb() + c.L->Bv;
+  const double* Mv = c.vb() + c.L->Mv;
+  const double* Dv = c.vb() + c.L->Dv;
   AHK_LANES(i, n) Nd[i] = Nc[i];
   if (p.ntd) {   // Tt(t), dc_analysis.py:222-237
     Grp<G>::sync(c.mask);
@@ -1145,7 +1247,7 @@ AHK_DEV int tran_analysis(Ctx& c, const TranArgs& a, bool live = true) {
   double* Nd = c.sm + c.L->Nd;
   const double* Nc = c.sm + c.L->Nc;
   double* T = c.sm + c.L->T;
-  const double* Dv = c.sm + c.L->Dv;
+  const double* Dv = c.vb() + c.L->Dv;
   double* xs = c.sm + c.L->xs;       // NR start point when nothing better exists
   int order, max_x, max_dx, pmax_x;
   if (method == AHK_IMPLICIT_EULER) { order = 1; max_x = 0; max_dx = -1; pmax_x = 1; }

@@ -110,8 +110,11 @@ struct ahk_engine {
   std::vector<int> cur_slots;
   bool slots_valid = false;
   double* d_scratch = nullptr;   // sweep values / omegas
+  double* bigA = nullptr;        // large-n engine: [B][n x RS] matrix workspace (grow-only)
+  size_t bigA_cap = 0;           // doubles
   size_t scratch_cap = 0;
   BigLin big;              // large-n linear path (biglin.cuh)
+  bool force_general = false;   // tests / tuning: large LINEAR circuits through the general large-n engine too
   // circuit-specialised kernels (jit_gen.hpp): 0 = never, 1 = always (failing to build one
   // is an error), 2 = batches of at least jit_min_batch instances, interpreted kernel if
   // NVRTC is not available
@@ -500,7 +503,7 @@ int to_scratch(ahk_engine* e, const double* host, int cnt, cudaStream_t s) {
 
 // ---- kernel-variant selection -------------------------------------------------------------
 bool fits(const VarInfo& v, int n) {
-  if (v.NC == 0) return n <= AHK_SMALL_NMAX;
+  if (v.NC == 0) return n <= (v.G == 32 ? AHK_BIG_NMAX : AHK_SMALL_NMAX);   // warp per instance: also the large-n engine
   return v.NC - 1 >= n && v.R * v.G >= n;
 }
 
@@ -602,6 +605,9 @@ int launched(int rc) {
 KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
   KBase k;
   k.p = e->dprog; k.o = e->o; k.L = L; k.vary = b->vary; k.B = b->B;
+  k.Ag = L.big ? e->bigA : nullptr;
+  k.Voff = L.big ? (long long)e->n * L.RS : 0;
+  k.Astride = L.big ? k.Voff + L.vlen : 0;
   return k;
 }
 
@@ -687,6 +693,19 @@ int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int
 int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
                            Launch* L, jit::Kernel** jk) {
   *jk = nullptr;
+  if (e->n > AHK_SMALL_NMAX) {
+    // General large-n engine: the generic variant with one warp per instance, vectors in shared
+    // memory, the dense matrix in the global workspace (core.cuh: lu_solve_glob).  Interpreted
+    // kernels only: the specialised ones hold the matrix in registers.
+    if (e->n > AHK_BIG_NMAX) return fail("circuit too large: n = " + std::to_string(e->n) + " > " + std::to_string(AHK_BIG_NMAX));
+    if (e->jit_mode == 1) return fail("specialised kernels need n <= 64");
+    const int vid = 1;
+    const VarInfo v = real_variants()[vid];
+    *vid_out = vid;
+    *Ly = make_layout(e->H, mode, method, usc, v.G, 0, 1, false, true);
+    if (plan(e, B, vid, v, Ly->stride, *L, real_min_blocks(0), nullptr)) return -1;
+    return 0;
+  }
   static const bool full_layout = getenv("AHK_JIT_FULL_LAYOUT") != nullptr;   // tuning experiments
   for (int jit = wants_jit(e, B) ? 1 : 0; jit >= 0; jit--) {
     int vid;
@@ -793,6 +812,20 @@ int jit_launched(bool ok, const std::string& err) {
   return 0;
 }
 
+// workspace of the large-n engine: one n x RS matrix per instance (L2 / HBM resident)
+int ensure_big_workspace(ahk_engine* e, long long B, const Layout& Ly, cudaStream_t s) {
+  if (!Ly.big) return 0;
+  const size_t need = (size_t)B * ((size_t)e->n * Ly.RS + Ly.vlen);
+  if (need <= e->bigA_cap) return 0;
+  if (need * sizeof(double) > ((size_t)96 << 30))
+    return fail("large-n workspace of " + std::to_string(need * sizeof(double) >> 20) + " MiB: split the batch");
+  CK(cudaStreamSynchronize(s));
+  if (e->bigA) { cudaFree(e->bigA); e->bigA = nullptr; e->bigA_cap = 0; }
+  CK(cudaMalloc(&e->bigA, need * sizeof(double)));
+  e->bigA_cap = need;
+  return 0;
+}
+
 int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* d_sweep, int npts,
                  const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
                  int32_t* status, cudaStream_t s) {
@@ -805,6 +838,7 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
     std::string err;
     return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
   }
+  if (ensure_big_workspace(e, batch->B, Ly, s)) return -1;
   KDc k;
   k.b = make_base(e, batch, Ly);
   k.a = DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status};
@@ -868,6 +902,7 @@ void ahk_destroy(ahk_engine* e) {
   if (!e) return;
   if (e->blob) cudaFree(e->blob);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->bigA) cudaFree(e->bigA);
   for (auto& kv : e->jit_cache) jit::unload(kv.second);
   if (e->hp.ready) {
     if (e->hp.graph_exec) cudaGraphExecDestroy(e->hp.graph_exec);
@@ -1029,6 +1064,9 @@ int ahk_set_variant(ahk_engine* e, int real_id, int ac_id) {
   if (ac_id >= 0 && !fits(ac_variants()[ac_id], e->n)) return fail("variant does not fit this circuit");
   e->force_vid = real_id < 0 ? -1 : real_id;
   e->force_ac_vid = ac_id < 0 ? -1 : ac_id;
+  // the generic warp-per-instance variant forced on a large LINEAR circuit: the general large-n
+  // engine instead of the factor-once linear path (tests, comparisons)
+  e->force_general = real_id == 1 && e->n > AHK_SMALL_NMAX;
   return 0;
 }
 
@@ -1071,11 +1109,12 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0, int use_gues
   if (!e || !x || !iters || !status) return fail("ahk_op: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
-  if (e->n > AHK_SMALL_NMAX) {
-    if (e->H.nonlinear) return fail("non-linear circuits with n > 64 are not supported yet");
+  if (e->n > AHK_SMALL_NMAX && !e->H.nonlinear && !e->force_general) {
+    // large LINEAR circuits: factor once per instance, static sparse schedule (biglin*.cuh)
     double v = 0.0;
     return e->big.run(e, batch, -1, &v, 1, x, iters, status, resid, s, g_err, g_launches);
   }
+  // (n > 64, non-linear: the general large-n engine inside run_dc_small)
   return run_dc_small(e, batch, -1, nullptr, 1, x0, use_guess, x, resid, iters, status, s);
 }
 
@@ -1222,13 +1261,13 @@ int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
   bool ok = false;
-  for (auto& so : e->H.src) if (so.elem == src_elem && !so.tf) ok = true;
-  if (!ok) return fail("ahk_dc_sweep: src_elem is not a DC V/I source");
-  if (e->n > AHK_SMALL_NMAX) {
-    if (e->H.nonlinear) return fail("non-linear circuits with n > 64 are not supported yet");
+  // (a source with a waveform sweeps too: dc_analysis sets its dc_value, which is what V(time=None)
+  // returns — VSource.py:92-95)
+  for (auto& so : e->H.src) if (so.elem == src_elem) ok = true;
+  if (!ok) return fail("ahk_dc_sweep: src_elem is not a V/I source");
+  if (e->n > AHK_SMALL_NMAX && !e->H.nonlinear && !e->force_general)
     return e->big.run(e, batch, src_elem, sweep_values, npts, x_out, iters, status, nullptr, s,
                       g_err, g_launches);
-  }
   if (to_scratch(e, sweep_values, npts, s)) return -1;
   return run_dc_small(e, batch, src_elem, e->d_scratch, npts, x0, use_guess, x_out, nullptr, iters,
                       status, s);
@@ -1243,7 +1282,6 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
     return fail("ahk_tran: unknown method");
   if (tstart > tstop) return fail("tstart > tstop");       // transient.py:153-155
   if (tstep < 0) return fail("tstep < 0");                 // transient.py:156-158
-  if (e->n > AHK_SMALL_NMAX) return fail("transient needs n <= 64 in this build");
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
   int vid; Layout Ly; Launch L;
@@ -1257,6 +1295,7 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
     std::string err;
     return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
   }
+  if (ensure_big_workspace(e, batch->B, Ly, s)) return -1;
   KTran k;
   k.b = make_base(e, batch, Ly);
   k.x0 = x0;
@@ -1269,7 +1308,8 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
            int npts, double* x_out, int32_t* status, void* stream) {
   if (!e || !omegas || npts <= 0 || !x_out || !status) return fail("ahk_ac: bad argument");
   if (e->H.nonlinear && !x_op) return fail("ahk_ac: non-linear circuit needs x_op");
-  if (e->n > AHK_SMALL_NMAX) return fail("AC needs n <= 64 in this build");
+  if (e->n > AHK_BIG_NMAX) return fail("circuit too large: n = " + std::to_string(e->n) + " > " + std::to_string(AHK_BIG_NMAX));
+  const bool big = e->n > AHK_SMALL_NMAX;    // general large-n engine: complex matrix in the global workspace
   cudaStream_t s = (cudaStream_t)stream;
   if (set_batch(e, batch, s)) return -1;
   if (to_scratch(e, omegas, npts, s)) return -1;
@@ -1281,12 +1321,17 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     if (const char* f = getenv("AHK_AC_CHUNKS")) nchunks = std::max(1, std::min(npts, atoi(f)));   // tuning
   }
   long long units = batch->B * nchunks;
-  int vid;
-  if (pick_variant(e, ac_variants(), AHK_N_AC_VARIANTS, e->force_ac_vid, units, ac_min_blocks,
-                   [&](const VarInfo& q) { return make_ac_layout(e->H, q.G, q.NC).stride; }, &vid))
+  int vid = 1;                                 // big: the generic warp-per-instance variant
+  if (!big && pick_variant(e, ac_variants(), AHK_N_AC_VARIANTS, e->force_ac_vid, units, ac_min_blocks,
+                           [&](const VarInfo& q) { return make_ac_layout(e->H, q.G, q.NC).stride; }, &vid))
     return -1;
   const VarInfo& v = ac_variants()[vid];
-  AcLayout AL = make_ac_layout(e->H, v.G, v.NC);
+  AcLayout AL = make_ac_layout(e->H, v.G, v.NC, big);
+  if (big) {
+    if (e->jit_mode == 1) return fail("specialised kernels need n <= 64");
+    Layout Lw = AL.L; Lw.RS = 2 * AL.RS;       // (complex elements: twice the doubles per row)
+    if (ensure_big_workspace(e, units, Lw, s)) return -1;
+  }
   Launch L;
   if (plan(e, units, vid, v, AL.stride, L, ac_min_blocks(v.NC), nullptr)) return -1;
   {
@@ -1315,6 +1360,9 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
   KAc k;
   k.p = e->dprog; k.o = e->o; k.AL = AL;
   k.vary = batch->vary; k.B = batch->B; k.nchunks = nchunks;
+  k.Ag = big ? e->bigA : nullptr;
+  k.Voff = big ? (long long)2 * e->n * AL.RS : 0;
+  k.Astride = big ? k.Voff + AL.L.vlen : 0;
   k.a = AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status};
   return launched(launch_ac(k, L, s));
 }

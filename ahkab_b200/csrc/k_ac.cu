@@ -10,6 +10,10 @@ __global__ void __launch_bounds__(128, (V::NC > 0 && V::NC <= 16) ? 4 : (V::NC =
   Ctx c; long long u;
   if (!make_ctx<V::G>(c, &k.p, &k.o, &k.AL.L, k.AL.stride, k.vary, k.B, k.B * k.nchunks, u)) return;
   c.inst = u / k.nchunks;
+  if (V::NC == 0 && k.Ag) {   // large n: one complex matrix (+ value arrays) per (instance, chunk)
+    c.Ag = k.Ag + (size_t)u * k.Astride;
+    if (k.AL.L.vglob) c.Vg = c.Ag + k.Voff;
+  }
   const int ch = (int)(u % k.nchunks);
   AcArgs a = k.a;
   const int per = (a.npts + k.nchunks - 1) / k.nchunks;

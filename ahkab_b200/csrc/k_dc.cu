@@ -8,6 +8,10 @@ template <class V>
 __global__ void __launch_bounds__(128, (V::NC <= 12) ? AHK_MINB : (V::NC <= 16 ? 3 : 2)) k_dc(const __grid_constant__ KDc k) {
   Ctx c; long long u;
   if (!make_ctx<V::G>(c, &k.b.p, &k.b.o, &k.b.L, k.b.L.stride, k.b.vary, k.b.B, k.b.B, u)) return;
+  if (V::NC == 0 && k.b.Ag) {   // large n: matrix (and, for dense patterns, the value arrays) in global memory
+    c.Ag = k.b.Ag + (size_t)c.inst * k.b.Astride;
+    if (k.b.L.vglob) c.Vg = c.Ag + k.b.Voff;
+  }
   run_dc<V>(c, k.a);
 }
 

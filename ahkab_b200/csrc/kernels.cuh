@@ -59,10 +59,13 @@ inline const VarInfo* ac_variants() {
 struct KBase {
   Prog p; Opts o; Layout L;
   const double* vary; long long B;
+  double* Ag;            // large-n layout: [B][n x RS] matrix workspace in global memory, else null
+  long long Astride;     // doubles per instance of Ag
+  long long Voff;        // Layout::vglob: offset of the Mv / Dv / Bv block inside the instance's workspace
 };
 struct KDc { KBase b; DcArgs a; };
 struct KTran { KBase b; const double* x0; TranArgs a; int* status; };
-struct KAc { Prog p; Opts o; AcLayout AL; const double* vary; long long B; AcArgs a; int nchunks; };
+struct KAc { Prog p; Opts o; AcLayout AL; const double* vary; long long B; AcArgs a; int nchunks; double* Ag; long long Astride, Voff; };
 
 struct Launch { int vid, G, threads, blocks; size_t smem; };
 

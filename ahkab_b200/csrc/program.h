@@ -8,6 +8,12 @@
 namespace ahk {
 
 #define AHK_SMALL_NMAX 64   // shared-memory engine: pivot mask is one 64-bit word
+// general large-n engine (core.cuh: lu_solve_glob): the per-instance VECTORS stay in shared
+// memory, the dense matrix lives in a global-memory workspace (L2 resident), one warp per
+// instance.  The reference solves any circuit densely (dc_analysis.py:796-822); its own limit
+// for switching to sparse storage is 400 unknowns (options.py:68).
+#define AHK_BIG_NMAX 512
+#define AHK_VGLOB_NPOS 2048    // large-n layouts: more matrix positions than this -> value arrays in global memory
 
 enum { K_R = 1, K_G, K_VDE, K_E, K_H, K_F, K_C, K_L, K_K };
 
@@ -85,6 +91,12 @@ struct Layout {     // offsets in doubles inside one instance's slice
   int dcon;         // per-device constants [ndev][EK_NCONST]
   int pvb;          // pivot-row broadcast buffers [2][NC]
   int xin;          // x at the entry of mdn_solver [n] (restored when the matrix turns out singular)
+  int big;          // 1: large-n layout — the matrix is in the global workspace (Ctx::Ag), not at A
+  int brhs;         // large-n layout: right-hand side column [n]
+  int vglob;        // large-n layout of a circuit with many matrix positions (dense patterns): the
+                    // per-position value arrays Mv / Dv / Bv live in the global workspace too
+                    // (offsets relative to Ctx::Vg), vlen doubles per instance
+  int vlen;
   int buflen;
   int stride;       // doubles per instance (padded: stride % 16 == (G*RS) % 16)
 };

@@ -366,18 +366,25 @@ enum { MODE_OP = 0, MODE_TRAN = 1 };
 // jit: layout of a circuit-specialised kernel (jit_gen.hpp) — it assembles straight into
 // registers and needs no staging rows.
 inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_control, int G,
-                          int NC = 0, int R = 1, bool jit = false) {
+                          int NC = 0, int R = 1, bool jit = false, bool big = false) {
   const Prog& h = H.hdr;
   Layout L; std::memset(&L, 0, sizeof L);
   const int n = h.n;
-  L.RS = NC > 0 ? NC - 1 : ((n + 1) | 1);
+  L.RS = NC > 0 ? NC - 1 : (big ? ((n + 3) & ~3) : ((n + 1) | 1));   // big: rows start on 32-byte sectors
   L.ARS = L.RS;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
   // register variants with several rows per lane stage through one scratch row per lane
-  L.A = take(jit && NC > 0 ? 0 : (NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS);
+  // big: run-time n beyond AHK_SMALL_NMAX — the n x RS matrix lives in the global workspace
+  L.big = big ? 1 : 0;
+  L.A = take(big ? 0 : (jit && NC > 0 ? 0 : (NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS));
+  L.brhs = take(big ? n : 0);
   L.x = take(n); L.dx = take(n); L.T = take(n); L.res = take(n);
-  L.Mv = take(h.npos);
+  // (many matrix positions — dense patterns — do not fit next to the vectors: global workspace)
+  L.vglob = big && h.npos > AHK_VGLOB_NPOS ? 1 : 0;
+  int voff = 0;
+  auto takev = [&](int cnt) { if (!L.vglob) return take(cnt); int o2 = voff; voff += cnt > 0 ? cnt : 0; return o2; };
+  L.Mv = takev(h.npos);
   // the matrix values are formed while assembling: Mv (+ C1 Dv in a transient) plus Gmin
   // on the node diagonals; Bv is kept as an alias of Mv
   L.Bv = L.Mv;
@@ -388,7 +395,9 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   // only before the first accepted step, when the history ring still holds it in slot 0
   // (aliased below); x1 is not used.
   if (mode != MODE_TRAN) { L.xs = take(n); L.x1 = take(n); }
-  L.bytes = take(NC > 0 ? 0 : 16);
+  // pivot bookkeeping of the generic solves: prow / stepof as bytes (n <= 64), or as 16-bit
+  // entries plus the row list of the current elimination step (large n)
+  L.bytes = take(NC > 0 ? 0 : (big ? (6 * n + 7) / 8 + 1 : 16));
   L.Pv = take(h.npersist); L.dcon = take(H.ncon);
   L.pvb = take(NC > 0 && G > 1 ? 2 * NC : 0);
   L.xin = take(n);
@@ -404,7 +413,7 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
     int bl = max_x > max_dx ? max_x : max_dx;
     if (use_step_control || max_dx < 0) { if (pmax_x > bl) bl = pmax_x; }
     L.buflen = bl + 1;
-    L.Dv = take(h.npos); L.Ntr = take(n); L.xacc = take(n);
+    L.Dv = takev(h.npos); L.Ntr = take(n); L.xacc = take(n);
     L.hx = take(L.buflen * n); L.hdx = take(n); L.ht = take(L.buflen);
     L.xs = L.hx; L.x1 = L.hx;
     L.C0 = take(n);
@@ -422,6 +431,7 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
     while (off % 16 != want) off++;
   }
   L.stride = off;
+  L.vlen = voff;
   return L;
 }
 

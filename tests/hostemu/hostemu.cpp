@@ -33,14 +33,23 @@ struct Emu {
     set_vary_slots(H, n_vary, slots);
     p = H.view();
     copy_opts(opts, o);
-    L = make_layout(H, mode, method, usc, 1, variant_nc(), variant_nc() ? variant_nc() - 1 : 1);
+    // n > AHK_SMALL_NMAX: the large-n layout of the generic variant (matrix in a "global" workspace)
+    const bool big = variant_nc() == 0 && H.hdr.n > AHK_SMALL_NMAX;
+    L = make_layout(H, mode, method, usc, 1, variant_nc(), variant_nc() ? variant_nc() - 1 : 1, false, big);
     sm.assign(L.stride + 64, 0.0);
+    if (big) Ag.assign((size_t)H.hdr.n * L.RS + L.vlen, 0.0);
   }
+  std::vector<double> Ag;
   Ctx ctx(const double* vary, long long B, long long b) {
     Ctx c; c.p = &p; c.o = &o; c.L = &L; c.sm = sm.data(); c.vary = vary; c.B = B; c.inst = b;
-    c.sub = 0; c.G = 1; c.mask = 1u; return c;
+    c.sub = 0; c.G = 1; c.mask = 1u; c.Ag = Ag.empty() ? nullptr : Ag.data();
+    c.Vg = (c.Ag && L.vglob) ? c.Ag + (size_t)p.n * L.RS : nullptr;
+    return c;
   }
-  bool fits() const { int nc = variant_nc(); return nc == 0 || p.n <= nc - 1; }
+  bool fits() const {
+    int nc = variant_nc();
+    return nc == 0 ? p.n <= AHK_BIG_NMAX : p.n <= nc - 1;
+  }
 };
 
 #define DISPATCH(CALL)                                   \
@@ -92,13 +101,17 @@ int emu_ac(const ahk_circuit* c, const ahk_options* o, int64_t B, int n_vary, co
   Emu e(c, o, n_vary, slots, MODE_OP, 0, 0);
   const int nc = g_variant == 1 ? 4 : 0;   // AC register variant on the host: Var<4,3,1>
   if (nc && e.p.n > nc - 1) return -2;
-  AcLayout AL = make_ac_layout(e.H, 1, nc);
+  const bool big = nc == 0 && e.p.n > AHK_SMALL_NMAX;
+  AcLayout AL = make_ac_layout(e.H, 1, nc, big);
   std::vector<double> sm(AL.stride + 64, 0.0);
+  std::vector<double> Ag(big ? (size_t)2 * e.p.n * AL.RS + AL.L.vlen : 0, 0.0);
   AcArgs a = {x_op, omegas, npts, 0, npts, x_out, status};
   for (int64_t b = 0; b < B; b++) {
     status[b] = AHK_ST_OK;
     Ctx cx = e.ctx(vary, B, b);
     cx.sm = sm.data();
+    cx.Ag = big ? Ag.data() : nullptr;
+    cx.Vg = (big && AL.L.vglob) ? Ag.data() + (size_t)2 * e.p.n * AL.RS : nullptr;
     if (nc) run_ac<Var<4, 3, 1> >(cx, AL, a); else run_ac<Var<0, 0, 1> >(cx, AL, a);
   }
   return 0;

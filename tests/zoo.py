@@ -163,6 +163,37 @@ def exp_src(Circuit, tf):
     return c
 
 
+def diode_ladder(Circuit, tf, N=100):
+    """Non-linear circuit with more than 64 unknowns (the reference solves any size densely,
+    dc_analysis.py:796-822): a resistor ladder with a diode and an RC load at every node, some
+    diodes bridging back two nodes, driven by a source with a DC value and a sine waveform."""
+    c = Circuit('diode ladder')
+    c.add_model('diode', 'dl', dict(IS=1e-14, N=1.2))
+    c.add_vsource('V1', 'n0', c.gnd, dc_value=5., ac_value=1., function=tf.sin(5., 2., 2e5))
+    for i in range(N):
+        c.add_resistor('R%d' % i, 'n%d' % i, 'n%d' % (i + 1), 100. + 3 * i)
+        c.add_diode('D%d' % i, 'n%d' % (i + 1), c.gnd if i % 3 else 'n%d' % max(0, i - 1), 'dl')
+        c.add_resistor('G%d' % i, 'n%d' % (i + 1), c.gnd, 5e3)
+        c.add_capacitor('C%d' % i, 'n%d' % (i + 1), c.gnd, 1e-10)
+    return c
+
+
+def diode_mesh(Circuit, tf, N=72):
+    """Dense non-linear circuit, n > 64: every pair of the N nodes is joined by a resistor (a
+    full MNA matrix), a diode and a resistor from every node to ground, two sources."""
+    c = Circuit('diode mesh')
+    c.add_model('diode', 'dm', dict(IS=2e-14, N=1.1))
+    c.add_vsource('V1', 'm0', c.gnd, dc_value=3.)
+    c.add_vsource('V2', 'm1', c.gnd, dc_value=-1.5)
+    for i in range(N):
+        for j in range(i + 1, N):
+            c.add_resistor('R%d_%d' % (i, j), 'm%d' % i, 'm%d' % j, 1e3 * (1 + ((7 * i + 3 * j) % 11)))
+        if i >= 2:
+            c.add_diode('D%d' % i, 'm%d' % i, c.gnd, 'dm')
+            c.add_resistor('G%d' % i, 'm%d' % i, c.gnd, 2e3 + 10 * i)
+    return c
+
+
 ZOO = {
     'rectifier': dict(build=rectifier, an=dict(kind='tran', tstart=0., tstop=2e-3, tstep=1e-5,
                                                method='TRAP', use_step_control=True, x0='op')),
@@ -193,6 +224,12 @@ ZOO = {
                                              method='TRAP', use_step_control=True, x0='op')),
     'exp_src': dict(build=exp_src, an=dict(kind='tran', tstart=0., tstop=6e-4, tstep=1e-6,
                                            method='GEAR2', use_step_control=True, x0='op')),
+    'ladder_op': dict(build=diode_ladder, an=dict(kind='op')),
+    'ladder_dc': dict(build=diode_ladder, an=dict(kind='dc', start=0., stop=6., points=7, source='V1')),
+    'ladder_tran': dict(build=diode_ladder, an=dict(kind='tran', tstart=0., tstop=1e-5, tstep=1e-7,
+                                                    method='TRAP', use_step_control=True, x0='op')),
+    'ladder_ac': dict(build=diode_ladder, an=dict(kind='ac', start=1e4, stop=1e8, points=9, x0='op')),
+    'mesh_op': dict(build=diode_mesh, an=dict(kind='op')),
     'rc_ie': dict(build=rc_gear3, an=dict(kind='tran', tstart=0., tstop=12e-6, tstep=2e-7,
                                           method='IMPLICIT_EULER', use_step_control=True, x0='op')),
 }
