@@ -62,12 +62,13 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0, bool big = 
   A.Ac = take2(big ? 0 : 2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
   A.L.big = big ? 1 : 0;
   A.L.brhs = take2(big ? 2 * n : 0);
+  A.L.nzm = take(big ? (n * ((n + 31) / 32) * 4 + 7) / 8 : 0);
   A.xc = take2(2 * n); A.dxc = take2(2 * n); A.Nac = take2(2 * n);
   A.pvc = take2(NC > 0 && G > 1 ? 4 * NC : 0);
   A.L.RS = A.RS;
   // (many matrix positions — dense patterns — do not fit next to the vectors: global workspace)
   A.L.vglob = big && h.npos > AHK_VGLOB_NPOS ? 1 : 0;
-  if (A.L.vglob) { A.L.Bv = 0; A.L.Mv = h.npos; A.L.Dv = 2 * h.npos; A.L.vlen = 3 * h.npos; }
+  if (A.L.vglob) { A.L.Bv = 0; A.L.Mv = h.npos; A.L.Dv = 2 * h.npos; A.L.vlen = (3 * h.npos + 3) & ~3; }
   else { A.L.Bv = take(h.npos); A.L.Mv = take(h.npos); A.L.Dv = take(h.npos); }
   A.L.x = take(n);
   A.L.dout = take(h.ndout); A.L.dst = take(H.nst);
@@ -140,25 +141,29 @@ AHK_DEV int zlu_solve_smem(Ctx& c, const AcLayout& AL) {
   return 1;
 }
 
-// large n: the complex matrix in global memory — the scheme of lu_solve_glob (core.cuh): lanes
-// along the columns of a row, only the rows with a non-zero multiplier are visited
+// large n: the complex matrix in global memory — the scheme of lu_solve_glob (core.cuh): per-row
+// bitmaps of the non-zero columns; column k is read only where its bit is set, a row update
+// touches only the columns of the pivot row's bitmap
 template <int G>
 AHK_DEV int zlu_solve_glob(Ctx& c, const AcLayout& AL) {
-  const int n = c.p->n, RS = AL.RS;
+  const int n = c.p->n, RS = AL.RS, W = (n + 31) >> 5;
   cd* A = (cd*)c.Ag;
   cd* dx = (cd*)(c.sm + AL.dxc);        // column k / multipliers while eliminating, then the solution
   cd* b = (cd*)(c.sm + AL.L.brhs);
+  unsigned* nzm = (unsigned*)(c.sm + AL.L.nzm);
   unsigned short* prow = (unsigned short*)(c.sm + AL.L.bytes);
   unsigned short* stepof = prow + n;
   unsigned short* list = stepof + n;
   for (int r = c.sub; r < n; r += G) stepof[r] = 0xffff;
   Grp<G>::sync(c.mask);
   for (int k = 0; k < n; k++) {
+    const int kw = k >> 5;
+    const unsigned kb = 1u << (k & 31);
     double best = -1.0;
     int bi = -1;
     for (int r = c.sub; r < n; r += G) {
       if (stepof[r] != 0xffff) continue;
-      const cd a = A[(size_t)r * RS + k];
+      const cd a = (nzm[r * W + kw] & kb) ? A[(size_t)r * RS + k] : cd{0.0, 0.0};
       dx[r] = a;
       const double v = fabs(a.re) + fabs(a.im);
       if (bi < 0 || v > best) { best = v; bi = r; }
@@ -189,22 +194,59 @@ AHK_DEV int zlu_solve_glob(Ctx& c, const AcLayout& AL) {
     }
     Grp<G>::sync(c.mask);
     const cd* Ap = A + (size_t)bi * RS;
+    const unsigned* nzp = nzm + bi * W;
     const cd bp = b[bi];
-    for (int t = 0; t < cnt; t++) {
-      const int r = list[t];
-      const cd l = dx[r];
-      cd* Ar = A + (size_t)r * RS;
+    const int w0 = (k + 1) >> 5, Wrem = W - w0;
+    const unsigned m0 = ~0u << ((k + 1) & 31);
+    int nnzp = 0;
+    for (int w = w0; w < W; w++) nnzp += big_popc(nzp[w] & (w == w0 ? m0 : ~0u));
+    if (k + 1 < n && cnt > 0) {
+      if (nnzp * 4 > n - k - 1) {
+        for (int t = 0; t < cnt; t++) {
+          const int r = list[t];
+          const cd l = dx[r];
+          cd* Ar = A + (size_t)r * RS;
 #pragma unroll 2
-      for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] = csub(Ar[j], cmul(l, Ap[j]));
-      if (c.sub == 0) b[r] = csub(b[r], cmul(l, bp));
+          for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] = csub(Ar[j], cmul(l, Ap[j]));
+          for (int w = w0 + c.sub; w < W; w += G) nzm[r * W + w] |= nzp[w] & (w == w0 ? m0 : ~0u);
+        }
+      } else {
+        for (int item = c.sub; item < cnt * Wrem; item += G) {
+          const int t = item / Wrem, w = w0 + item % Wrem;
+          unsigned bits = nzp[w] & (w == w0 ? m0 : ~0u);
+          if (!bits) continue;
+          const int r = list[t];
+          const cd l = dx[r];
+          cd* Ar = A + (size_t)r * RS;
+          nzm[r * W + w] |= bits;
+          while (bits) {
+            const int j = (w << 5) + big_ctz(bits);
+            bits &= bits - 1;
+            Ar[j] = csub(Ar[j], cmul(l, Ap[j]));
+          }
+        }
+      }
     }
+    for (int t = c.sub; t < cnt; t += G) { const int r = list[t]; b[r] = csub(b[r], cmul(dx[r], bp)); }
     Grp<G>::sync(c.mask);
   }
   for (int k = n - 1; k >= 0; k--) {
     const int pr = prow[k];
     const cd* Ap = A + (size_t)pr * RS;
+    const unsigned* nzp = nzm + pr * W;
+    const int w0 = (k + 1) >> 5;
+    const unsigned m0 = ~0u << ((k + 1) & 31);
     cd s = {0.0, 0.0};
-    for (int j = k + 1 + c.sub; j < n; j += G) s = cadd(s, cmul(Ap[j], dx[j]));
+    if (k + 1 < n) {
+      for (int w = w0 + c.sub; w < W; w += G) {
+        unsigned bits = nzp[w] & (w == w0 ? m0 : ~0u);
+        while (bits) {
+          const int j = (w << 5) + big_ctz(bits);
+          bits &= bits - 1;
+          s = cadd(s, cmul(Ap[j], dx[j]));
+        }
+      }
+    }
     s.re = Grp<G>::sum_all(s.re, c.mask);
     s.im = Grp<G>::sum_all(s.im, c.mask);
     if (c.sub == 0) dx[k] = cdivv(csub(b[pr], s), Ap[k]);
@@ -343,6 +385,9 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
   const int n = p.n, RS = AL.RS;
   c.L = &AL.L;
   c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0; c.gadd = 0.0; c.G = G;
+  if constexpr (V::NC == 0) {
+    if (AL.L.big) big_init<G>(c, c.Ag, (size_t)2 * n * RS);   // large n: complex matrix zero, no entry flagged
+  }
   build_values<Var<0, 0, V::G> >(c, true);   // parameters, Mv, Dv, device constants
   double* Bv = c.vb() + AL.L.Bv;
   const double* Mv = c.vb() + AL.L.Mv;
@@ -421,7 +466,15 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     } else if (AL.L.big) {     // large n: matrix in the global workspace
       cd* A = (cd*)c.Ag;
       cd* b = (cd*)(c.sm + AL.L.brhs);
-      for (size_t i = c.sub; i < (size_t)n * RS; i += G) A[i] = cd{0.0, 0.0};
+      const int W = (n + 31) >> 5;
+      unsigned* nzm = (unsigned*)(c.sm + AL.L.nzm);
+      for (int item = c.sub; item < n * W; item += G) {     // clear the flagged entries of the last factorisation
+        unsigned bits = nzm[item];
+        if (!bits) continue;
+        nzm[item] = 0u;
+        cd* Ar = A + (size_t)(item / W) * RS + ((item % W) << 5);
+        while (bits) { Ar[big_ctz(bits)] = cd{0.0, 0.0}; bits &= bits - 1; }
+      }
       Grp<G>::sync(c.mask);
       for (int r = c.sub; r < n; r += G) {
         cd* Ar = A + (size_t)r * RS;
@@ -430,6 +483,7 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
           int col = p.pcol[k];
           cd v = {Bv[k], om * Dv[k]};
           Ar[col] = v;
+          nzm[r * W + (col >> 5)] |= 1u << (col & 31);
           s = cadd(s, cmul(v, x[col]));
         }
         b[r] = cd{-s.re, -s.im};

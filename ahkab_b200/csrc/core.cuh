@@ -685,31 +685,240 @@ AHK_DEV int lu_solve_smem(Ctx& c) {
 // ---- dense solve, large n (AHK_SMALL_NMAX < n <= AHK_BIG_NMAX): matrix in global memory ------
 // numpy.linalg.solve at dc_analysis.py:822 for circuits of any size.  The same elimination as
 // lu_solve_smem / dgesv (partial pivoting: largest magnitude among the rows not yet used, ties
-// to the lowest row; rows are never moved), organised for a matrix that lives in L2 / HBM: the
-// lanes run along the COLUMNS of a row (coalesced), the rows of a step are visited one after
-// the other — and only those whose multiplier is not zero (their list is compacted per step:
-// circuit matrices are sparse, and a - 0*b == a keeps the result identical to the dense
-// algorithm's).  The multiplier column, the right-hand side and the pivot bookkeeping stay in
-// shared memory.  One warp per instance on the device (G == 32), one lane on the host (tests).
+// to the lowest row; rows are never moved) on a dense n x RS matrix that lives in L2 / HBM —
+// a warp cannot afford to walk 2 KB-strided columns and full rows of zeros there (measured: a
+// 252-unknown diode ladder spent its time pulling one DRAM sector per matrix element), so the
+// non-zero STRUCTURE is tracked next to the values: one bitmap of non-zero columns per row, in
+// shared memory, set from the stamp pattern at assembly and OR-ed with the pivot row's bitmap
+// at every row update (fill-in).  Column k is read only in the rows whose bit k is set; a row
+// update touches only the columns of the pivot row's bitmap (sparse pivot row: the lanes split
+// the (row, bitmap word) pairs; dense pivot row: the lanes run along the columns, coalesced);
+// the next assembly clears only the flagged entries.  Skipped entries are exact zeros and
+// a - 0*b == a, so the result is that of the dense algorithm.  The multiplier column, the
+// right-hand side and the pivot bookkeeping stay in shared memory.  One warp per instance on
+// the device (G == 32), one lane on the host (tests).
+AHK_DEV int big_ctz(unsigned v) {
+#ifdef __CUDACC__
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+AHK_DEV int big_popc(unsigned v) {
+#ifdef __CUDACC__
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+
+// once per instance: the whole matrix zero, no entry flagged
+template <int G>
+AHK_DEV void big_init(Ctx& c, double* A, size_t len) {
+  const int n = c.p->n, W = (n + 31) >> 5;
+  unsigned* nzm = (unsigned*)(c.sm + c.L->nzm);
+  for (size_t i = c.sub; i < len; i += G) A[i] = 0.0;
+  for (int i = c.sub; i < n * W; i += G) nzm[i] = 0u;
+  Grp<G>::sync(c.mask);
+}
+
+// One panel of BIG_NB pivot steps of lu_solve_glob on a DENSE remainder, blocked (right-looking):
+//   1. per column of the panel: pivot search (dgesv's rule), multipliers of ALL unused rows into
+//      the shared-memory panel Lp[row][BIG_NB], eager update of the remaining PANEL columns and
+//      of the right-hand side only (the next pivot search needs them);
+//   2. the pivot rows' trailing parts: U12 = L11^-1 A12, a unit-lower-triangular solve with the
+//      lanes along the columns (registers);
+//   3. trailing update A22 -= L21 U12: 8 x 8 tiles of C over K = 8, two mma.sync m8n8k4 FP64
+//      (DMMA) per tile — every element of the trailing matrix is read and written ONCE per panel
+//      instead of once per pivot step.
+// The operations on an element are those of the unblocked elimination in another order of
+// summation (rounding-level differences); the pivot sequence is the same.
+#define BIG_NB 8
+template <int G, bool FLAT>
+AHK_DEV int lu_panel_dense(Ctx& c, const int k0) {
+  const int n = c.p->n, RS = c.L->RS, W = (n + 31) >> 5, NB = BIG_NB;
+  const unsigned gm = FLAT ? 0xffffffffu : c.mask;
+  int nonsing = 1;
+  double* A = c.Ag;
+  double* dx = c.sm + c.L->dx;
+  double* b = c.sm + c.L->brhs;
+  double* Lp = c.Ag + c.L->lpan;       // [n][NB] multipliers of this panel (global workspace, L1 / L2 resident)
+  unsigned* nzm = (unsigned*)(c.sm + c.L->nzm);
+  unsigned short* prow = (unsigned short*)(c.sm + c.L->bytes);
+  unsigned short* stepof = prow + n;
+  unsigned short* list = stepof + n;
+  const int kend = k0 + NB;
+  for (int kk = 0; kk < NB; kk++) {
+    const int k = k0 + kk;
+    double best = -1.0;
+    int bi = -1;
+    for (int r = c.sub; r < n; r += G) {
+      if (stepof[r] != 0xffff) continue;
+      const double a = A[(size_t)r * RS + k];
+      dx[r] = a;
+      const double v = fabs(a);
+      if (bi < 0 || v > best) { best = v; bi = r; }
+    }
+    Grp<G>::argmax(best, bi, gm);
+    if (best == 0.0) {
+      if (!FLAT) return 0;
+      nonsing = 0;
+    }
+    if (c.sub == 0) { prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k; }
+    Grp<G>::sync(gm);
+    const double inv = 1.0 / dx[bi];
+    const double* Ap = A + (size_t)bi * RS;
+    const double bp = b[bi];
+    double pv[BIG_NB];                  // the pivot row inside the panel (every lane: broadcast loads)
+#pragma unroll
+    for (int j = 0; j < NB; j++) pv[j] = (j > kk) ? Ap[k0 + j] : 0.0;
+    for (int r = c.sub; r < n; r += G) {
+      if (stepof[r] != 0xffff) continue;
+      const double l = dx[r] * inv;
+      Lp[r * NB + kk] = l;
+      if (l != 0.0) {
+        double* Ar = A + (size_t)r * RS + k0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) if (j > kk) Ar[j] -= l * pv[j];
+        b[r] -= l * bp;
+      }
+    }
+    Grp<G>::sync(gm);
+  }
+  // 2. U12: rows prow[k0 .. kend), columns >= kend
+  for (int j = kend + c.sub; j < n; j += G) {
+    double u[BIG_NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      const int pi = prow[k0 + i];
+      double v = A[(size_t)pi * RS + j];
+#pragma unroll
+      for (int m = 0; m < NB; m++) if (m < i) v -= Lp[pi * NB + m] * u[m];
+      u[i] = v;
+      if (i > 0) A[(size_t)pi * RS + j] = v;
+    }
+  }
+  // rows of the trailing update: unused, some multiplier of the panel not zero
+  int cnt = 0;
+  for (int r0 = 0; r0 < n; r0 += G) {
+    const int r = r0 + c.sub;
+    bool nz = false;
+    if (r < n && stepof[r] == 0xffff) {
+#pragma unroll
+      for (int m = 0; m < NB; m++) nz = nz || (Lp[r * NB + m] != 0.0);
+    }
+#ifdef __CUDACC__
+    if (G == 32) {
+      const unsigned bal = __ballot_sync(0xffffffffu, nz);
+      if (nz) list[cnt + __popc(bal & ((1u << c.sub) - 1u))] = (unsigned short)r;
+      cnt += __popc(bal);
+    } else
+#endif
+    { if (nz) list[cnt++] = (unsigned short)r; }
+  }
+  Grp<G>::sync(gm);                     // U12 and the list are visible
+  // 3. A22 -= L21 U12
+#ifdef __CUDACC__
+  if (G == 32) {
+    const int g = c.sub >> 2, tig = c.sub & 3;
+    const double* U0 = A + (size_t)prow[k0 + tig] * RS;          // B operands: U[tig][*], U[4 + tig][*]
+    const double* U1 = A + (size_t)prow[k0 + 4 + tig] * RS;
+    for (int j0 = kend; j0 < n; j0 += 8) {
+      const int jb = j0 + g;
+      const double b0 = jb < n ? U0[jb] : 0.0, b1 = jb < n ? U1[jb] : 0.0;
+      const int jc = j0 + 2 * tig;
+      for (int t0 = 0; t0 < cnt; t0 += 8) {
+        const int r = t0 + g < cnt ? (int)list[t0 + g] : -1;
+        double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+        double* Cr = nullptr;
+        if (r >= 0) {
+          a0 = -Lp[r * NB + tig]; a1 = -Lp[r * NB + 4 + tig];
+          Cr = A + (size_t)r * RS + jc;
+          if (jc + 1 < n) { const double2 cc = *(const double2*)Cr; c0 = cc.x; c1 = cc.y; }
+          else if (jc < n) c0 = Cr[0];
+        }
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
+        if (r >= 0) {
+          if (jc + 1 < n) *(double2*)Cr = make_double2(c0, c1);
+          else if (jc < n) Cr[0] = c0;
+        }
+      }
+    }
+  } else
+#endif
+  {
+    for (int t = 0; t < cnt; t++) {
+      const int r = list[t];
+      double* Ar = A + (size_t)r * RS;
+      for (int j = kend + c.sub; j < n; j += G) {
+        double v = Ar[j];
+        for (int m = 0; m < NB; m++) v -= Lp[r * NB + m] * A[(size_t)prow[k0 + m] * RS + j];
+        Ar[j] = v;
+      }
+    }
+  }
+  // the rows touched are dense right of the panel from here on (and keep their panel columns)
+  {
+    const int w0 = k0 >> 5;
+    const unsigned m0 = ~0u << (k0 & 31);
+    for (int item = c.sub; item < (cnt + NB) * (W - w0); item += G) {
+      const int t = item / (W - w0), w = w0 + item % (W - w0);
+      const int r = t < cnt ? (int)list[t] : (int)prow[k0 + t - cnt];
+      unsigned full = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : ~0u;
+      if (w == w0) full &= m0;
+      nzm[r * W + w] |= full;
+    }
+  }
+  Grp<G>::sync(gm);
+  return nonsing;
+}
+
 template <int G, bool FLAT = false>
 AHK_DEV int lu_solve_glob(Ctx& c) {
-  const int n = c.p->n, RS = c.L->RS;
+  const int n = c.p->n, RS = c.L->RS, W = (n + 31) >> 5;
   const unsigned gm = FLAT ? 0xffffffffu : c.mask;
   int nonsing = 1;
   double* A = c.Ag;
   double* dx = c.sm + c.L->dx;          // column k / multipliers while eliminating, then the solution
   double* b = c.sm + c.L->brhs;
+  unsigned* nzm = (unsigned*)(c.sm + c.L->nzm);
   unsigned short* prow = (unsigned short*)(c.sm + c.L->bytes);
   unsigned short* stepof = prow + n;    // 0xffff: row not used as a pivot row yet
   unsigned short* list = stepof + n;
   for (int r = c.sub; r < n; r += G) stepof[r] = 0xffff;
   Grp<G>::sync(gm);
   for (int k = 0; k < n; k++) {
+    if ((k & (BIG_NB - 1)) == 0 && k + BIG_NB + 8 <= n) {
+      // A full panel of BIG_NB columns ahead: where the remaining matrix is DENSE (more than half
+      // of the entries of the unused rows right of k are flagged — dense circuits, or fill-in late
+      // in a sparse elimination) the panel is eliminated as a block: the trailing update is a
+      // genuine dense contraction, C -= L U with K = BIG_NB, done on the FP64 tensor cores.
+      double cntb = 0.0, cntr = 0.0;
+      const int w0 = k >> 5;
+      for (int r = c.sub; r < n; r += G) {
+        if (stepof[r] != 0xffff) continue;
+        cntr += 1.0;
+        for (int w = w0; w < W; w++) cntb += (double)big_popc(nzm[r * W + w] & (w == w0 ? ~0u << (k & 31) : ~0u));
+      }
+      cntb = Grp<G>::sum_all(cntb, gm);
+      cntr = Grp<G>::sum_all(cntr, gm);
+      if (cntb * 2.0 > cntr * (double)(n - k)) {
+        const int ok = lu_panel_dense<G, FLAT>(c, k);
+        if (!ok) { if (!FLAT) return 0; nonsing = 0; }
+        k += BIG_NB - 1;
+        continue;
+      }
+    }
+    const int kw = k >> 5;
+    const unsigned kb = 1u << (k & 31);
     double best = -1.0;
     int bi = -1;
     for (int r = c.sub; r < n; r += G) {
       if (stepof[r] != 0xffff) continue;
-      const double a = A[(size_t)r * RS + k];
+      const double a = (nzm[r * W + kw] & kb) ? A[(size_t)r * RS + k] : 0.0;
       dx[r] = a;
       const double v = fabs(a);
       if (bi < 0 || v > best) { best = v; bi = r; }
@@ -743,23 +952,62 @@ AHK_DEV int lu_solve_glob(Ctx& c) {
     }
     Grp<G>::sync(gm);
     const double* Ap = A + (size_t)bi * RS;
+    const unsigned* nzp = nzm + bi * W;
     const double bp = b[bi];
-    for (int t = 0; t < cnt; t++) {
-      const int r = list[t];
-      const double l = dx[r];
-      double* Ar = A + (size_t)r * RS;
+    const int w0 = (k + 1) >> 5, Wrem = W - w0;
+    const unsigned m0 = ~0u << ((k + 1) & 31);          // columns > k of word w0
+    int nnzp = 0;                                         // entries of the pivot row right of the pivot
+    for (int w = w0; w < W; w++) nnzp += big_popc(nzp[w] & (w == w0 ? m0 : ~0u));
+    if (k + 1 < n && cnt > 0) {
+      if (nnzp * 4 > n - k - 1) {
+        // dense pivot row: lanes along the columns (coalesced), one row after the other
+        for (int t = 0; t < cnt; t++) {
+          const int r = list[t];
+          const double l = dx[r];
+          double* Ar = A + (size_t)r * RS;
 #pragma unroll 4
-      for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] -= l * Ap[j];
-      if (c.sub == 0) b[r] -= l * bp;
+          for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] -= l * Ap[j];
+          for (int w = w0 + c.sub; w < W; w += G) nzm[r * W + w] |= nzp[w] & (w == w0 ? m0 : ~0u);
+        }
+      } else {
+        // sparse pivot row: the lanes split the (row, bitmap word) pairs
+        for (int item = c.sub; item < cnt * Wrem; item += G) {
+          const int t = item / Wrem, w = w0 + item % Wrem;
+          unsigned bits = nzp[w] & (w == w0 ? m0 : ~0u);
+          if (!bits) continue;
+          const int r = list[t];
+          const double l = dx[r];
+          double* Ar = A + (size_t)r * RS;
+          nzm[r * W + w] |= bits;
+          while (bits) {
+            const int j = (w << 5) + big_ctz(bits);
+            bits &= bits - 1;
+            Ar[j] -= l * Ap[j];
+          }
+        }
+      }
     }
+    for (int t = c.sub; t < cnt; t += G) { const int r = list[t]; b[r] -= dx[r] * bp; }
     Grp<G>::sync(gm);
   }
   // back-substitution, row-wise: dx[k] = (b[p] - sum_{j > k} U[p][j] dx[j]) / U[p][k]
   for (int k = n - 1; k >= 0; k--) {
     const int pr = prow[k];
     const double* Ap = A + (size_t)pr * RS;
+    const unsigned* nzp = nzm + pr * W;
+    const int w0 = (k + 1) >> 5;
+    const unsigned m0 = ~0u << ((k + 1) & 31);
     double s = 0.0;
-    for (int j = k + 1 + c.sub; j < n; j += G) s += Ap[j] * dx[j];
+    if (k + 1 < n) {
+      for (int w = w0 + c.sub; w < W; w += G) {
+        unsigned bits = nzp[w] & (w == w0 ? m0 : ~0u);
+        while (bits) {
+          const int j = (w << 5) + big_ctz(bits);
+          bits &= bits - 1;
+          s += Ap[j] * dx[j];
+        }
+      }
+    }
     s = Grp<G>::sum_all(s, gm);
     if (c.sub == 0) dx[k] = (b[pr] - s) / Ap[k];
     Grp<G>::sync(gm);
@@ -854,10 +1102,26 @@ AHK_DEV int assemble_solve(Ctx& c) {
     } else return gj_solve<V, FLAT>(c, a);
   } else {
     if (c.L->big) {       // large n: matrix in the global workspace, right-hand side in shared memory
-      for (size_t i = c.sub; i < (size_t)n * RS; i += G) A[i] = 0.0;
+      const int W = (n + 31) >> 5;
+      unsigned* nzm = (unsigned*)(c.sm + c.L->nzm);
+      // clear what the previous factorisation left behind: the flagged entries only
+      for (int item = c.sub; item < n * W; item += G) {
+        unsigned bits = nzm[item];
+        if (!bits) continue;
+        nzm[item] = 0u;
+        double* Ar = A + (size_t)(item / W) * RS + ((item % W) << 5);
+        while (bits) { Ar[big_ctz(bits)] = 0.0; bits &= bits - 1; }
+      }
       Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
       double* b = c.sm + c.L->brhs;
-      for (int r = c.sub; r < n; r += G) b[r] = assemble_row(c, r, A + (size_t)r * RS);
+      const Prog& p = *c.p;
+      for (int r = c.sub; r < n; r += G) {
+        b[r] = assemble_row(c, r, A + (size_t)r * RS);
+        for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {     // the stamp pattern of the row
+          const int col = p.pcol[k];
+          nzm[r * W + (col >> 5)] |= 1u << (col & 31);
+        }
+      }
       Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
       return lu_solve_glob<G, FLAT>(c);
     }

@@ -607,7 +607,7 @@ KBase make_base(ahk_engine* e, const ahk_batch* b, const Layout& L) {
   k.p = e->dprog; k.o = e->o; k.L = L; k.vary = b->vary; k.B = b->B;
   k.Ag = L.big ? e->bigA : nullptr;
   k.Voff = L.big ? (long long)e->n * L.RS : 0;
-  k.Astride = L.big ? k.Voff + L.vlen : 0;
+  k.Astride = L.big ? k.Voff + L.vlen + (long long)e->n * 8 : 0;   // matrix | value block | panel multipliers
   return k;
 }
 
@@ -815,7 +815,7 @@ int jit_launched(bool ok, const std::string& err) {
 // workspace of the large-n engine: one n x RS matrix per instance (L2 / HBM resident)
 int ensure_big_workspace(ahk_engine* e, long long B, const Layout& Ly, cudaStream_t s) {
   if (!Ly.big) return 0;
-  const size_t need = (size_t)B * ((size_t)e->n * Ly.RS + Ly.vlen);
+  const size_t need = (size_t)B * ((size_t)e->n * Ly.RS + Ly.vlen + (size_t)e->n * 8);
   if (need <= e->bigA_cap) return 0;
   if (need * sizeof(double) > ((size_t)96 << 30))
     return fail("large-n workspace of " + std::to_string(need * sizeof(double) >> 20) + " MiB: split the batch");

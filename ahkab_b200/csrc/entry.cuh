@@ -16,6 +16,9 @@ struct DcArgs {
 template <class V>
 AHK_DEV void init_ctx(Ctx& c) {
   c.singular = 0; c.dc_src = -1; c.dc_val = 0.0; c.C1 = 0.0; c.gadd = 0.0; c.G = V::G;
+  if constexpr (V::NC == 0) {
+    if (c.L->big) big_init<V::G>(c, c.Ag, (size_t)c.p->n * c.L->RS);   // large n: matrix zero, no entry flagged
+  }
 }
 
 // dc_analysis.op_analysis (one point) / dc_analysis.dc_analysis for one instance: the

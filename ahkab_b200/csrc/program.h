@@ -93,6 +93,8 @@ struct Layout {     // offsets in doubles inside one instance's slice
   int xin;          // x at the entry of mdn_solver [n] (restored when the matrix turns out singular)
   int big;          // 1: large-n layout — the matrix is in the global workspace (Ctx::Ag), not at A
   int brhs;         // large-n layout: right-hand side column [n]
+  int nzm;          // large-n layout: per-row bitmaps of the non-zero columns, [n][(n + 31) / 32] words
+  int lpan;         // large-n layout: multipliers of the current dense panel, [n][8] — offset in the GLOBAL workspace (from Ctx::Ag)
   int vglob;        // large-n layout of a circuit with many matrix positions (dense patterns): the
                     // per-position value arrays Mv / Dv / Bv live in the global workspace too
                     // (offsets relative to Ctx::Vg), vlen doubles per instance

@@ -379,6 +379,8 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
   L.big = big ? 1 : 0;
   L.A = take(big ? 0 : (jit && NC > 0 ? 0 : (NC > 0 && R > 1 ? (G < n ? G : n) : n) * L.RS));
   L.brhs = take(big ? n : 0);
+  L.nzm = take(big ? (n * ((n + 31) / 32) * 4 + 7) / 8 : 0);
+
   L.x = take(n); L.dx = take(n); L.T = take(n); L.res = take(n);
   // (many matrix positions — dense patterns — do not fit next to the vectors: global workspace)
   L.vglob = big && h.npos > AHK_VGLOB_NPOS ? 1 : 0;
@@ -431,7 +433,10 @@ inline Layout make_layout(const HostProg& H, int mode, int method, int use_step_
     while (off % 16 != want) off++;
   }
   L.stride = off;
-  L.vlen = voff;
+  L.vlen = (voff + 3) & ~3;      // (keeps every instance's workspace 32-byte aligned: double2 tiles of the dense panels)
+  // multipliers of a dense panel (lu_panel_dense): in the instance's global workspace, behind
+  // the matrix and the value block — sparse circuits never touch it and pay no shared memory
+  L.lpan = big ? n * L.RS + L.vlen : 0;
   return L;
 }
 

@@ -162,6 +162,79 @@ class op_solution(solution):
     def __getitem__(self, name):
         return self.x[:, self._index(name)]
 
+    def get_table_array(self, b=0):
+        """results.py:325-336: the RESULTS table of instance b (Variable, Units, Value, Error, %)."""
+        import tabulate
+        x, err = self.x[b], self.errors[b]
+        table = []
+        for i, v in enumerate(self.variables):
+            rel = err[i] / x[i] * 100.0 if x[i] != 0 else 0.0
+            table.append((v, self.units[v], float(x[i]), float(err[i]),
+                          '%d' % rel if np.isfinite(rel) else 'nan'))
+        return tabulate.tabulate(table, headers=("Variable", "Units", "Value", "Error", "%"))
+
+    def _elements_op(self, circ, b):
+        """results.py:338-438 for instance b: the per-element OP tables of the linear elements
+        (resistors, independent sources — `get_op_info` of Resistor.py:71-92, VSource.py:126-149,
+        ISource.py) and the total power delivered by the sources.  Device reports (diode / MOS
+        small-signal tables) are not produced: they re-evaluate the Python device models."""
+        x = self.x[b]
+        nv_1 = circ.get_nodes_number() - 1
+        vde = [e for e in circ if _c.is_elem_voltage_defined(e)]
+
+        def vof(n1, n2):
+            return (x[n1 - 1] if n1 else 0.0) - (x[n2 - 1] if n2 else 0.0)
+        info, tot_power = {}, 0.0
+        for e in circ:
+            pid = e.part_id.upper()
+            if isinstance(e, _c.Resistor):
+                v = vof(e.n1, e.n2)
+                info.setdefault('R', (['Part ID', u"R [\u2126]", "V(n1,n2) [V]", "I(n1->n2) [A]", "P [W]"], []))[1] \
+                    .append([pid, e.value, float(v), float(v / e.value), float(v * v / e.value)])
+            elif isinstance(e, _c.VSource):
+                i = float(x[nv_1 + vde.index(e)])
+                V = e.dc_value if e.dc_value is not None else 0.0
+                info.setdefault('V', (['Part ID', "V(n1,n2) [V]", "I(n1->n2) [A]", "P [W]"], []))[1] \
+                    .append([pid, V, i, V * i])
+                tot_power -= vof(e.n1, e.n2) * i
+            elif isinstance(e, _c.ISource):
+                v, I = float(vof(e.n1, e.n2)), (e.dc_value if e.dc_value is not None else 0.0)
+                info.setdefault('I', (['Part ID', "V(n1-n2) [V]", "I [A]", "P [W]"], []))[1] \
+                    .append([pid, v, I, v * I])
+                tot_power -= v * I
+            elif isinstance(e, _c.EVSource):
+                tot_power -= vof(e.n1, e.n2) * float(x[nv_1 + vde.index(e)])
+            elif isinstance(e, _c.GISource):
+                tot_power -= vof(e.n1, e.n2) * vof(e.sn1, e.sn2) * e.alpha
+        return info, tot_power
+
+    def write_opinfo(self, filename, circ, b=0, options=None):
+        """Optional exporter: the reference's human-readable `.opinfo` report for instance b
+        (op_solution.write_to_file, ahkab/results.py:441-475): banner, options, iteration count,
+        the RESULTS table, the element OP tables and the total power dissipation."""
+        import time
+        import tabulate
+        from . import options as _o
+        o = _o.snapshot()
+        if options:
+            o.update(options)
+        info, tot_power = self._elements_op(circ, b)
+        with open(filename, 'w', encoding='utf-8') as fp:
+            fp.write(time.strftime("%c") + "\n")
+            fp.write("ahkab_b200 (batched hot path of ahkab v0.18), instance %d of %d\n\n" % (b, len(self.x)))
+            fp.write("Operating Point (OP) analysis\n\n")
+            fp.write("Netlist: %s\nTitle: %s\n" % (None, self.netlist_title))
+            fp.write("At %.2f K\n" % (300.0,))
+            fp.write("Options:\n\tvea = %e\n\tver = %f\n\tiea = %e\n\tier = %f\n\tgmin = %e\n"
+                     % (o['vea'], o['ver'], o['iea'], o['ier'], o['gmin']))
+            fp.write("\nConvergence reached in %d iterations.\n" % (int(self.iterations[b]),))
+            fp.write("\n========\nRESULTS:\n========\n\n")
+            fp.write(self.get_table_array(b) + '\n')
+            fp.write("\n========================\nELEMENTS OP INFORMATION:\n========================\n\n")
+            for k in sorted(info):
+                fp.write(tabulate.tabulate(info[k][1], headers=info[k][0]) + '\n\n')
+            fp.write('Total power dissipation: %g W\n\n' % tot_power)
+
     @property
     def gmin_check_failed(self):
         return (self.status & _abi.ST_GMIN_CHECK) != 0

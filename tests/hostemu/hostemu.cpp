@@ -37,7 +37,7 @@ struct Emu {
     const bool big = variant_nc() == 0 && H.hdr.n > AHK_SMALL_NMAX;
     L = make_layout(H, mode, method, usc, 1, variant_nc(), variant_nc() ? variant_nc() - 1 : 1, false, big);
     sm.assign(L.stride + 64, 0.0);
-    if (big) Ag.assign((size_t)H.hdr.n * L.RS + L.vlen, 0.0);
+    if (big) Ag.assign((size_t)H.hdr.n * L.RS + L.vlen + (size_t)H.hdr.n * 8, 0.0);
   }
   std::vector<double> Ag;
   Ctx ctx(const double* vary, long long B, long long b) {

@@ -228,3 +228,55 @@ def test_csv_files_load_with_the_reference_loader(tmp_path):
     assert np.allclose(data[0], om / 2 / np.pi, rtol=1e-15)
     assert np.array_equal(data[1::2], np.abs(xa[0]).T) and np.array_equal(data[2::2], np.angle(xa[0]).T)
     del ref
+
+
+def test_opinfo_report_matches_the_reference_report(tmp_path):
+    """`.opinfo` (results.py:441-475): same RESULTS table, resistor / source tables and total
+    power as the file the reference writes for the same circuit — values fed from the oracle's
+    OP.  Skipped where the reference package is absent."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'oracle'))
+    import ref_loop
+    if ref_loop.reference_path() is None:
+        pytest.skip("reference package not on this machine")
+    ref = ref_loop._load()
+    import zoo
+
+    def build(Circuit):
+        c = Circuit('opinfo check')
+        c.add_vsource('V1', 'a', c.gnd, dc_value=2.)
+        c.add_resistor('R1', 'a', 'b', 1e3)
+        c.add_resistor('R2', 'b', c.gnd, 3e3)
+        c.add_isource('I1', 'b', c.gnd, dc_value=1e-3)
+        return c
+    rc = build(ref.Circuit)
+    f_ref = str(tmp_path / 'ref.op')
+    ref.run(rc, ref.new_op(outfile=f_ref, verbose=0))
+    ours = build(Circuit)
+    o = oracle.Oracle(ours).op()
+    sol = results.op_solution(ours, dict(x=o['x'], resid=o['resid'], iters=o['iters'], status=o['status']))
+    f_our = str(tmp_path / 'our.opinfo')
+    sol.write_opinfo(f_our, ours)
+    a, b = open(f_ref + '.opinfo', encoding='utf-8').read(), open(f_our, encoding='utf-8').read()   # new_op appends '.op', write_to_file 'info'
+
+    def section(txt, start, stop):
+        return txt[txt.index(start):txt.index(stop)]
+    # RESULTS table: same variables, units and values (the Error column is the solver residual)
+    ra = [ln.split() for ln in section(a, 'RESULTS:', 'ELEMENTS OP').splitlines() if ln[:1] in 'VI' and '(' in ln or ln[:2] in ('VA', 'VB')]
+    rb = [ln.split() for ln in section(b, 'RESULTS:', 'ELEMENTS OP').splitlines() if ln[:1] in 'VI' and '(' in ln or ln[:2] in ('VA', 'VB')]
+    assert [r[:2] for r in ra] == [r[:2] for r in rb] and len(ra) == 3
+    assert np.allclose([float(r[2]) for r in ra], [float(r[2]) for r in rb], rtol=1e-5, atol=1e-12)
+    # element tables and total power, number by number
+    import re
+    num = re.compile(r'-?\d+\.?\d*(?:e[-+]?\d+)?')
+    ta = section(a, 'ELEMENTS OP INFORMATION', 'Total power')
+    tb = section(b, 'ELEMENTS OP INFORMATION', 'Total power')
+    for pid in ('R1', 'R2', 'V1', 'I1'):
+        la = [ln for ln in ta.splitlines() if ln.startswith(pid)][0]
+        lb = [ln for ln in tb.splitlines() if ln.startswith(pid)][0]
+        assert np.allclose([float(t) for t in num.findall(la)[1:]], [float(t) for t in num.findall(lb)[1:]], rtol=1e-5, atol=1e-12), (la, lb)
+    pa = float(num.findall(a[a.index('Total power dissipation'):])[0])
+    pb = float(num.findall(b[b.index('Total power dissipation'):])[0])
+    assert abs(pa - pb) <= 1e-5 * abs(pa)
+    assert 'Convergence reached in' in b and 'vea =' in b

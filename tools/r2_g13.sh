@@ -1,8 +1,8 @@
 set -x
 export AHK_DEBUG=1
-timeout 1500 python -m pytest tests -m gpu -x -q -k "ladder or mesh" > gpurun_out/r2m_gputests.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2m_gputests.log
+timeout 1500 python -m pytest tests -m gpu -x -q -k "ladder or mesh" > gpurun_out/r2n_gputests.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2n_gputests.log
 unset AHK_DEBUG
-timeout 600 python - > gpurun_out/r2m_bign_time.txt 2>&1 <<'PY'
+timeout 600 python - > gpurun_out/r2n_bign_time.txt 2>&1 <<'PY'
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np, torch
