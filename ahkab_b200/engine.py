@@ -309,8 +309,8 @@ class Engine(object):
         if method not in _abi.METHODS:
             raise ValueError("unknown method %s" % method)
         if max_rows is None:
-            max_rows = self.default_max_rows(tstart, tstep, tstop,
-                                             use_step_control)
+            max_rows = self._cap_max_rows(self.default_max_rows(tstart, tstep, tstop,
+                                                                use_step_control))
         x0 = self._x0(x0)
         pk = self._new_packed((('t', (self.B, max_rows), torch.float64),
                                ('x', (self.B, max_rows, self.n), torch.float64),
@@ -372,6 +372,16 @@ class Engine(object):
         # step; 64x the nominal count (min 4096) covers stiff oscillators, the
         # ROWS_FULL status bit reports the rare overflow.
         return max(4096, 64 * nominal)
+
+    def _cap_max_rows(self, max_rows):
+        """Row buffers are [B][max_rows][n + 1] doubles: keep the default inside a quarter of
+        the device memory (the ROWS_FULL status bit reports an overflow)."""
+        try:
+            free, total = torch.cuda.mem_get_info(self.device)
+        except Exception:
+            return max_rows
+        per_row = 8.0 * (self.n + 1) * max(1, self.B)
+        return int(max(16, min(max_rows, (0.25 * total) // per_row)))
 
     def ac(self, omegas, x_op=None):
         om = np.ascontiguousarray(omegas, np.float64)

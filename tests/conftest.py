@@ -28,6 +28,22 @@ def pytest_configure(config):
             subprocess.check_call(['sh', script], stdout=subprocess.DEVNULL)
 
 
+def pytest_collection_modifyitems(config, items):
+    """A machine without a CUDA device skips the GPU tests instead of failing them (the engine
+    itself still fails loudly there: tests/test_abi.py::test_no_cpu_fallback)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200)")
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 

@@ -176,3 +176,34 @@ def test_argument_errors_raise():
     e9 = Engine(w9.circuit(Circuit), w9.batch())
     with pytest.raises(EngineError):
         e9.set_variant(real=2)                    # Var<4,3,1> cannot hold n = 9
+
+
+@pytest.mark.gpu
+def test_near_tie_pivots_of_the_multi_lane_solve():
+    """The multi-lane Gauss-Jordan compares pivot candidates through a key that treats
+    magnitudes equal to 2^-47 as ties (lowest row wins), where LAPACK's idamax takes the
+    exact maximum: here column 0 holds 1 - 2^-50 in rows 0, 1 and exactly 1 in the KVL row
+    2 (pass 2, no Gmin), so the two rules pick DIFFERENT pivot rows.  Both are valid
+    pivots: the solutions must agree to rounding."""
+    import oracle
+    from ahkab_b200 import _abi
+    from ahkab_b200.circuit import Circuit
+    from ahkab_b200.engine import Engine
+    c = Circuit('near tie')
+    c.add_vsource('V1', 'a', c.gnd, dc_value=1.)
+    c.add_resistor('R1', 'a', 'b', 1.0 + 2.0 ** -50)       # 1/R1 = 1 - 2^-50
+    c.add_resistor('R2', 'b', c.gnd, 1.0)
+    assert 1.0 / (1.0 + 2.0 ** -50) == 1.0 - 2.0 ** -50
+    o = oracle.Oracle(c).op()
+    table = {i: (NC, R, G) for i, NC, R, G in _abi.variants('real')}
+    multi = [i for i in _abi.fitting_variants(3, 'real') if table[i][2] > 1]
+    assert multi
+    for v in [-1] + multi:
+        for jit in ('off', 'on'):
+            e = Engine(c)
+            e.set_variant(real=v)
+            e.set_jit(jit)
+            r = e.op()
+            x = r['x'].cpu().numpy()
+            assert (r['status'].cpu().numpy() & 1).all()
+            assert np.abs(x - o['x']).max() <= 1e-14, (v, jit, x, o['x'])
