@@ -544,7 +544,12 @@ int pick_variant(const ahk_engine* e, const VarInfo* tab, int ntab, int forced, 
     if (plan(e, units, i, q, stride_of(q), tmp, reg_blocks_of(q.NC), &res))
       continue;   // does not fit in shared memory
     const long long lanes = std::min(res, per_sm) * q.G;
-    if (res >= per_sm && per_sm * q.G >= 128 &&
+    // (specialised kernels, one lane per instance: measured best at EVERY batch size on C2 —
+    // 14.3 us at 2 K-16 K instances where 4 / 16 lanes per instance take 35 / 31 us,
+    // profiles/r2s_c2_shapes.txt: the straight-line one-lane LU has the shortest serial chain,
+    // and a small batch is bound by that chain, not by idle lanes)
+    const bool one_lane_jit = exact_nc && q.G == 1 && res >= per_sm;
+    if (res >= per_sm && (per_sm * q.G >= 128 || one_lane_jit) &&
         (best_one_wave < 0 || q.G < tab[best_one_wave].G))
       best_one_wave = i;
     if (best < 0 || lanes > best_lanes || (lanes == best_lanes && q.G < tab[best].G)) {
@@ -725,11 +730,18 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
       //  * larger matrices: rows distributed, about five per lane.
       const int nd = (int)e->H.dev.size();
       int G = 1, R;
+      //  * small batches leave the machine empty and every instance is a serial chain: more
+      //    lanes per instance shorten it, as long as the batch still runs in one wave (C4 at
+      //    2048 / 4096 instances: 8 lanes 37 / 43 ms, 2 lanes 65 / 66 ms; C3 at 2048 / 4096: 4
+      //    lanes 4.7 / 4.9 ms, 2 lanes 6.3 / 6.7 ms — profiles/r2s_c4_small.txt, r2s_c3_small.txt;
+      //    at the full 16 384 the two-lane shapes win: 68 vs 87 ms, 6.5 vs 7.1 ms)
       if (e->n <= 6) {
         while (G < 8 && (nd + G - 1) / G > 3) G *= 2;
+        while (G < 8 && B * (2 * G) / 32 <= 1184) G *= 2;
         R = e->n;
       } else {
         while (G < 32 && (e->n + G - 1) / G > 5) G *= 2;
+        while (G < 16 && B * (2 * G) / 32 <= 600) G *= 2;
         R = (e->n + G - 1) / G;
       }
       vid = 1000 + R * 64 + G;

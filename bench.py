@@ -123,7 +123,9 @@ class Runner(object):
         self.eng = Engine(self.circ, self.w.batch(lo, hi), opts=self.w.opts)
         # (threshold 1024: the chunks of the pipelined end-to-end paths are sub-batches of
         # 1024 instances and the bench repeats every call, so the compilation amortises)
-        self.eng.set_jit(JIT_MODE, min_batch=1024)
+        # (a rank's shard of a strong-scaling run may be smaller than that — C1 / C5 at 8 GPUs hold
+        # 512 instances each: the bench repeats every call, so the compilation amortises there too)
+        self.eng.set_jit(JIT_MODE, min_batch=min(1024, max(1, B)))
         self.B = B
         self.pipe = None
         self.vary_host = torch.empty(self.eng.vary.shape, dtype=torch.float64,
@@ -574,6 +576,11 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     # end to end, host buffers
     hbm_resident = breakdown = None
     if dist_on:
+        # (NCCL sets its point-to-point channels up lazily, pair by pair, over the first exchanges:
+        # a fixed number of untimed gathers first — the first workload of an 8-rank run otherwise
+        # reads 0.45 ms per step for the HBM-resident figure and 0.18 ms for the longer path)
+        for _ in range(8):
+            r.e2e_dist(d2h=False)
         ms_a, _ = timer.timed(lambda: r.e2e_dist(d2h=False), steps, warmup)
         hbm_resident = {"value": units * steps / (ms_a * 1e-3), "ms_per_step": ms_a / steps,
                         "what": "same step, clock stopped when the gathered results are in rank 0's HBM"}
