@@ -8,7 +8,7 @@
 
 Importing the package does not need a GPU; running an analysis does (the CUDA
 library has no CPU fallback)."""
-from . import options, constants, time_functions            # noqa: F401
+from . import options, constants, time_functions, netlist   # noqa: F401
 from .circuit import Circuit                                  # noqa: F401
 from .batch import ParamBatch                                 # noqa: F401
 from .analyses import (new_op, new_dc, new_tran, new_ac, queue, run,   # noqa: F401
