@@ -221,7 +221,7 @@ def _run_tran(circ, eng, tstart, tstep, tstop, method=None,
         raise ValueError("tstep < 0")
     raw = eng.tran(_resolve_x0(x0, eng), tstart, tstep, tstop, method=method,
                    use_step_control=use_step_control, max_rows=max_rows)
-    return results.tran_solution(circ, raw, tstart, tstop, method)
+    return results.tran_solution(circ, raw, tstart, tstop, method, engine=eng)
 
 
 def _run_ac(circ, eng, start, points, stop, sweep_type=None, x0=None,

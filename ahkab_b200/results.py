@@ -277,12 +277,50 @@ class tran_solution(solution):
     sol_type = "TRAN"
 
     def __init__(self, circ, raw, tstart, tstop, method, engine=None):
-        solution.__init__(self, circ, raw, engine)
+        solution.__init__(self, circ, dict(raw), engine)
         names, units = _varnames(circ, upper=True)
         self.variables = ["T"] + names
         self.units = dict(units)
         self.units["T"] = "s"
         self.tstart, self.tstop, self.method = tstart, tstop, method
+
+    # With an engine behind it the solution reads PACKED rows: the kernel writes ragged
+    # [B][max_rows] buffers (rows[b] of them used: C4 ~1790 of 3072), `Engine.pack_tran` packs
+    # the rows that exist contiguously on the device and ONE device->host copy brings them over;
+    # the padded device buffers are released.  Per-instance access slices the packed arrays;
+    # per-variable access builds a NaN-padded (B, max(rows)) array on the host.
+    def _fetch_packed(self):
+        if self._np.get('_packed_rows') is not None or self._engine is None:
+            return self._np.get('_packed_rows')
+        if not (hasattr(self.raw.get('t'), 'is_cuda') and self.raw['t'].is_cuda):
+            return None
+        pk = self._engine.pack_tran(self.raw)
+        host = self._engine.to_host_owned(pk)
+        rows = host['rows']
+        total = int(rows.sum())
+        offs = np.zeros(len(rows) + 1, np.int64)
+        np.cumsum(rows, out=offs[1:])
+        P = dict(t=host['t'][:total], x=host['x'][:total], offsets=offs)
+        self._np.update(rows=rows, counters=host['counters'], status=host['status'], _packed_rows=P)
+        self._shape = tuple(self.raw['t'].shape)
+        self.raw = {k: (None if k in ('t', 'x', '_packed') else v) for k, v in self.raw.items()}
+        return P
+
+    def _get(self, key):
+        if key in ('t', 'x') and key not in self._np:
+            P = self._fetch_packed()
+            if P is not None:                     # padded view of the packed rows, built on demand
+                rows, offs = self._np['rows'], P['offsets']
+                width = int(rows.max()) if len(rows) else 0
+                shape = (len(rows), width) + P[key].shape[1:]
+                a = np.full(shape, np.nan)
+                for b in range(len(rows)):
+                    a[b, :rows[b]] = P[key][offs[b]:offs[b + 1]]
+                self._np[key] = a
+                return a
+        elif key in ('rows', 'counters', 'status') and key not in self._np:
+            self._fetch_packed()
+        return solution._get(self, key)
 
     @property
     def rows(self):
@@ -302,6 +340,14 @@ class tran_solution(solution):
 
     def __getitem__(self, name):
         i = self._index(name)
+        P = self._fetch_packed()
+        if P is not None:
+            rows, offs = self._np['rows'], P['offsets']
+            col = P['t'] if i == 0 else P['x'][:, i - 1]
+            a = np.full((len(rows), int(rows.max()) if len(rows) else 0), np.nan)
+            m = np.arange(a.shape[1])[None, :] < rows[:, None]
+            a[m] = col                           # row-major fill == instance-major packed order
+            return a
         if i == 0:
             return self._masked(self._get('t'))
         return self._masked(self._get('x')[:, :, i - 1])
@@ -311,9 +357,26 @@ class tran_solution(solution):
 
     def instance(self, b):
         """(1 + n, rows[b]) array of instance b — the reference's asarray()."""
+        P = self._fetch_packed()
+        if P is not None:
+            lo, hi = P['offsets'][b], P['offsets'][b + 1]
+            return np.concatenate((P['t'][None, lo:hi], P['x'][lo:hi].T), axis=0)
         r = int(self.rows[b])
         return np.concatenate((self._get('t')[b, None, :r],
                                self._get('x')[b, :r, :].T), axis=0)
+
+    def packed(self):
+        """(t [R], x [R, n], offsets [B + 1]): every accepted row of every instance, instance
+        after instance — the cheapest host view of a large transient batch."""
+        P = self._fetch_packed()
+        if P is None:
+            rows = self.rows
+            offs = np.zeros(len(rows) + 1, np.int64)
+            np.cumsum(rows, out=offs[1:])
+            t, x = self._get('t'), self._get('x')
+            return (np.concatenate([t[b, :rows[b]] for b in range(len(rows))]),
+                    np.concatenate([x[b, :rows[b]] for b in range(len(rows))]), offs)
+        return P['t'], P['x'], P['offsets']
 
     def get_x(self):
         return self['T']

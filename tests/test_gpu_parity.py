@@ -246,6 +246,49 @@ def test_run_api_matches_engine():
         ahkab.options.vea, ahkab.options.iea = 1e-6, 1e-9
     assert (res['tran'].rows == 250).all()
     assert res['tran'].keys()[:3] == ['T', 'VDD', 'VND']
+    # the solution reads PACKED rows from the device (one copy); every view agrees with the
+    # engine's padded buffers and with the oracle
+    tr = res['tran']
+    t, x, offs = tr.packed()
+    assert t.shape == (16 * 250,) and x.shape == (16 * 250, 9) and offs[-1] == 16 * 250
+    orc = _oracle(w)
+    ot = orc.tran(common.c3_x0(orc.op()['x']), 0., W.C3_TRAN['tstep'], W.C3_TRAN['tstop'], 'TRAP', False, 256)
+    for b in (0, 7, 15):
+        inst = tr.instance(b)
+        assert inst.shape == (10, 250)
+        assert np.array_equal(inst[0], ot['t'][b, :250])
+        assert common.parity_tol(inst[1:].T, ot['x'][b, :250], 5, 1e-6, 1e-6) < 1.0
+    v = tr['VND']
+    assert v.shape == (16, 250) and np.array_equal(v[3], tr.instance(3)[2])
+    assert np.array_equal(tr['T'][5], ot['t'][5, :250])
+
+
+def test_lte_transient_results_are_ragged_and_packed():
+    """C4 (LTE step control) through run(): rows differ per instance; the padded per-variable
+    view carries NaN beyond rows[b], the packed view holds exactly the accepted rows."""
+    import ahkab_b200 as ahkab
+    w = W.c4_ring3(12)
+    circ = w.circuit(ahkab.Circuit)
+    saved = {k: getattr(ahkab.options, k) for k in w.opts}
+    for k, v_ in w.opts.items():
+        setattr(ahkab.options, k, v_)
+    try:
+        x0 = ahkab.new_x0(circ, W.C4_IC)
+        tr = ahkab.run(circ, ahkab.new_tran(x0=x0, **W.C4_TRAN), batch=w.batch())['tran']
+    finally:
+        for k, v_ in saved.items():
+            setattr(ahkab.options, k, v_)
+    rows = tr.rows
+    assert (tr.status & 1).all() and rows.min() > 100 and rows.max() > rows.min()
+    t, x, offs = tr.packed()
+    assert offs[-1] == rows.sum() and len(t) == rows.sum()
+    v = tr['T']
+    assert v.shape == (12, rows.max())
+    for b in range(12):
+        assert np.isnan(v[b, rows[b]:]).all() and not np.isnan(v[b, :rows[b]]).any()
+        assert np.array_equal(v[b, :rows[b]], t[offs[b]:offs[b + 1]])
+        assert np.array_equal(tr.instance(b)[1:].T, x[offs[b]:offs[b + 1]])
+        assert (np.diff(t[offs[b]:offs[b + 1]]) > 0).all()
 
 
 def test_c5_big_linear_paths_agree(monkeypatch):
