@@ -827,23 +827,39 @@ AHK_DEV int lu_panel_dense(Ctx& c, const int k0) {
       const int jb = j0 + g;
       const double b0 = jb < n ? U0[jb] : 0.0, b1 = jb < n ? U1[jb] : 0.0;
       const int jc = j0 + 2 * tig;
-      for (int t0 = 0; t0 < cnt; t0 += 8) {
-        const int r = t0 + g < cnt ? (int)list[t0 + g] : -1;
-        double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
-        double* Cr = nullptr;
-        if (r >= 0) {
-          a0 = -Lp[r * NB + tig]; a1 = -Lp[r * NB + 4 + tig];
-          Cr = A + (size_t)r * RS + jc;
-          if (jc + 1 < n) { const double2 cc = *(const double2*)Cr; c0 = cc.x; c1 = cc.y; }
-          else if (jc < n) c0 = Cr[0];
+      // four row tiles per pass: all their loads are in flight before the first MMA needs one
+      // (a warp is alone with its instance: memory-level parallelism is what hides the L2 latency)
+      for (int t0 = 0; t0 < cnt; t0 += 32) {
+        double a0[4], a1[4], c0[4], c1[4];
+        double* Cr[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int t = t0 + 8 * q + g;
+          const int r = t < cnt ? (int)list[t] : -1;
+          a0[q] = a1[q] = c0[q] = c1[q] = 0.0;
+          Cr[q] = nullptr;
+          if (r >= 0) {
+            a0[q] = -Lp[r * NB + tig]; a1[q] = -Lp[r * NB + 4 + tig];
+            Cr[q] = A + (size_t)r * RS + jc;
+            if (jc + 1 < n) { const double2 cc = *(const double2*)Cr[q]; c0[q] = cc.x; c1[q] = cc.y; }
+            else if (jc < n) c0[q] = Cr[q][0];
+          }
         }
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(a0), "d"(b0));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(a1), "d"(b1));
-        if (r >= 0) {
-          if (jc + 1 < n) *(double2*)Cr = make_double2(c0, c1);
-          else if (jc < n) Cr[0] = c0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (t0 + 8 * q < cnt) {        // (warp-uniform)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[q]), "+d"(c1[q]) : "d"(a0[q]), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[q]), "+d"(c1[q]) : "d"(a1[q]), "d"(b1));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (Cr[q]) {
+            if (jc + 1 < n) *(double2*)Cr[q] = make_double2(c0[q], c1[q]);
+            else if (jc < n) Cr[q][0] = c0[q];
+          }
         }
       }
     }

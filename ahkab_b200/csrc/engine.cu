@@ -737,10 +737,16 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
       //    at the full 16 384 the two-lane shapes win: 68 vs 87 ms, 6.5 vs 7.1 ms)
       if (e->n <= 6) {
         while (G < 8 && (nd + G - 1) / G > 3) G *= 2;
-        while (G < 8 && B * (2 * G) / 32 <= 1184) G *= 2;
+        // (C4: 8 lanes — one device per lane — win up to 8 K instances: 55.6 vs 63.0 ms with 4
+        // lanes and 69 ms with 2; from 16 K on the batch fills the machine and 2 lanes win)
+        int gdev = 1;                       // lanes that would each own a device
+        while (gdev < 8 && gdev < nd) gdev *= 2;
+        if (gdev > G && B * gdev / 32 <= 2368) G = gdev;
         R = e->n;
       } else {
         while (G < 32 && (e->n + G - 1) / G > 5) G *= 2;
+        // (C3 at 8 K instances: 4 lanes 5.3 ms, 2 lanes 6.8 ms; at 4 K: 4 lanes 4.9, 8 lanes 5.5)
+        if (B * (2 * G) / 32 <= 1184) G *= 2;
         while (G < 16 && B * (2 * G) / 32 <= 600) G *= 2;
         R = (e->n + G - 1) / G;
       }
