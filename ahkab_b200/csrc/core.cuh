@@ -246,12 +246,39 @@ AHK_DEV void build_values(Ctx& c, bool with_D) {
   Grp<V::G>::sync(c.mask);
   double* Mv = c.vb() + c.L->Mv;
   double* Dv = c.vb() + c.L->Dv;
+  bool gathered = false;
+#ifndef AHK_JIT
+  if (c.L->big) {
+    // Large circuits: the MNA values in GATHER form, one position per lane (the term lists of
+    // program_build.hpp replay the stamp operations below per position, in the same order:
+    // same sums, bit for bit).  The serial replay by one lane cost a dense 202-node mesh
+    // (19 900 resistors, values in global memory) 40 % of its whole OP (ncu,
+    // profiles/r2w_ncu_source_lines_large_n_mesh202.txt).
+    for (int q = c.sub; q < p.npos; q += G) {
+      double v = 0.0;
+      for (int t = p.term_ptr[q]; t < p.term_ptr[q + 1]; t++) {
+        const int kd = p.term_kind[t], ak = kd < 0 ? -kd : kd;
+        const double sg = kd < 0 ? -1.0 : 1.0;
+        if (ak == 1) v += sg * (1. / c.P(p.term_slot[t]));
+        else if (ak == 2) v += sg * c.P(p.term_slot[t]);
+        else v += sg;
+      }
+      Mv[q] = v;
+      if (with_D) Dv[q] = 0.0;
+    }
+    gathered = true;
+    Grp<V::G>::sync(c.mask);
+  }
+#endif
   if (c.sub == 0) {
-    AHK_UNROLL
-    for (int k = 0; k < p.npos; k++) { Mv[k] = 0.0; if (with_D) Dv[k] = 0.0; }
+    if (!gathered) {
+      AHK_UNROLL
+      for (int k = 0; k < p.npos; k++) { Mv[k] = 0.0; if (with_D) Dv[k] = 0.0; }
+    }
     AHK_UNROLL
     for (int k = 0; k < p.nlin; k++) {
       const LinOp& op = p.lin[k];
+      if (gathered && op.kind < K_C) continue;      // (only the D operations are left to replay)
       const int* q = op.pos;
 #define ADDP(arr, i, v) do { if (q[i] >= 0) arr[q[i]] += (v); } while (0)
 #define SETP(arr, i, v) do { if (q[i] >= 0) arr[q[i]] = (v); } while (0)
@@ -712,6 +739,14 @@ AHK_DEV int big_popc(unsigned v) {
 #endif
 }
 
+AHK_DEV void big_or(unsigned* p, unsigned v) {     // lanes of one warp may hit the same word
+#ifdef __CUDACC__
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+
 // once per instance: the whole matrix zero, no entry flagged
 template <int G>
 AHK_DEV void big_init(Ctx& c, double* A, size_t len) {
@@ -904,7 +939,17 @@ AHK_DEV int lu_solve_glob(Ctx& c) {
   unsigned short* prow = (unsigned short*)(c.sm + c.L->bytes);
   unsigned short* stepof = prow + n;    // 0xffff: row not used as a pivot row yet
   unsigned short* list = stepof + n;
+  // The same structure by COLUMNS (czm[col]: bitmap of the rows with an entry in it) and a
+  // bitmap of the used rows give the candidates of a pivot step directly — ncu on the
+  // 252-unknown ladder: scanning all n rows per step for the pivot and for the multipliers was
+  // 1065 warp instructions per pivot step on a lone warp (7 cycles each), 60 % of the kernel.
+  // Maintained while the elimination is sparse; after the first dense panel (which does not
+  // maintain it) the steps fall back to the row scan (`densemode`).
+  unsigned* czm = (unsigned*)(c.sm + (c.L->czm < 0 ? 0 : c.L->czm));
+  unsigned* usedw = (unsigned*)((char*)prow + ((6 * n + 3) & ~3));   // behind the three 16-bit arrays, 4-byte aligned
+  bool densemode = c.L->czm < 0;        // dense stamp pattern: no column bitmaps at all
   for (int r = c.sub; r < n; r += G) stepof[r] = 0xffff;
+  for (int w = c.sub; w < W; w += G) usedw[w] = 0u;
   Grp<G>::sync(gm);
   for (int k = 0; k < n; k++) {
     if ((k & (BIG_NB - 1)) == 0 && k + BIG_NB + 8 <= n) {
@@ -925,48 +970,123 @@ AHK_DEV int lu_solve_glob(Ctx& c) {
         const int ok = lu_panel_dense<G, FLAT>(c, k);
         if (!ok) { if (!FLAT) return 0; nonsing = 0; }
         k += BIG_NB - 1;
+        densemode = true;
         continue;
       }
     }
-    const int kw = k >> 5;
-    const unsigned kb = 1u << (k & 31);
     double best = -1.0;
     int bi = -1;
-    for (int r = c.sub; r < n; r += G) {
-      if (stepof[r] != 0xffff) continue;
-      const double a = (nzm[r * W + kw] & kb) ? A[(size_t)r * RS + k] : 0.0;
-      dx[r] = a;
-      const double v = fabs(a);
-      if (bi < 0 || v > best) { best = v; bi = r; }
-    }
-    Grp<G>::argmax(best, bi, gm);
-    if (best == 0.0) {
-      if (!FLAT) return 0;
-      nonsing = 0;
-    }
-    if (c.sub == 0) { prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k; }
-    Grp<G>::sync(gm);
-    const double inv = 1.0 / dx[bi];
-    // rows of this step: not yet used, multiplier not zero
     int cnt = 0;
-    for (int r0 = 0; r0 < n; r0 += G) {
-      const int r = r0 + c.sub;
-      bool nz = false;
-      if (r < n && stepof[r] == 0xffff) {
-        const double l = dx[r] * inv;
-        nz = l != 0.0;
-        if (nz) dx[r] = l;
+    if (!densemode) {
+      // ---- sparse step: the candidates are the flagged, unused rows of column k ----
+      const unsigned* cz = czm + k * W;
+      for (int w = c.sub; w < W; w += G) {
+        unsigned bits = cz[w] & ~usedw[w];
+        while (bits) {
+          const int r = (w << 5) + big_ctz(bits);
+          bits &= bits - 1;
+          const double a = A[(size_t)r * RS + k];
+          dx[r] = a;
+          const double v = fabs(a);
+          if (bi < 0 || v > best) { best = v; bi = r; }   // (ascending rows: the first maximum stays)
+        }
       }
+      Grp<G>::argmax(best, bi, gm);
+      if (bi < 0 || best == 0.0) {       // no entry / only zeros in the column: singular
+        if (!FLAT) return 0;
+        nonsing = 0;
+        if (bi < 0) {                    // (flat kernels run on: any unused row, the result is discarded)
+          for (int w = 0; w < W && bi < 0; w++) {
+            unsigned u = ~usedw[w];
+            if (w == W - 1 && (n & 31)) u &= (1u << (n & 31)) - 1u;
+            if (u) bi = (w << 5) + big_ctz(u);
+          }
+          if (c.sub == 0) dx[bi] = 1.0;
+        }
+      }
+      if (c.sub == 0) {
+        prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k;
+        usedw[bi >> 5] |= 1u << (bi & 31);
+      }
+      Grp<G>::sync(gm);
+      const double inv0 = 1.0 / dx[bi];
+      // rows of this step: candidates whose multiplier is not zero, in ascending order
 #ifdef __CUDACC__
-      if (G == 32) {
-        const unsigned bal = __ballot_sync(0xffffffffu, nz);
-        if (nz) list[cnt + __popc(bal & ((1u << c.sub) - 1u))] = (unsigned short)r;
-        cnt += __popc(bal);
+      if (G == 32) {               // W <= 16 words: one word per lane, offsets by a warp scan
+        const int w = c.sub;
+        unsigned nzb = 0u;
+        if (w < W) {
+          unsigned bits = cz[w] & ~usedw[w];
+          while (bits) {
+            const int bq = big_ctz(bits);
+            bits &= bits - 1;
+            const int r = (w << 5) + bq;
+            const double l = dx[r] * inv0;
+            if (l != 0.0) { dx[r] = l; nzb |= 1u << bq; }
+          }
+        }
+        const int my = __popc(nzb);
+        int off = my;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, off, o);
+          if (c.sub >= o) off += t;
+        }
+        cnt = __shfl_sync(0xffffffffu, off, 31);
+        off -= my;
+        while (nzb) { list[off++] = (unsigned short)((w << 5) + big_ctz(nzb)); nzb &= nzb - 1; }
       } else
 #endif
-      { if (nz) list[cnt++] = (unsigned short)r; }     // one lane per instance
+      {
+        for (int w = 0; w < W; w++) {
+          unsigned bits = cz[w] & ~usedw[w];
+          while (bits) {
+            const int r = (w << 5) + big_ctz(bits);
+            bits &= bits - 1;
+            const double l = dx[r] * inv0;
+            if (l != 0.0) { dx[r] = l; list[cnt++] = (unsigned short)r; }
+          }
+        }
+      }
+      Grp<G>::sync(gm);
+    } else {
+      // ---- after a dense panel: scan the rows ----
+      const int kw = k >> 5;
+      const unsigned kb = 1u << (k & 31);
+      for (int r = c.sub; r < n; r += G) {
+        if (stepof[r] != 0xffff) continue;
+        const double a = (nzm[r * W + kw] & kb) ? A[(size_t)r * RS + k] : 0.0;
+        dx[r] = a;
+        const double v = fabs(a);
+        if (bi < 0 || v > best) { best = v; bi = r; }
+      }
+      Grp<G>::argmax(best, bi, gm);
+      if (best == 0.0) {
+        if (!FLAT) return 0;
+        nonsing = 0;
+      }
+      if (c.sub == 0) { prow[k] = (unsigned short)bi; stepof[bi] = (unsigned short)k; }
+      Grp<G>::sync(gm);
+      const double inv = 1.0 / dx[bi];
+      for (int r0 = 0; r0 < n; r0 += G) {
+        const int r = r0 + c.sub;
+        bool nz = false;
+        if (r < n && stepof[r] == 0xffff) {
+          const double l = dx[r] * inv;
+          nz = l != 0.0;
+          if (nz) dx[r] = l;
+        }
+#ifdef __CUDACC__
+        if (G == 32) {
+          const unsigned bal = __ballot_sync(0xffffffffu, nz);
+          if (nz) list[cnt + __popc(bal & ((1u << c.sub) - 1u))] = (unsigned short)r;
+          cnt += __popc(bal);
+        } else
+#endif
+        { if (nz) list[cnt++] = (unsigned short)r; }     // one lane per instance
+      }
+      Grp<G>::sync(gm);
     }
-    Grp<G>::sync(gm);
     const double* Ap = A + (size_t)bi * RS;
     const unsigned* nzp = nzm + bi * W;
     const double bp = b[bi];
@@ -983,7 +1103,16 @@ AHK_DEV int lu_solve_glob(Ctx& c) {
           double* Ar = A + (size_t)r * RS;
 #pragma unroll 4
           for (int j = k + 1 + c.sub; j < n; j += G) Ar[j] -= l * Ap[j];
-          for (int w = w0 + c.sub; w < W; w += G) nzm[r * W + w] |= nzp[w] & (w == w0 ? m0 : ~0u);
+          for (int w = w0 + c.sub; w < W; w += G) {
+            const unsigned bits = nzp[w] & (w == w0 ? m0 : ~0u), old = nzm[r * W + w];
+            nzm[r * W + w] = old | bits;
+            unsigned nb = densemode ? 0u : bits & ~old;      // fill-in: the column bitmaps follow
+            while (nb) {
+              const int j = (w << 5) + big_ctz(nb);
+              nb &= nb - 1;
+              big_or(&czm[j * W + (r >> 5)], 1u << (r & 31));
+            }
+          }
         }
       } else {
         // sparse pivot row: the lanes split the (row, bitmap word) pairs
@@ -994,7 +1123,14 @@ AHK_DEV int lu_solve_glob(Ctx& c) {
           const int r = list[t];
           const double l = dx[r];
           double* Ar = A + (size_t)r * RS;
-          nzm[r * W + w] |= bits;
+          const unsigned old = nzm[r * W + w];
+          nzm[r * W + w] = old | bits;
+          unsigned nb = densemode ? 0u : bits & ~old;        // fill-in: the column bitmaps follow
+          while (nb) {
+            const int j = (w << 5) + big_ctz(nb);
+            nb &= nb - 1;
+            big_or(&czm[j * W + (r >> 5)], 1u << (r & 31));
+          }
           while (bits) {
             const int j = (w << 5) + big_ctz(bits);
             bits &= bits - 1;
@@ -1128,6 +1264,9 @@ AHK_DEV int assemble_solve(Ctx& c) {
         double* Ar = A + (size_t)(item / W) * RS + ((item % W) << 5);
         while (bits) { Ar[big_ctz(bits)] = 0.0; bits &= bits - 1; }
       }
+      const bool cz = c.L->czm >= 0;
+      unsigned* czm = (unsigned*)(c.sm + (cz ? c.L->czm : 0));
+      if (cz) for (int i = c.sub; i < n * W; i += G) czm[i] = 0u;
       Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
       double* b = c.sm + c.L->brhs;
       const Prog& p = *c.p;
@@ -1136,6 +1275,7 @@ AHK_DEV int assemble_solve(Ctx& c) {
         for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {     // the stamp pattern of the row
           const int col = p.pcol[k];
           nzm[r * W + (col >> 5)] |= 1u << (col & 31);
+          if (cz) big_or(&czm[col * W + (r >> 5)], 1u << (r & 31));
         }
       }
       Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);

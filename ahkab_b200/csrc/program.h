@@ -13,7 +13,7 @@ namespace ahk {
 // instance.  The reference solves any circuit densely (dc_analysis.py:796-822); its own limit
 // for switching to sparse storage is 400 unknowns (options.py:68).
 #define AHK_BIG_NMAX 512
-#define AHK_VGLOB_NPOS 2048    // large-n layouts: more matrix positions than this -> value arrays in global memory
+#define AHK_VGLOB_NPOS 512     // large-n layouts: more matrix positions than this -> value arrays in global memory (read once per Newton iteration; shared memory there is worth more as occupancy)
 
 enum { K_R = 1, K_G, K_VDE, K_E, K_H, K_F, K_C, K_L, K_K };
 
@@ -94,6 +94,7 @@ struct Layout {     // offsets in doubles inside one instance's slice
   int big;          // 1: large-n layout — the matrix is in the global workspace (Ctx::Ag), not at A
   int brhs;         // large-n layout: right-hand side column [n]
   int nzm;          // large-n layout: per-row bitmaps of the non-zero columns, [n][(n + 31) / 32] words
+  int czm;          // large-n layout: per-COLUMN bitmaps of the rows with an entry, [n][(n + 31) / 32] words; -1: none (dense pattern)
   int lpan;         // large-n layout: multipliers of the current dense panel, [n][8] — offset in the GLOBAL workspace (from Ctx::Ag)
   int vglob;        // large-n layout of a circuit with many matrix positions (dense patterns): the
                     // per-position value arrays Mv / Dv / Bv live in the global workspace too
