@@ -27,8 +27,22 @@ def _is_arr(v):
 
 class Flat(object):
     """Result of `flatten`: everything the engine needs for one topology and
-    (optionally) one batch."""
-    pass
+    (optionally) one batch.  `vary` ([n_vary][B], slot-major) is stacked from `vary_rows` on
+    first use: the engine uploads a fresh batch row by row into its pinned staging instead."""
+    _vary = None
+    vary_rows = ()
+    uploads = 0
+
+    @property
+    def vary(self):
+        if self._vary is None:
+            self._vary = (np.ascontiguousarray(np.stack(self.vary_rows)) if len(self.vary_rows)
+                          else np.zeros((0, self.B or 0)))
+        return self._vary
+
+    @vary.setter
+    def vary(self, v):
+        self._vary = v
 
 
 def _src_block(elem, ov, B):
@@ -59,6 +73,7 @@ def _src_block(elem, ov, B):
     return [dc, abs_ac, arg_ac] + tfp, flags, tfk
 
 
+_GUESS_CACHE = {}
 _SCALARS = (int, float, bool, str, type(None), complex)
 
 
@@ -308,7 +323,15 @@ def _flatten(circ, batch=None):
             if e.n1 == e.n2:
                 continue
             hint_rows.append((e.n1, e.n2, int(r['pbase']), 1.0, 0.0))
-    G, kept = _guess.build_guess_operator(circ, hint_rows)
+    # (topology only: cached per hint rows — a fresh batch of the same circuit re-uses it)
+    gkey = (circ.get_nodes_number(), tuple(hint_rows), tuple(bool(C.is_elem_voltage_defined(e)) for e in circ))
+    hit = _GUESS_CACHE.get(gkey)
+    if hit is None:
+        hit = _guess.build_guess_operator(circ, hint_rows)
+        if len(_GUESS_CACHE) > 64:
+            _GUESS_CACHE.clear()
+        _GUESS_CACHE[gkey] = hit
+    G, kept = hit
 
     out = Flat()
     out.n_nodes = circ.get_nodes_number()
@@ -328,8 +351,7 @@ def _flatten(circ, batch=None):
             nominal[s] = v
     out.nominal = nominal
     out.vary_slots = np.asarray(vary_slots, dtype=np.int32)
-    out.vary = (np.ascontiguousarray(np.stack(vary_rows))
-                if vary_rows else np.zeros((0, B or 0)))
+    out.vary_rows = vary_rows
     out.B = B
     out.vary_pinned = None      # pinned torch copy of `vary`, made by the engine on first upload
     if G is None:

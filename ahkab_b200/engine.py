@@ -106,11 +106,41 @@ class Engine(object):
         cached on the batch (compile.flatten) and keeps a PINNED copy of its value matrix,
         made here on first use: repeated runs on the same batch copy host->device straight
         from it, with no staging copy on the host."""
-        if flat.vary.size == 0:
+        rows = flat.vary_rows
+        if not len(rows):
             return self.set_vary(flat.vary)
         if getattr(flat, 'vary_pinned', None) is None:
+            flat.uploads += 1
+            if flat.uploads < 2:
+                # first upload of this batch: straight into the engine's rotating pinned staging,
+                # row by row (no stacked copy, no new pinned allocation — a Monte-Carlo loop that
+                # builds a fresh batch per call never gets past this branch)
+                return self._set_vary_rows(rows)
             flat.vary_pinned = torch.from_numpy(flat.vary).pin_memory()
         return self.set_vary(flat.vary_pinned)
+
+    def _set_vary_rows(self, rows):
+        shape = (len(rows), len(rows[0]))
+        st = getattr(self, '_stage', None)
+        if st is None or tuple(st[0][0].shape) != shape:
+            st = [[torch.empty(shape, dtype=torch.float64, pin_memory=True), None] for _ in range(2)]
+            self._stage, self._stage_i = st, 0
+        self._stage_i ^= 1
+        staged = st[self._stage_i]
+        if staged[1] is not None:
+            staged[1].synchronize()
+        host = staged[0].numpy()
+        for i, r in enumerate(rows):
+            host[i] = r
+        if self.vary is None or tuple(self.vary.shape) != shape:
+            self.vary = torch.empty(shape, dtype=torch.float64, device=self.device)
+        self.vary.copy_(staged[0], non_blocking=True)
+        with torch.cuda.device(self.device):
+            staged[1] = torch.cuda.Event()
+            staged[1].record(torch.cuda.current_stream(self.device))
+        self._vary_host = staged[0]
+        self.B = shape[1]
+        return self
 
     def set_options(self, **kw):
         self.opts.update(kw)

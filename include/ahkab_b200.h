@@ -269,6 +269,14 @@ int ahk_op(ahk_engine* e, const ahk_batch* batch, const double* x0,
            int use_guess, double* x, double* resid, int32_t* iters,
            int32_t* status, void* stream);
 
+/* Circuit size, all four analyses: n = nodes - 1 + voltage-defined elements up to 512 (the
+ * reference solves every size densely, ahkab/dc_analysis.py:796-822).  n <= 64: matrix in
+ * registers / shared memory.  65 <= n <= 512: the general large-n engine — one warp per
+ * instance, the dense matrix in a global workspace the library allocates (B x n x (n + 8)
+ * doubles, grow-only), non-zero bitmaps, dense panels on the FP64 tensor cores; interpreted
+ * kernels only (ahk_set_jit mode 1 is an error there).  Sources with a waveform enter OP / DC
+ * with their dc slot (VSource.V(time=None), ahkab/components/sources/VSource.py:92-97). */
+
 /* Operating point with HOST buffers (what a caller holding numpy arrays binds): the same
  * analysis as ahk_op, but parameters and results live in host memory (pinned memory for
  * the copies to be asynchronous).  The batch is cut into `nchunks` chunks that flow
@@ -289,7 +297,8 @@ int ahk_op_host(ahk_engine* e, int64_t B, int n_vary, const int32_t* vary_slots,
  * n > 64 take the sparse large-circuit path: both matrices are factored once per
  * instance, the points are solved independently — each is one exact Newton step —
  * and x0 / use_guess do not influence the result beyond rounding.)
- *   src_elem  index in circ->elems of the swept V or I source
+ *   src_elem  index in circ->elems of the swept V or I source (its dc value is swept; a
+ *             waveform on it is ignored, as in the reference)
  *   x_out   device [B][npts][n]; iters/status device [B][npts] */
 int ahk_dc_sweep(ahk_engine* e, const ahk_batch* batch, int src_elem,
                  const double* sweep_values, int npts, const double* x0,
