@@ -194,6 +194,16 @@ class Runner(object):
         array of the analysis), through ahkab_b200.analyses.run and the results objects."""
         import ahkab_b200 as ahkab
         W, n = self.W, self.name
+        saved = {k: getattr(ahkab.options, k) for k in self.w.opts}
+        for k, v in self.w.opts.items():      # the workload's option overrides, as module globals
+            setattr(ahkab.options, k, v)      # (the reference's way: ahkab.options.vea = ...)
+        try:
+            return self._api(ahkab, W, n, fresh)
+        finally:
+            for k, v in saved.items():
+                setattr(ahkab.options, k, v)
+
+    def _api(self, ahkab, W, n, fresh):
         if fresh or not hasattr(self, 'api_batch'):
             self.api_batch = self.w.batch(self.lo, self.hi)     # ParamBatch of host numpy arrays
         if n == 'c2':
