@@ -204,9 +204,14 @@ struct Ctx {
     int v = p->slot_vary[slot];
     return v < 0 ? p->nominal[slot] : vary[(long long)v * B + inst];
   }
-  AHK_MEM double* A() const { return Ag ? Ag : sm + L->A; }
   double* Vg = nullptr;  // Layout::vglob: base of this instance's Mv / Dv / Bv block in the global workspace
+#ifdef AHK_JIT           // specialised kernels exist for n <= 31 only: everything is in shared memory / registers
+  AHK_MEM double* A() const { return sm + L->A; }
+  AHK_MEM double* vb() const { return sm; }
+#else
+  AHK_MEM double* A() const { return Ag ? Ag : sm + L->A; }
   AHK_MEM double* vb() const { return Vg ? Vg : sm; }   // base the offsets Layout::Mv / Dv / Bv refer to
+#endif
   AHK_MEM double* x() const { return sm + L->x; }
   AHK_MEM unsigned char* prow() const { return (unsigned char*)(sm + L->bytes); }
   AHK_MEM unsigned char* stepof() const { return (unsigned char*)(sm + L->bytes) + 64; }
