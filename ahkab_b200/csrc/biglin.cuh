@@ -271,8 +271,8 @@ struct BigLin {
   int c3_state = 0;                       // 0 not tried for this epoch, 1 ready, -1 unavailable
   int last_path = -1;                     // ahk_big_stats: 0 dense workspace, 1 sparse dynamic, 2 static schedule, 3 compiled schedule
   int c3_nf = 0, c3_npos = 0;
-  double* c3_F = nullptr; double* c3_Mv = nullptr; int* c3_flagm = nullptr;
-  size_t c3_F_cap = 0, c3_Mv_cap = 0, c3_flag_cap = 0;
+  double* c3_F = nullptr; double* c3_Mv = nullptr; int* c3_flagm = nullptr; double* c3_scr = nullptr;
+  size_t c3_F_cap = 0, c3_Mv_cap = 0, c3_flag_cap = 0, c3_scr_cap = 0;
   void release_c3();
   ahk::Big3Sched* s3_S = nullptr;         // host copy of the schedule (source of the generated code), owned
   void release3();

@@ -153,9 +153,9 @@ void BigLin::release_c3() {
     if (k) { if (i == 0) jit::unload(*k); delete k; }
     c3_mod[i] = nullptr;
   }
-  cudaFree(c3_F); cudaFree(c3_Mv); cudaFree(c3_flagm);
-  c3_F = c3_Mv = nullptr; c3_flagm = nullptr;
-  c3_F_cap = c3_Mv_cap = c3_flag_cap = 0; c3_state = 0;
+  cudaFree(c3_F); cudaFree(c3_Mv); cudaFree(c3_flagm); cudaFree(c3_scr);
+  c3_F = c3_Mv = c3_scr = nullptr; c3_flagm = nullptr;
+  c3_F_cap = c3_Mv_cap = c3_flag_cap = c3_scr_cap = 0; c3_state = 0;
 }
 void BigLin::release3() {
   release_c3();
@@ -237,11 +237,27 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
       }
       if (c3_state == 1) {
         const long long B = batch->B;
-        const size_t needF = (size_t)2 * c3_nf * B, needM = (size_t)c3_npos * B;
-        if (needF > c3_F_cap || needM > c3_Mv_cap || (size_t)2 * B > c3_flag_cap || B + 1 > ovf_cap) {
+        // one launch for all sweep points unless the grid would be enormous: measured on C5
+        // (gpurun_out/r2i_ptc.txt) 1 / 2 / 3 / 5 / 10 points per launch = 6.9 / 3.6 / 3.0 / 1.7 /
+        // 1.15 ms — the solve is a serial chain per thread, more threads in flight hide it
+        int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 22) / std::max<long long>(1, B)));
+        if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
+        // Solve blocks: the straight-line code is ~640 KB per thread and every warp streams it once —
+        // with 64-thread blocks the warps of an SM drifted apart and instruction fetch was the
+        // first stall (ncu r3c: no_instruction 11 cycles per issued instruction).  One block per SM,
+        // its warps kept inside the same block of steps by a barrier, fetches the code once per SM.
+        long long sthr = ((B * ptc + e->sm_count - 1) / e->sm_count + 31) / 32 * 32;
+        sthr = std::max<long long>(32, std::min<long long>(320, sthr));
+        if (const char* f = getenv("AHK_BIGLIN3C_THREADS")) sthr = std::max(32, std::min(320, atoi(f) / 32 * 32));   // tuning
+        const long long sgrid_max = (B * ptc + sthr - 1) / sthr;
+        // scratch of the solve threads: right-hand side and iterate, [2 n][threads of a launch]
+        const size_t B32 = (size_t)(B + 31) / 32 * 32;   // (tiled by 32 lanes: biglin3_gen.hpp)
+        const size_t needF = (size_t)2 * c3_nf * B32, needM = (size_t)c3_npos * B32, needS = (size_t)2 * n * sgrid_max * sthr;
+        if (needF > c3_F_cap || needM > c3_Mv_cap || needS > c3_scr_cap || (size_t)2 * B > c3_flag_cap || B + 1 > ovf_cap) {
           CKB(cudaStreamSynchronize(s));
           if (needF > c3_F_cap) { cudaFree(c3_F); c3_F = nullptr; CKB(cudaMalloc(&c3_F, needF * 8)); c3_F_cap = needF; }
           if (needM > c3_Mv_cap) { cudaFree(c3_Mv); c3_Mv = nullptr; CKB(cudaMalloc(&c3_Mv, needM * 8)); c3_Mv_cap = needM; }
+          if (needS > c3_scr_cap) { cudaFree(c3_scr); c3_scr = nullptr; CKB(cudaMalloc(&c3_scr, needS * 8)); c3_scr_cap = needS; }
           if ((size_t)2 * B > c3_flag_cap) { cudaFree(c3_flagm); c3_flagm = nullptr; CKB(cudaMalloc(&c3_flagm, (size_t)2 * B * 4)); c3_flag_cap = 2 * B; }
           if (B + 1 > ovf_cap) {
             cudaFree(d_ovf); d_ovf = nullptr; ovf_cap = B + 1;
@@ -254,19 +270,15 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         ck.pt0 = 0; ck.ptc = npts;
         ck.x_out = x_out; ck.iters = iters; ck.status = status; ck.resid = resid;
         ck.F = c3_F; ck.Mv = c3_Mv; ck.flagm = c3_flagm; ck.ovf = d_ovf;
+        ck.scr = c3_scr; ck.scr_stride = sgrid_max * sthr;
         std::string lerr;
         const int T = 64;
         if (!jit::launch(*(jit::Kernel*)c3_mod[0], (int)((2 * B + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
         launches++; g_jit_launches++;
-        // one launch for all sweep points unless the grid would be enormous: measured on C5
-        // (gpurun_out/r2i_ptc.txt) 1 / 2 / 3 / 5 / 10 points per launch = 6.9 / 3.6 / 3.0 / 1.7 /
-        // 1.15 ms — the solve is a serial chain per thread, more threads in flight hide it
-        int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 22) / std::max<long long>(1, B)));
-        if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
         for (int pt0 = 0; pt0 < npts; pt0 += ptc) {
           ck.pt0 = pt0; ck.ptc = std::min(ptc, npts - pt0);
           const long long TT = B * ck.ptc;
-          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)((TT + T - 1) / T), T, 0, s, &ck, lerr)) { err = lerr; return -1; }
+          if (!jit::launch(*(jit::Kernel*)c3_mod[1], (int)((TT + sthr - 1) / sthr), (int)sthr, 0, s, &ck, lerr)) { err = lerr; return -1; }
           launches++; g_jit_launches++;
         }
         staged = true; last_path = 3;

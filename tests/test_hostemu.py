@@ -137,7 +137,8 @@ class _Big3CK(__import__('ctypes').Structure):
     import ctypes as _C
     _fields_ = [('vary', _C.c_void_p), ('B', _C.c_longlong), ('src_elem', _C.c_int), ('sweep', _C.c_void_p),
                 ('npts', _C.c_int), ('pt0', _C.c_int), ('ptc', _C.c_int), ('x_out', _C.c_void_p),
-                ('iters', _C.c_void_p), ('status', _C.c_void_p), ('resid', _C.c_void_p), ('F', _C.c_void_p),
+                ('iters', _C.c_void_p), ('status', _C.c_void_p), ('resid', _C.c_void_p), ('scr', _C.c_void_p), ('scr_stride', _C.c_longlong),
+                ('F', _C.c_void_p),
                 ('Mv', _C.c_void_p), ('flagm', _C.c_void_p), ('ovf', _C.c_void_p)]
 
 
@@ -170,11 +171,13 @@ def test_compiled_schedule_host_build_matches_interpreted(nodes):
     B, nn, P = e.B, e.n, len(sw)
     x = np.zeros((B, P, nn)); res = np.zeros((B, P, nn))
     it = np.zeros((B, P), np.int32); st = np.zeros((B, P), np.int32)
-    F = np.zeros((2, nf.value, B)); Mv = np.zeros((npos.value, B))
+    B32 = (B + 31) // 32 * 32
+    F = np.zeros(2 * nf.value * B32); Mv = np.zeros(npos.value * B32)   # tiled by 32 lanes
     fl = np.zeros((2, B), np.int32); ovf = np.zeros(B + 1, np.int32)
     vary = np.ascontiguousarray(e.vary)
+    scr = np.zeros(2 * nn * 32)
     k = _Big3CK(vary.ctypes.data, B, 0, sw.ctypes.data, P, 0, P, x.ctypes.data, it.ctypes.data,
-                st.ctypes.data, res.ctypes.data, F.ctypes.data, Mv.ctypes.data, fl.ctypes.data,
+                st.ctypes.data, res.ctypes.data, scr.ctypes.data, 1, F.ctypes.data, Mv.ctypes.data, fl.ctypes.data,
                 ovf.ctypes.data)
     so.b3_host_run(C.byref(k))
     ref = e.big3_sweep(0, sw)
