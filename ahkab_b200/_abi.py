@@ -66,7 +66,7 @@ EXPORTS = ('ahk_create', 'ahk_destroy', 'ahk_size', 'ahk_set_options',
            'ahk_set_variant', 'ahk_variant_count', 'ahk_variant_info',
            'ahk_h2d_columns', 'ahk_set_jit', 'ahk_jit_launch_count',
            'ahk_jit_build_count', 'ahk_jit_compile', 'ahk_op_host',
-           'ahk_set_jit_shape', 'ahk_set_jit_tuning', 'ahk_last_launch', 'ahk_pack_rows', 'ahk_big_stats')
+           'ahk_set_jit_shape', 'ahk_set_jit_tuning', 'ahk_set_jit_slu', 'ahk_jit_slu_stats', 'ahk_last_launch', 'ahk_pack_rows', 'ahk_big_stats')
 
 
 def _dp(a):
@@ -180,6 +180,10 @@ def load_library(path=None):
     lib.ahk_big_stats.restype = C.c_int
     lib.ahk_set_jit_tuning.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.ahk_set_jit_tuning.restype = C.c_int
+    lib.ahk_set_jit_slu.argtypes = [vp, C.c_int]
+    lib.ahk_set_jit_slu.restype = C.c_int
+    lib.ahk_jit_slu_stats.argtypes = [vp, C.POINTER(i32)]
+    lib.ahk_jit_slu_stats.restype = C.c_int
     lib.ahk_jit_launch_count.argtypes = []
     lib.ahk_jit_launch_count.restype = i64
     lib.ahk_jit_build_count.argtypes = []

@@ -196,6 +196,7 @@ struct Ctx {
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
   double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
   double* Ag = nullptr;  // large-n layout (Layout::big): this instance's n x RS matrix in the global workspace
+  int* pivrec = nullptr; // static-schedule kernels, calibration launch, written by instance 0: [0] solves that left the schedule, [1..n] the pivot positions of the last of them, [40] solves
 
   // persistent parameter (staged in shared memory; index = SrcOp/DevOp ppb/pmb + k)
   AHK_MEM double PP(int pslot) const { return sm[L->Pv + pslot]; }
@@ -612,8 +613,8 @@ AHK_DEV int gj_solve(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC 
 // the rows below only, then back-substitution (with the stored pivot reciprocals).  About a
 // third of the instructions of the Gauss-Jordan form below, which pays for keeping every
 // lane of a group busy — pointless when the group is one lane.  0 = a pivot is exactly zero.
-template <class V>
-AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
+template <class V, bool REC = false>
+AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1], int* rec = nullptr) {
   const int NC = V::NC, R = V::R;
   const int n = c.p->n;
   double* dx = c.sm + c.L->dx;
@@ -631,6 +632,7 @@ AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ?
         if (r < n && v > best) { best = v; p = r; }
       }
       if (best == 0.0) return 0;
+      if (REC) { if (rec) rec[k] = p; }
 #pragma unroll
       for (int j = k; j < NC; j++) {        // swap rows k and p (columns < k are not needed again)
         const double t = a[k][j];
@@ -663,6 +665,29 @@ AHK_DEV int lu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ?
   }
   return 1;
 }
+
+#ifdef AHK_JIT_SLU
+// ---- the same LU along a STATIC schedule (specialised kernels, one lane per instance or
+// replicated rows) -------------------------------------------------------------------------
+// The circuit fixes the sparsity pattern of mna + J, and in practice the operating region
+// fixes dgesv's pivot sequence too (C3: one sequence in 11 525 solves of 16 instances, C4: one in
+// 102 608).  jit_gen.hpp (slu_codegen) eliminates symbolically along the sequence the engine
+// learned in its calibration launch and emits the elimination as straight-line statements
+// on literal indices (AHK_JIT_SLU_BODY): no pivot search, no row swaps, only the structural
+// non-zeros are touched (C3: 43 multiply-adds + 9 reciprocals instead of a dense 9 x 10
+// elimination).  Every step VERIFIES that the scheduled pivot is the one dgesv would take
+// (largest magnitude among the rows not yet used, first one in LAPACK's swapped row order on
+// ties); skipped operations are on exact zeros, so while the pivots agree the result has the
+// bits of lu_solve_thread.  A solve whose pivots differ (`same` false, or a zero pivot) is
+// assembled again and goes through lu_solve_thread.
+template <class V>
+AHK_DEV int slu_solve_thread(Ctx& c, double (&a)[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1]) {
+  double* dx = c.sm + c.L->dx;
+  bool same = true;
+  AHK_JIT_SLU_BODY
+  return same ? 1 : 0;
+}
+#endif
 
 // ---- dense solve, generic fallback (Var<0,0,G>): matrix in shared memory ----------------
 // Gaussian elimination with implicit partial pivoting + back-substitution, run-time n.
@@ -1203,6 +1228,33 @@ AHK_DEV double assemble_row_switch(Ctx& c, int r, double (&row)[NC]) {
 }
 #endif
 
+#ifdef AHK_JIT_SLU
+// a solve that left the static schedule (or is singular): the matrix again, through the pivoting
+// elimination.  Not inlined: its dense register matrix must not weigh on the scheduled path.
+template <class V>
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+static
+#endif
+int slu_fallback(Ctx& c, int* rec) {
+  const int NC = V::NC, R = V::R, n = c.p->n;
+  double a[R > 0 ? R : 1][NC > 0 ? NC : 1];
+#pragma unroll
+  for (int s = 0; s < R; s++) {
+    if (s < n) {
+#pragma unroll
+      for (int j = 0; j < NC - 1; j++) a[s][j] = 0.0;
+      a[s][NC - 1] = assemble_row(c, s, a[s]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; j++) a[s][j] = 0.0;
+    }
+  }
+  return lu_solve_thread<V, true>(c, a, rec);
+}
+#endif
+
 // one Newton linear step: assemble at x() and solve into dx(); 0 = singular
 template <class V, bool FLAT = false>
 AHK_DEV int assemble_solve(Ctx& c) {
@@ -1253,7 +1305,23 @@ AHK_DEV int assemble_solve(Ctx& c) {
 #endif
     }
     if constexpr (V::G == 1 || REP) {
+#ifdef AHK_JIT_SLU
+      int okk = slu_solve_thread<V>(c, a);
+      // calibration launch (engine.cu): instance 0 counts its solves and the ones that left the schedule
+      const bool rec_on = c.pivrec != nullptr && c.inst == 0 && c.sub == 0;
+      if (rec_on) c.pivrec[40]++;
+      if (!okk) {
+        int rec[R > 0 ? R : 1];
+        okk = slu_fallback<V>(c, rec);
+        if (rec_on && okk) {                       // ... and leaves the sequence dgesv took
+          c.pivrec[0]++;
+#pragma unroll
+          for (int k = 0; k < R; k++) if (k < n) c.pivrec[1 + k] = rec[k];
+        }
+      }
+#else
       const int okk = lu_solve_thread<V>(c, a);   // (REP: every lane stores the same dx)
+#endif
       Grp<G>::sync(FLAT ? 0xffffffffu : c.mask);
       return okk;
     } else return gj_solve<V, FLAT>(c, a);

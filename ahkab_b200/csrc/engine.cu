@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,13 @@ struct ahk_engine {
   std::map<std::vector<long long>, Prepared> prepared;
   long long slots_epoch = 0, opts_epoch = 0;   // bumped when the varied slots / options change
   std::map<std::vector<long long>, jit::Kernel> jit_cache;
+  // static-schedule LU of the specialised one-lane / replicated kernels (core.cuh: slu_solve_thread):
+  // pivot sequences learned by calibration launches, per (mode, method, step control)
+  std::map<std::vector<long long>, std::vector<int> > slu_seq;
+  int* d_pivrec = nullptr;     // [64] calibration record (instance 0 of the calibration launch)
+  int slu_mode = -1;           // ahk_set_jit_slu: -1 = AHK_SLU / default (transients), 0 off, 1 transients, 2 OP / DC too
+  int slu_stats[4] = {0, 0, 0, 0};   // calibration launches, schedules replaced, last: solves off the schedule / solves
+  double slu_c1_hint = 0.0;    // DF coefficient of the transient being planned (nominal step), for slu_guess
   // host-buffer entry points (ahk_op_host): three internal streams + two chunk workspaces
   struct HostPipe {
     enum { NS = 8 };   // chunk slots: each has its own kernel stream, events and workspace
@@ -641,6 +649,17 @@ int jit_ilp_for(const ahk_engine* e, const VarInfo& v, int mode) {
   return std::max(1, std::min(std::min(ilp, 4), std::max(1, per_lane)));
 }
 
+// AHK_SLU = 0: pivoting LU everywhere; tran (default): static schedule in the transient kernels;
+// all: in the OP / DC kernels too (their homotopy stages tend to change the pivot sequence).
+bool slu_wanted(const ahk_engine* e, int mode) {
+  int m = e ? e->slu_mode : -1;
+  if (m < 0) {
+    static const char* env = getenv("AHK_SLU");
+    m = !env ? 1 : (env[0] == '0' ? 0 : (env[0] == 'a' ? 2 : 1));
+  }
+  return m == 2 || (m == 1 && mode == MODE_TRAN);
+}
+
 // The specialised kernel for (analysis, variant, launch shape, options, varied slots) —
 // compiled on first use, cached in the engine.  *out = nullptr: use the interpreted kernel.
 int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, const Layout& Ly,
@@ -651,13 +670,23 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
   if (e->jit_mode == 2 && B < e->jit_min_batch) return 0;
   const bool must = e->jit_mode == 1;
   const int ilp = jit_ilp_for(e, v, mode);
-  std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, ilp, e->slots_epoch, e->opts_epoch};
+  // static elimination schedule: one lane per instance or replicated rows (jit_gen.hpp: slu_codegen)
+  std::vector<int> seq;
+  if (slu_wanted(e, mode) && v.NC > 0 && mode != JIT_MODE_AC && (v.G == 1 || v.R >= e->n) && v.R >= e->n && e->n <= 31) {
+    auto f = e->slu_seq.find(std::vector<long long>{mode, method, usc});
+    seq = f != e->slu_seq.end() ? f->second : slu_guess(e->H, e->o.gmin, mode == MODE_TRAN ? e->slu_c1_hint : 0.0);
+    if (slu_codegen(e->H, seq).empty()) seq.clear();
+  }
+  std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, ilp};
+  for (int q : seq) key.push_back(q);
+  key.push_back(e->slots_epoch); key.push_back(e->opts_epoch);
   auto it = e->jit_cache.find(key);
   if (it == e->jit_cache.end()) {
     jit::Kernel k;
     // reg_blocks > 0: resident 128-thread blocks the registers are capped for; < 0: -min_blocks of this block size
     const int minb = reg_blocks < 0 ? -reg_blocks : std::max(1, std::min(32, reg_blocks * 128 / L.threads));
     JitCfg cfg = {v.NC, v.R, v.G, L.threads, minb, mode, method, usc, ilp};
+    cfg.slu = seq; k.slu = !seq.empty();
     std::string err;
     const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg, ac);
     bool cached = false;
@@ -695,7 +724,7 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
 int prepare_small(ahk_engine* e, long long B, int mode, int method, int usc, int* vid_out, Layout* Ly,
                   Launch* L, jit::Kernel** jk) {
   const std::vector<long long> key = {B, mode, method, usc, e->slots_epoch, e->opts_epoch, e->jit_mode,
-                                      e->jit_min_batch, e->force_vid, e->group, e->jit_R, e->jit_G, e->jit_ilp, e->jit_threads, e->jit_minb};
+                                      e->jit_min_batch, e->force_vid, e->group, e->jit_R, e->jit_G, e->jit_ilp, e->jit_threads, e->jit_minb, e->slu_mode};
   auto it = e->prepared.find(key);
   if (it != e->prepared.end()) {
     *vid_out = it->second.vid; *Ly = it->second.Ly; *L = it->second.L; *jk = it->second.jk;
@@ -754,6 +783,16 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
         int gdev = 1;                       // lanes that would each own a device
         while (gdev < 8 && gdev < nd) gdev *= 2;
         if (gdev > G && B * gdev / 32 <= 2368) G = gdev;
+        R = e->n;
+      } else if (slu_wanted(e, MODE_TRAN) && e->n <= 12) {
+        //  * static-schedule LU (core.cuh: slu_solve_thread): the solve is a few dozen multiply-adds
+        //    on literal indices, cheaper done redundantly by every lane than distributed — two
+        //    replicated lanes per instance split the vector work of the step (C3: 2.67 ms at
+        //    16 384 instances against 5.1 with one lane, 4.2 with four and 6.5 for the distributed
+        //    Gauss-Jordan; 2.2 ms from 2 K to 8 K instances, profiles/r3f_slu_c3.txt)
+        G = 2;
+        while (G < 8 && (nd + G - 1) / G > 3) G *= 2;
+        if (B * G / 32 > 2368) G = std::max(1, G / 2);
         R = e->n;
       } else {
         while (G < 32 && (e->n + G - 1) / G > 5) G *= 2;
@@ -856,6 +895,37 @@ int ensure_big_workspace(ahk_engine* e, long long B, const Layout& Ly, cudaStrea
   return 0;
 }
 
+// Calibration of a static-schedule kernel (first launch of a freshly built one): ONE block of
+// the real call runs with the record buffer on, instance 0 counts its solves and those whose
+// pivots left the schedule (they went through the pivoting LU: results are right either way).
+// If most of them did, the sequence it recorded becomes the schedule and the kernel is built
+// again — at most twice.  `launch1(jk, L, pivrec)` launches one block; `replan()` plans the
+// call again (new kernel).  Calibration launches are counted in slu_stats, not in the launch
+// counters of the call.  Returns 0, or -1 on a CUDA error.
+template <typename Launch1, typename Replan>
+int slu_calibrate(ahk_engine* e, int mode, int method, int usc, jit::Kernel*& jk, cudaStream_t s,
+                  Launch1 launch1, Replan replan) {
+  for (int round = 0; round < 2 && jk && jk->slu && !jk->calibrated; round++) {
+    if (!e->d_pivrec) CK(cudaMalloc(&e->d_pivrec, 64 * sizeof(int)));
+    CK(cudaMemsetAsync(e->d_pivrec, 0, 64 * sizeof(int), s));
+    if (launch1(jk, e->d_pivrec)) return -1;
+    int rec[64];
+    CK(cudaMemcpyAsync(rec, e->d_pivrec, sizeof rec, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    jk->calibrated = true;
+    e->slu_stats[0]++; e->slu_stats[2] = rec[0]; e->slu_stats[3] = rec[40];
+    if (getenv("AHK_DEBUG"))
+      fprintf(stderr, "[ahk] static-schedule calibration: %d of %d solves of instance 0 left the schedule\n", rec[0], rec[40]);
+    if (rec[0] * 2 > rec[40] && round == 0) {
+      e->slu_seq[std::vector<long long>{mode, method, usc}] = std::vector<int>(rec + 1, rec + 1 + e->n);
+      e->prepared.clear();
+      e->slu_stats[1]++;
+      if (replan()) return -1;
+    }
+  }
+  return 0;
+}
+
 int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const double* d_sweep, int npts,
                  const double* x0, int use_guess, double* x, double* resid, int32_t* iters,
                  int32_t* status, cudaStream_t s) {
@@ -864,8 +934,14 @@ int run_dc_small(ahk_engine* e, const ahk_batch* batch, int src_elem, const doub
   if (prepare_small(e, batch->B, MODE_OP, 0, 0, &vid, &Ly, &L, &jk)) return -1;
   note_launch(e, vid, L, jk != nullptr, 0);
   if (jk) {
-    KDcJ kj = {batch->vary, batch->B, DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status}};
+    KDcJ kj = {batch->vary, batch->B, DcArgs{src_elem, d_sweep, npts, x0, use_guess, x, resid, iters, status}, nullptr};
     std::string err;
+    if (jk->slu && !jk->calibrated) {
+      if (slu_calibrate(e, MODE_OP, 0, 0, jk, s,
+            [&](jit::Kernel* q, int* rec) { kj.pivrec = rec; const bool ok = jit::launch(*q, 1, L.threads, L.smem, s, &kj, err); kj.pivrec = nullptr; return ok ? 0 : fail(err); },
+            [&]() { return prepare_small(e, batch->B, MODE_OP, 0, 0, &vid, &Ly, &L, &jk); })) return -1;
+      if (!jk) return fail("static-schedule calibration lost the specialised kernel");
+    }
     return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
   }
   if (ensure_big_workspace(e, batch->B, Ly, s)) return -1;
@@ -932,6 +1008,7 @@ void ahk_destroy(ahk_engine* e) {
   if (!e) return;
   if (e->blob) cudaFree(e->blob);
   if (e->d_scratch) cudaFree(e->d_scratch);
+  if (e->d_pivrec) cudaFree(e->d_pivrec);
   if (e->bigA) cudaFree(e->bigA);
   for (auto& kv : e->jit_cache) jit::unload(kv.second);
   if (e->hp.ready) {
@@ -987,6 +1064,19 @@ int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks) {
   if (threads < 0 || threads > 1024 || threads % 32) return fail("ahk_set_jit_tuning: threads must be a multiple of 32");
   if (min_blocks < 0 || min_blocks > 32) return fail("ahk_set_jit_tuning: min_blocks must be 0..32");
   e->jit_ilp = ilp; e->jit_threads = threads; e->jit_minb = min_blocks;
+  return 0;
+}
+
+int ahk_set_jit_slu(ahk_engine* e, int mode) {
+  if (!e) return fail("null engine");
+  if (mode < -1 || mode > 2) return fail("ahk_set_jit_slu: mode must be -1..2");
+  e->slu_mode = mode;
+  return 0;
+}
+
+int ahk_jit_slu_stats(const ahk_engine* e, int32_t* out4) {
+  if (!e || !out4) return fail("null argument");
+  for (int i = 0; i < 4; i++) out4[i] = e->slu_stats[i];
   return 0;
 }
 
@@ -1058,6 +1148,11 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
       if (const char* f = getenv("AHK_JIT_ILP")) cfg.ilp = std::max(1, std::min(4, atoi(f)));        // tuning
       if (const char* f = getenv("AHK_JIT_THREADS")) cfg.threads = std::max(32, atoi(f));            // tuning
       if (const char* f = getenv("AHK_JIT_MINB")) cfg.min_blocks = std::max(1, atoi(f));             // tuning
+      // AHK_SLU_SEQ="5 6 2 ..." (tools/jit_sass.py): the static-schedule build along that pivot sequence
+      if (const char* f = getenv("AHK_SLU_SEQ")) {
+        std::istringstream is(f); int q;
+        while (is >> q) cfg.slu.push_back(q);
+      } else if (slu_wanted(nullptr, mode)) cfg.slu = slu_guess(H, o.gmin);
       spec = jit_spec_source(H, o, Ly, cfg);
     }
     std::string err;
@@ -1316,13 +1411,21 @@ int ahk_tran(ahk_engine* e, const ahk_batch* batch, const double* x0, double tst
   if (set_batch(e, batch, s)) return -1;
   int vid; Layout Ly; Launch L;
   jit::Kernel* jk = nullptr;
+  e->slu_c1_hint = tstep > 0 ? (method == AHK_TRAP ? 2.0 : 1.0) / tstep : 0.0;
   if (prepare_small(e, batch->B, MODE_TRAN, method, use_step_control ? 1 : 0, &vid, &Ly, &L, &jk)) return -1;
   note_launch(e, vid, L, jk != nullptr, 1);
   if (jk) {
     KTranJ kj = {batch->vary, batch->B, x0,
                  TranArgs{tstart, tstep, tstop, method, use_step_control, max_rows, t_out, x_out, rows, counters},
-                 status};
+                 status, nullptr};
     std::string err;
+    if (jk->slu && !jk->calibrated) {
+      const int usc = use_step_control ? 1 : 0;
+      if (slu_calibrate(e, MODE_TRAN, method, usc, jk, s,
+            [&](jit::Kernel* q, int* rec) { kj.pivrec = rec; const bool ok = jit::launch(*q, 1, L.threads, L.smem, s, &kj, err); kj.pivrec = nullptr; return ok ? 0 : fail(err); },
+            [&]() { return prepare_small(e, batch->B, MODE_TRAN, method, usc, &vid, &Ly, &L, &jk); })) return -1;
+      if (!jk) return fail("static-schedule calibration lost the specialised kernel");
+    }
     return jit_launched(jit::launch(*jk, L.blocks, L.threads, L.smem, s, &kj, err), err);
   }
   if (ensure_big_workspace(e, batch->B, Ly, s)) return -1;

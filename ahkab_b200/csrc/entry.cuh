@@ -66,8 +66,8 @@ AHK_DEV void run_tran(Ctx& c, const double* x0, const TranArgs& a, int* status, 
 
 // kernel parameters of the circuit-specialised kernels (jit_kernels.cuh; filled by
 // engine.cu): no program / options / layout — those are constants of the build
-struct KDcJ { const double* vary; long long B; DcArgs a; };
-struct KTranJ { const double* vary; long long B; const double* x0; TranArgs a; int* status; };
+struct KDcJ { const double* vary; long long B; DcArgs a; int* pivrec; };
+struct KTranJ { const double* vary; long long B; const double* x0; TranArgs a; int* status; int* pivrec; };
 
 #ifdef __CUDACC__
 // the group's context: its lanes, its instance, its shared-memory slice

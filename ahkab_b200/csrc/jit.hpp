@@ -235,6 +235,8 @@ struct Kernel {
   CUfunction fn = nullptr;
   bool failed = false;     // compilation / load failed once: do not retry on every call
   std::string why;
+  bool slu = false;        // built with a static elimination schedule (jit_gen.hpp: slu_codegen)
+  bool calibrated = false; // ... whose pivot sequence a calibration launch has checked (engine.cu)
 };
 
 inline std::string cu_err(CUresult r) {

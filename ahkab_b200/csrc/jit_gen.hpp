@@ -20,6 +20,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@ struct JitCfg {
   int mode;                // MODE_OP / MODE_TRAN / JIT_MODE_AC
   int method, use_step_control;   // transient only
   int ilp = 1;             // devices a lane evaluates interleaved (ekv_eval_v), 1 = one at a time
+  std::vector<int> slu;    // pivot sequence of the static-schedule LU (slu_codegen), empty = pivoting LU
 };
 enum { JIT_MODE_AC = 2 };
 // the complex arrays of the AC kernels' layout (ac.cuh: AcLayout) — offsets in doubles
@@ -66,6 +68,124 @@ void arr(std::ostringstream& s, const char* type, const char* name, const std::v
 
 }  // namespace jitgen
 
+// ---- static elimination schedule of the one-lane / replicated LU (core.cuh: slu_solve_thread) ----
+// seq[k] = the POSITION LAPACK's dgetf2 swaps into place k at step k (what lu_solve_thread's
+// pivot search returns); the rows are tracked through those swaps, the elimination is done
+// symbolically on the stamp pattern (every structural entry counts as non-zero), and the
+// statements come out on literal row / column indices.  Returns "" if the sequence is not a
+// valid pivot sequence for the pattern.
+inline std::string slu_codegen(const HostProg& H, const std::vector<int>& seq) {
+  const int n = H.hdr.n;
+  if ((int)seq.size() != n || n > 31) return "";
+  std::vector<unsigned> pat(n, 0u);
+  for (int r = 0; r < n; r++)
+    for (int q = H.row_ptr[r]; q < H.row_ptr[r + 1]; q++) pat[r] |= 1u << H.pcol[q];
+  std::vector<int> rowat(n), prow(n);
+  for (int i = 0; i < n; i++) rowat[i] = i;
+  std::vector<unsigned> ucols(n, 0u);
+  std::vector<std::string> st;
+  auto A = [](int r, int c) { return "a[" + std::to_string(r) + "][" + std::to_string(c) + "]"; };
+  for (int k = 0; k < n; k++) {
+    const int p = seq[k];
+    if (p < k || p >= n) return "";
+    const int pr = rowat[p];
+    if (!((pat[pr] >> k) & 1u)) return "";
+    // candidates: the other rows not yet used with a structural entry in column k; `<` for the
+    // ones LAPACK's search meets before the pivot row, `<=` after it (first maximum wins)
+    st.push_back("{ const double piv = " + A(pr, k) + ", ap = fabs(piv); if (!(ap > 0.0)) same = false;");
+    std::vector<int> cand;
+    for (int q = k; q < n; q++) {
+      const int r = rowat[q];
+      if (r == pr || !((pat[r] >> k) & 1u)) continue;
+      cand.push_back(r);
+      st.push_back(std::string("  if (!(fabs(") + A(r, k) + ") " + (q < p ? "<" : "<=") + " ap)) same = false;");
+    }
+    rowat[p] = rowat[k]; rowat[k] = pr; prow[k] = pr;
+    const unsigned uc = pat[pr] & ~((2u << k) - 1u);
+    ucols[k] = uc;
+    st.push_back("  const double iv" + std::to_string(k) + " = fm::rcp(piv);");
+    for (int r : cand) {
+      st.push_back("  { const double l = " + A(r, k) + " * iv" + std::to_string(k) + ";");
+      for (int j = k + 1; j < n; j++)
+        if ((uc >> j) & 1u) st.push_back("    " + A(r, j) + " -= l * " + A(pr, j) + ";");
+      st.push_back("    " + A(r, n) + " -= l * " + A(pr, n) + "; }");
+      pat[r] = (pat[r] | uc) & ~(1u << k);
+    }
+    st.push_back("  (void)iv" + std::to_string(k) + "; }");
+  }
+  // (the reciprocals are block-scoped above: keep them for the back-substitution)
+  std::vector<std::string> out;
+  for (int k = 0; k < n; k++) out.push_back("double sluinv" + std::to_string(k) + " = 0.0, slux" + std::to_string(k) + " = 0.0;");
+  for (auto& t : st) {
+    // "const double ivK = fm::rcp(piv);" -> also kept in sluinvK
+    out.push_back(t);
+    const size_t at = t.find("const double iv");
+    if (at != std::string::npos && t.find("fm::rcp") != std::string::npos) {
+      const std::string kk = t.substr(at + 15, t.find(' ', at + 15) - (at + 15));
+      out.push_back("  sluinv" + kk + " = iv" + kk + ";");
+    }
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    const int pr = prow[k];
+    out.push_back("{ double s = " + A(pr, n) + ";");
+    for (int j = k + 1; j < n; j++)
+      if ((ucols[k] >> j) & 1u) out.push_back("  s -= " + A(pr, j) + " * slux" + std::to_string(j) + ";");
+    out.push_back("  slux" + std::to_string(k) + " = s * sluinv" + std::to_string(k) + "; dx[" + std::to_string(k) + "] = slux" + std::to_string(k) + "; }");
+  }
+  std::string body;
+  for (auto& t : out) body += "  " + t + " \\\n";
+  return body;
+}
+
+// Nominal guess of the pivot sequence (before the calibration launch has seen the real one):
+// dgetf2's search on the linear stamps at their nominal values, with every Jacobian / dynamic
+// entry of the pattern at a small conductance and, for a transient, the dynamic elements at the
+// DF coefficient of the nominal step.  Only a starting point: a wrong guess costs one
+// more compilation, never a wrong result (slu_solve_thread verifies every pivot).
+inline std::vector<int> slu_guess(const HostProg& H, double gmin, double c1 = 0.0) {
+  const int n = H.hdr.n, np = H.hdr.npos;
+  std::vector<double> A((size_t)n * n, 0.0);
+  for (int q = 0; q < np; q++) {
+    double v = 0.0;
+    for (int t = H.term_ptr[q]; t < H.term_ptr[q + 1]; t++) {
+      const int kd = H.term_kind[t], ak = kd < 0 ? -kd : kd;
+      const double sg = kd < 0 ? -1.0 : 1.0, P = H.nominal[H.term_slot[t]];
+      if (ak == 1) v += sg * (1. / P); else if (ak == 2) v += sg * P; else v += sg;
+    }
+    if (H.pdiag[q]) v += gmin;
+    A[(size_t)H.prowi[q] * n + H.pcol[q]] = v;
+  }
+  // transient: + C1 D with the DF coefficient of the nominal step (core.cuh: build_values)
+  if (c1 != 0.0)
+    for (const LinOp& op : H.lin) {
+      auto add = [&](int i, double v) { if (op.pos[i] >= 0) A[(size_t)H.prowi[op.pos[i]] * n + H.pcol[op.pos[i]]] += c1 * v; };
+      if (op.kind == K_C) { const double v = H.nominal[op.pbase]; add(0, v); add(1, -v); add(2, v); add(3, -v); }
+      else if (op.kind == K_L) add(0, -H.nominal[op.pbase]);
+      else if (op.kind == K_K) { const double M = std::sqrt(H.nominal[op.aux0] * H.nominal[op.aux1]) * H.nominal[op.pbase]; add(0, -M); add(1, -M); }
+    }
+  for (int q = 0; q < np; q++) {   // an entry only the devices write: a small conductance
+    double& v = A[(size_t)H.prowi[q] * n + H.pcol[q]];
+    if (v == 0.0) v = 1e-4;
+  }
+  std::vector<int> seq(n, 0);
+  for (int k = 0; k < n; k++) {
+    int p = k; double mx = std::fabs(A[(size_t)k * n + k]);
+    for (int i = k + 1; i < n; i++) { const double v = std::fabs(A[(size_t)i * n + k]); if (v > mx) { mx = v; p = i; } }
+    seq[k] = p;
+    if (mx == 0.0) continue;
+    if (p != k) for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
+    for (int i = k + 1; i < n; i++) {
+      const double l = A[(size_t)i * n + k] / A[(size_t)k * n + k];
+      if (l == 0.0) continue;
+      for (int j = k + 1; j < n; j++) {
+        const double u = A[(size_t)k * n + j];
+        if (u != 0.0) { double& t = A[(size_t)i * n + j]; t -= l * u; if (t == 0.0) t = 1e-300; }   // fill stays structural
+      }
+    }
+  }
+  return seq;
+}
+
 // Text of jit_spec.h for one (circuit, varied slots, options, layout, variant).
 inline std::string jit_spec_source(const HostProg& H, const Opts& o, const Layout& L, const JitCfg& cfg,
                                    const JitAc* ac = nullptr) {
@@ -81,6 +201,10 @@ inline std::string jit_spec_source(const HostProg& H, const Opts& o, const Layou
     bool all_ekv = !H.dev.empty();
     for (const DevOp& q : H.dev) if (q.type != AHK_EKV || !q.active) all_ekv = false;
     s << "#define AHK_JIT_ILP " << (cfg.ilp > 1 ? cfg.ilp : 1) << "\n#define AHK_JIT_ALL_EKV " << (all_ekv ? 1 : 0) << "\n";
+  }
+  if (!cfg.slu.empty() && (cfg.G == 1 || (cfg.R >= h.n && cfg.mode != JIT_MODE_AC))) {
+    const std::string body = slu_codegen(H, cfg.slu);
+    if (!body.empty()) s << "#define AHK_JIT_SLU 1\n#define AHK_JIT_SLU_BODY \\\n" << body << "\n";
   }
   s << "#include \"program.h\"\n";
   s << "#ifdef __CUDACC__\n#define AHK_JD_CONST __constant__ const\n#define AHK_JFN __device__ __forceinline__\n"

@@ -26,6 +26,7 @@ extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_dc(const __grid_constant__ KDcJ k) {
   Ctx c; long long u;
   if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
+  c.pivrec = k.pivrec;
   run_dc<JitVar>(c, k.a);
 }
 #elif AHK_JIT_MODE == 2
@@ -48,6 +49,7 @@ extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_tran(const __grid_constant__ KTranJ k) {
   Ctx c; bool live;
   make_ctx_uniform<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, live);
+  c.pivrec = live ? k.pivrec : nullptr;
   run_tran<JitVar>(c, k.x0, k.a, k.status, live);
 }
 #endif

@@ -182,6 +182,20 @@ class Engine(object):
             raise EngineError(self._err())
         return self
 
+    def set_slu(self, mode=-1):
+        """ahk_set_jit_slu: static-schedule LU of the specialised kernels (-1 default: transients,
+        0 off, 1 transients, 2 OP / DC too)."""
+        if self.lib.ahk_set_jit_slu(self._h, int(mode)) != 0:
+            raise EngineError(self._err())
+        return self
+
+    def slu_stats(self):
+        """ahk_jit_slu_stats as a dict: calibrations, replaced, last_off, last_solves."""
+        out = (C.c_int32 * 4)()
+        if self.lib.ahk_jit_slu_stats(self._h, out) != 0:
+            raise EngineError(self._err())
+        return dict(zip(('calibrations', 'replaced', 'last_off', 'last_solves'), list(out)))
+
     def last_launch(self):
         """ahk_last_launch as a dict: vid, NC, R, G, threads, blocks, jit, analysis."""
         out = (C.c_int32 * 8)()

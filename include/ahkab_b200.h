@@ -209,6 +209,16 @@ int ahk_set_jit_shape(ahk_engine* e, int rows_per_lane, int lanes);
  * interleaved (1..4, 0 = heuristic); threads = block size (multiple of 32, 0 = heuristic);
  * min_blocks = resident blocks per SM the register allocation is capped for (0 = heuristic). */
 int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks);
+/* Static-schedule LU of the specialised kernels whose lanes hold every row (one lane per
+ * instance or replicated rows): numpy.linalg.solve's LU (dc_analysis.py:822) eliminated
+ * symbolically along the pivot sequence a calibration launch observed, emitted as straight-line
+ * code on the structural non-zeros; every pivot is verified against dgesv's rule at run time and
+ * a solve that leaves the sequence goes through the pivoting LU (same results either way).
+ * mode: -1 default (environment AHK_SLU, else transients), 0 off, 1 transients, 2 OP / DC too. */
+int ahk_set_jit_slu(ahk_engine* e, int mode);
+/* out4 = { calibration launches, schedules replaced by the observed sequence, solves of
+ * instance 0 that left the schedule in the last calibration, solves of instance 0 in it }. */
+int ahk_jit_slu_stats(const ahk_engine* e, int32_t* out4);
 /* Shape of the last small-circuit kernel launch of this engine (diagnostics, tests):
  * out8 = { variant id (>= 1000: free shape), matrix columns, rows per lane, lanes per
  * instance, threads per block, blocks, 1 if circuit-specialised, analysis 0 OP/DC 1 tran 2 AC }. */

@@ -12,6 +12,7 @@ import tempfile
 
 import numpy as np
 import pytest
+torch = pytest.importorskip("torch")
 
 import common  # noqa: F401  (sys.path set-up)
 from ahkab_b200 import _abi, workloads as W
@@ -120,6 +121,45 @@ def test_specialised_host_build_is_bit_identical_tran(ilp, always):
         emu.set_variant(0)
     lib = _build_host_jit(e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1, ilp=ilp),
                           'c4', ['-DAHK_EMU_ALWAYS'] if always else [])
+    B, n = e.B, e.n
+    t = np.full((B, rows_cap), np.nan); x = np.full((B, rows_cap, n), np.nan)
+    rows = np.zeros(B, np.int32); cnt = np.zeros((B, 4), np.int32); st = np.zeros(B, np.int32)
+    rc = lib.emuj_tran(C.c_int64(B), _dp(e.vary), _dp(x0), C.c_double(tr['tstart']),
+                       C.c_double(tr['tstep']), C.c_double(tr['tstop'] / 10), C.c_int64(rows_cap),
+                       _dp(t), _dp(x), _ip(rows), _ip(cnt), _ip(st))
+    assert rc == 0
+    assert (rows == ref['rows']).all() and (rows > 20).all()
+    assert (st == ref['status']).all() and (cnt == ref['counters']).all()
+    assert np.array_equal(t, ref['t'], equal_nan=True) and np.array_equal(x, ref['x'], equal_nan=True)
+
+
+@pytest.mark.parametrize('seq,what', [('0 1 4 3 4', 'the sequence dgesv takes'),
+                                      ('2 2 4 3 4', 'another valid sequence: every solve falls back'),
+                                      ('4 1 2 3 4', 'a sequence with a structurally zero pivot: no schedule')])
+def test_static_schedule_lu_host_build_is_bit_identical(seq, what, monkeypatch):
+    """core.cuh slu_solve_thread / jit_gen.hpp slu_codegen: the LU eliminated symbolically along a
+    pivot sequence, as straight-line code on the structural non-zeros, gives the bits of the
+    pivoting one-lane LU — while the pivots agree because the skipped operations are on exact
+    zeros, and otherwise because the solve is assembled again and goes through the pivoting LU."""
+    import emu
+    w = W.c4_ring3(B=2)
+    e = _emu(w)
+    tr = dict(W.C4_TRAN)
+    rows_cap = 4096
+    x0 = np.zeros((e.B, e.n))
+    emu.set_variant(2)                                    # Var<6,5,1>
+    try:
+        ref = e.tran(x0, tr['tstart'], tr['tstep'], tr['tstop'] / 10, 'GEAR2', True, rows_cap)
+    finally:
+        emu.set_variant(0)
+    plain = e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1)
+    monkeypatch.setenv('AHK_SLU_SEQ', seq)
+    spec = e.jit_source(1, method='GEAR2', use_step_control=True, NC=6, R=5, G=1)
+    assert ('AHK_JIT_SLU_BODY' in spec) == (seq != '4 1 2 3 4'), what
+    assert 'AHK_JIT_SLU_BODY' not in plain
+    if 'AHK_JIT_SLU_BODY' not in spec:
+        return
+    lib = _build_host_jit(spec, 'c4slu')
     B, n = e.B, e.n
     t = np.full((B, rows_cap), np.nan); x = np.full((B, rows_cap, n), np.nan)
     rows = np.zeros(B, np.int32); cnt = np.zeros((B, 4), np.int32); st = np.zeros(B, np.int32)
@@ -262,6 +302,44 @@ def test_gpu_specialised_ac(vid):
     xa, xb = _np(a['x']), _np(b['x'])
     assert (_np(b['status']) & 1).all() and (_np(a['status']) == _np(b['status'])).all()
     assert np.abs(xa - xb).max() <= 1e-10 * np.abs(xa).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['c3', 'c4'])
+def test_gpu_static_schedule_lu_matches_pivoting_lu(name):
+    """Specialised transient kernels with the static-schedule LU (calibrated on the first call)
+    against the same kernel shape with the pivoting LU: the scheduled elimination only skips
+    operations on exact zeros, so rows, counters and values agree; the calibration must end on a
+    schedule that instance 0 never leaves."""
+    if name == 'c3':
+        w = W.c3_colpitts(2048)
+        e = _engine(w)
+        e.set_jit('off')
+        x0 = torch.as_tensor(common.c3_x0(_np(e.op()['x']))).cuda()
+        run = lambda: e.tran(x0, max_rows=256, **W.C3_TRAN)
+    else:
+        w = W.c4_ring3(1024)
+        e = _engine(w)
+        x0 = torch.as_tensor(common.c4_x0(w.circuit(Circuit), w.B)).cuda()
+        tr = dict(W.C4_TRAN); tr['tstop'] = tr['tstop'] / 5
+        run = lambda: e.tran(x0, max_rows=1024, **tr)
+    e.set_jit('on')
+    e.set_jit_shape(9 if name == 'c3' else 5, 2)          # replicated rows, two lanes: the same shape for both
+    e.set_slu(0); a = run(); sa = e.last_launch()
+    e.set_slu(1); b = run(); sb = e.last_launch()
+    st = e.slu_stats()
+    assert sa['jit'] == 1 and sb['jit'] == 1 and (sa['R'], sa['G']) == (sb['R'], sb['G']), (sa, sb)
+    assert st['calibrations'] >= 1 and st['last_solves'] > 100 and st['last_off'] == 0, st
+    b2 = run()                                            # calibrated: no further calibration launch
+    assert e.slu_stats()['calibrations'] == st['calibrations']
+    for r in (b, b2):
+        assert (_np(a['rows']) == _np(r['rows'])).all() and (_np(a['status']) == _np(r['status'])).all()
+        assert (_np(a['counters']) == _np(r['counters'])).all()
+        rows = _np(a['rows'])
+        valid = np.arange(_np(a['t']).shape[1])[None, :] < rows[:, None]      # rows each instance wrote
+        assert np.array_equal(_np(a['t'])[valid], _np(r['t'])[valid])
+        xa, xr = _np(a['x'])[valid], _np(r['x'])[valid]
+        assert np.abs(xa - xr).max() <= 1e-9 * (1 + np.abs(xa).max())
 
 
 def test_generated_constants_do_not_depend_on_the_batch_values():
