@@ -51,7 +51,9 @@ struct AcLayout {
 
 // big: n beyond AHK_SMALL_NMAX — the complex matrix lives in the global workspace (Ctx::Ag,
 // n x RS complex elements), its right-hand side column in shared memory (L.brhs)
-inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0, bool big = false) {
+// nostage: the lane-per-chunk static-schedule kernel — rows are built from Bv / Dv on literal
+// indices (no staging rows), every lane of the group has its own x / dx (its own frequencies)
+inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0, bool big = false, bool nostage = false) {
   AcLayout A; std::memset(&A, 0, sizeof A);
   const Prog& h = H.hdr;
   const int n = h.n;
@@ -59,11 +61,11 @@ inline AcLayout make_ac_layout(const HostProg& H, int G, int NC = 0, bool big = 
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += cnt > 0 ? cnt : 0; return o; };
   auto take2 = [&](int cnt) { off += off & 1; return take(cnt); };   // 16-byte aligned
-  A.Ac = take2(big ? 0 : 2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
+  A.Ac = take2((big || nostage) ? 0 : 2 * n * A.RS);   // fallback: complex matrix; register variants: (Bv, Dv) staging rows
   A.L.big = big ? 1 : 0;
   A.L.brhs = take2(big ? 2 * n : 0);
   A.L.nzm = take(big ? (n * ((n + 31) / 32) * 4 + 7) / 8 : 0);
-  A.xc = take2(2 * n); A.dxc = take2(2 * n); A.Nac = take2(2 * n);
+  A.xc = take2(2 * n * (nostage ? G : 1)); A.dxc = take2(2 * n * (nostage ? G : 1)); A.Nac = take2(2 * n);
   A.pvc = take2(NC > 0 && G > 1 ? 4 * NC : 0);
   A.L.RS = A.RS;
   // (many matrix positions — dense patterns — do not fit next to the vectors: global workspace)
@@ -94,7 +96,7 @@ struct AcArgs {
 };
 
 // kernel parameters of the circuit-specialised AC kernel (jit_kernels.cuh; filled by engine.cu)
-struct KAcJ { const double* vary; long long B; AcArgs a; int nchunks; };
+struct KAcJ { const double* vary; long long B; AcArgs a; int nchunks; int* pivrec; };
 
 // generic fallback: complex LU + back-substitution on the shared-memory matrix
 template <int G>
@@ -377,6 +379,88 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
   return 1;
 }
 
+#ifdef AHK_JIT_SLU
+#ifdef __CUDACC__
+#define AHK_SLU_FENCE asm volatile("" ::: "memory");
+#else
+#define AHK_SLU_FENCE
+#endif
+// ---- one lane per (instance, frequency chunk): zgesv's LU along a static schedule ------------
+// The G lanes of a group share their instance's set-up (parameters, Bv, Dv, Nac in the group's
+// shared-memory slice) and then each walks its own chunk of the sweep with its own x / dx.
+// The complex form of core.cuh: slu_solve_thread — AHK_JIT_SLU_BODY is generated by
+// jit_gen.hpp (slu_codegen, cx) on the entries m[r][c]: elimination and back-substitution on
+// the structural non-zeros, literal indices, every pivot verified against zgetf2's rule
+// (first maximum of |re| + |im| among the rows not yet used).
+template <class V>
+AHK_DEV int zslu_solve_thread(const double* Bv, const double* Dv, const cd* Nac, const double om, const cd* x,
+                              cd* dx) {
+  // the rows are assembled inside the body (jit_gen.hpp: SluEmit::need_row), each right before the
+  // first pivot step that reads it; AHK_SLU_FENCE keeps the compiler from hoisting all of those
+  // loads to the top again (the matrix with its fill-in does not fit in 255 registers)
+  cd m[V::R > 0 ? V::R : 1][V::NC > 0 ? V::NC : 1];
+#pragma unroll
+  for (int s = 0; s < V::R; s++) {
+#pragma unroll
+    for (int j = 0; j < V::NC; j++) m[s][j] = cd{0.0, 0.0};
+  }
+  bool same = true;
+  AHK_JIT_SLU_BODY
+  return same ? 1 : 0;
+}
+
+// A solve that left the schedule (or is singular): zgetf2 / zgetrs as LAPACK runs them — pivot
+// search, row swaps — on a dense local matrix, with the arithmetic of the scheduled form
+// (reciprocal pivot, multiply).  Not inlined; rec receives the pivot positions.
+template <class V>
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+static
+#endif
+int zslu_fallback(Ctx& c, const AcLayout& AL, double om, const cd* x, cd* dx, int* rec) {
+  const int NC = V::NC, n = c.p->n;
+  const Prog& p = *c.p;
+  const double* Bv = c.vb() + AL.L.Bv;
+  const double* Dv = c.vb() + AL.L.Dv;
+  const cd* Nac = (const cd*)(c.sm + AL.Nac);
+  cd m[V::R > 0 ? V::R : 1][NC > 0 ? NC : 1];
+  cd inv[V::R > 0 ? V::R : 1];
+  for (int r = 0; r < n; r++) {
+    for (int j = 0; j < NC; j++) m[r][j] = cd{0.0, 0.0};
+    cd acc = Nac[r];
+    for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; k++) {
+      const cd v = {Bv[k], om * Dv[k]};
+      m[r][p.pcol[k]] = v;
+      acc = cadd(acc, cmul(v, x[p.pcol[k]]));
+    }
+    m[r][NC - 1] = cd{-acc.re, -acc.im};
+  }
+  for (int k = 0; k < n; k++) {
+    int pv = k; double best = fabs(m[k][k].re) + fabs(m[k][k].im);
+    for (int r = k + 1; r < n; r++) {
+      const double v = fabs(m[r][k].re) + fabs(m[r][k].im);
+      if (v > best) { best = v; pv = r; }
+    }
+    if (best == 0.0) return 0;
+    rec[k] = pv;
+    if (pv != k) for (int j = k; j < NC; j++) { const cd t = m[k][j]; m[k][j] = m[pv][j]; m[pv][j] = t; }
+    inv[k] = crecip(m[k][k]);
+    for (int r = k + 1; r < n; r++) {
+      if (m[r][k].re == 0.0 && m[r][k].im == 0.0) continue;   // (exact zero: nothing to eliminate)
+      const cd l = cmul(m[r][k], inv[k]);
+      for (int j = k + 1; j < NC; j++) m[r][j] = csub(m[r][j], cmul(l, m[k][j]));
+    }
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    cd s = m[k][NC - 1];
+    for (int j = k + 1; j < n; j++) s = csub(s, cmul(m[k][j], dx[j]));
+    dx[k] = cmul(s, inv[k]);
+  }
+  return 1;
+}
+#endif
+
 template <class V>
 AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
   const int G = V::G;
@@ -428,7 +512,12 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
   // register variants: dense staging rows of (Bv, Dv) pairs, filled once per instance;
   // every frequency then builds its complex row with NC loads and no scatter
   double* BD = c.sm + AL.Ac;
-  if constexpr (V::NC > 0) {
+#ifdef AHK_JIT_SLU
+  constexpr bool SLU1 = V::NC > 0;   // lane per chunk; rows built from Bv / Dv on literal indices: no staging
+#else
+  constexpr bool SLU1 = false;
+#endif
+  if constexpr (V::NC > 0 && !SLU1) {
     for (int i = c.sub; i < 2 * n * V::NC; i += G) BD[i] = 0.0;
     Grp<G>::sync(c.mask);
     for (int k = c.sub; k < p.npos; k += G) {
@@ -438,9 +527,32 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     Grp<G>::sync(c.mask);
   }
   int st = AHK_ST_OK;
-  for (int f = a.f0; f < a.f1; f++) {
+  int f0 = a.f0, f1 = a.f1;
+  if constexpr (SLU1) {       // this lane's chunk of the sweep, its own iterate
+    const int per = (a.npts + G - 1) / G;
+    f0 = c.sub * per; f1 = f0 + per < a.npts ? f0 + per : a.npts;
+    Grp<G>::sync(c.mask);
+    cd* xs = x;
+    x += c.sub * n; dx += c.sub * n;
+    if (c.sub) for (int i = 0; i < n; i++) x[i] = xs[i];
+  }
+  for (int f = f0; f < f1; f++) {
     const double om = a.omegas[f];
     int ok;
+#ifdef AHK_JIT_SLU
+    if constexpr (SLU1) {
+      const int R = V::R;
+      ok = zslu_solve_thread<V>(Bv, Dv, Nac, om, x, dx);
+      // calibration launch: every lane of instance 0 keeps its own record (engine.cu merges them)
+      int* prec = (c.pivrec != nullptr && c.inst == 0) ? c.pivrec + 256 * c.sub : nullptr;
+      if (prec) prec[1]++;
+      if (!ok) {
+        int rec[R > 0 ? R : 1];
+        ok = zslu_fallback<V>(c, AL, om, x, dx, rec);
+        if (prec && ok) slu_record(prec, rec, n);
+      }
+    } else
+#endif
     if constexpr (V::NC > 0) {
       const int NC = V::NC, R = V::R;
       cd m[R > 0 ? R : 1][NC > 0 ? NC : 1];
@@ -508,24 +620,25 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
       ok = zlu_solve_smem<G>(c, AL);
     }
     double* xo = a.x_out + ((c.inst * a.npts + f) * n) * 2;
+    const int i0 = SLU1 ? 0 : c.sub, di = SLU1 ? 1 : G;     // lane per chunk: the whole vector is this lane's
     if (!ok) {
       st = AHK_ST_SINGULAR;
       const double qn = nan("");
-      for (int g = f; g < a.f1; g++) {
+      for (int g = f; g < f1; g++) {
         double* xg = a.x_out + ((c.inst * a.npts + g) * n) * 2;
-        for (int i = c.sub; i < n; i += G) { xg[2 * i] = qn; xg[2 * i + 1] = qn; }
+        for (int i = i0; i < n; i += di) { xg[2 * i] = qn; xg[2 * i + 1] = qn; }
       }
       break;
     }
-    for (int i = c.sub; i < n; i += G) {
+    for (int i = i0; i < n; i += di) {
       cd v = cadd(x[i], dx[i]);
       x[i] = v;
       xo[2 * i] = v.re; xo[2 * i + 1] = v.im;
     }
-    Grp<G>::sync(c.mask);
+    if constexpr (!SLU1) Grp<G>::sync(c.mask);
   }
   // status[] is pre-filled with AHK_ST_OK by the caller; chunks only downgrade it
-  if (c.sub == 0 && a.status && st != AHK_ST_OK) a.status[c.inst] = st;
+  if ((SLU1 || c.sub == 0) && a.status && st != AHK_ST_OK) a.status[c.inst] = st;
 }
 
 }  // namespace ahk

@@ -196,7 +196,7 @@ struct Ctx {
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
   double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
   double* Ag = nullptr;  // large-n layout (Layout::big): this instance's n x RS matrix in the global workspace
-  int* pivrec = nullptr; // static-schedule kernels, calibration launch, written by instance 0: [0] solves that left the schedule, [1..n] the pivot positions of the last of them, [40] solves
+  int* pivrec = nullptr; // static-schedule kernels, calibration launch, written by instance 0 (layout: slu_record)
 
   // persistent parameter (staged in shared memory; index = SrcOp/DevOp ppb/pmb + k)
   AHK_MEM double PP(int pslot) const { return sm[L->Pv + pslot]; }
@@ -1228,6 +1228,23 @@ AHK_DEV double assemble_row_switch(Ctx& c, int r, double (&row)[NC]) {
 }
 #endif
 
+// Calibration record of the static-schedule kernels (engine.cu: slu_calibrate), written by ONE
+// thread (instance 0): rec[0] solves that left the schedule, rec[1] solves, rec[2] distinct
+// sequences seen among them (at most 4), rec[8 + i] how often, rec[16 + 32 i + k] sequence i.
+AHK_DEV void slu_record(int* rec, const int* seq, int n) {
+  rec[0]++;
+  const int ns = rec[2];
+  for (int i = 0; i < ns; i++) {
+    bool eq = true;
+    for (int k = 0; k < n; k++) if (rec[16 + 32 * i + k] != seq[k]) eq = false;
+    if (eq) { rec[8 + i]++; return; }
+  }
+  if (ns < 4) {
+    for (int k = 0; k < n; k++) rec[16 + 32 * ns + k] = seq[k];
+    rec[8 + ns] = 1; rec[2] = ns + 1;
+  }
+}
+
 #ifdef AHK_JIT_SLU
 // a solve that left the static schedule (or is singular): the matrix again, through the pivoting
 // elimination.  Not inlined: its dense register matrix must not weigh on the scheduled path.
@@ -1309,15 +1326,11 @@ AHK_DEV int assemble_solve(Ctx& c) {
       int okk = slu_solve_thread<V>(c, a);
       // calibration launch (engine.cu): instance 0 counts its solves and the ones that left the schedule
       const bool rec_on = c.pivrec != nullptr && c.inst == 0 && c.sub == 0;
-      if (rec_on) c.pivrec[40]++;
+      if (rec_on) c.pivrec[1]++;
       if (!okk) {
         int rec[R > 0 ? R : 1];
         okk = slu_fallback<V>(c, rec);
-        if (rec_on && okk) {                       // ... and leaves the sequence dgesv took
-          c.pivrec[0]++;
-#pragma unroll
-          for (int k = 0; k < R; k++) if (k < n) c.pivrec[1 + k] = rec[k];
-        }
+        if (rec_on && okk) slu_record(c.pivrec, rec, n);   // ... and leaves the sequence dgesv took
       }
 #else
       const int okk = lu_solve_thread<V>(c, a);   // (REP: every lane stores the same dx)

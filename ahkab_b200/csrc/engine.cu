@@ -133,8 +133,8 @@ struct ahk_engine {
   std::map<std::vector<long long>, jit::Kernel> jit_cache;
   // static-schedule LU of the specialised one-lane / replicated kernels (core.cuh: slu_solve_thread):
   // pivot sequences learned by calibration launches, per (mode, method, step control)
-  std::map<std::vector<long long>, std::vector<int> > slu_seq;
-  int* d_pivrec = nullptr;     // [64] calibration record (instance 0 of the calibration launch)
+  std::map<std::vector<long long>, std::vector<std::vector<int> > > slu_seq;
+  int* d_pivrec = nullptr;     // [32][256] calibration records (instance 0 of the calibration launch; core.cuh: slu_record)
   int slu_mode = -1;           // ahk_set_jit_slu: -1 = AHK_SLU / default (transients), 0 off, 1 transients, 2 OP / DC too
   int slu_stats[4] = {0, 0, 0, 0};   // calibration launches, schedules replaced, last: solves off the schedule / solves
   double slu_c1_hint = 0.0;    // DF coefficient of the transient being planned (nominal step), for slu_guess
@@ -651,13 +651,27 @@ int jit_ilp_for(const ahk_engine* e, const VarInfo& v, int mode) {
 
 // AHK_SLU = 0: pivoting LU everywhere; tran (default): static schedule in the transient kernels;
 // all: in the OP / DC kernels too (their homotopy stages tend to change the pivot sequence).
+std::vector<std::string> split_semicolon(const char* f) {
+  std::vector<std::string> out; std::string cur;
+  for (const char* q = f; *q; q++) { if (*q == ';') { out.push_back(cur); cur.clear(); } else cur += *q; }
+  out.push_back(cur);
+  return out;
+}
+
 bool slu_wanted(const ahk_engine* e, int mode) {
   int m = e ? e->slu_mode : -1;
   if (m < 0) {
     static const char* env = getenv("AHK_SLU");
     m = !env ? 1 : (env[0] == '0' ? 0 : (env[0] == 'a' ? 2 : 1));
   }
-  return m == 2 || (m == 1 && mode == MODE_TRAN);
+  return m == 2 || (m == 1 && (mode == MODE_TRAN || mode == JIT_MODE_AC));
+}
+
+// ... and the calibration has not given up on this (analysis, method, step control)
+bool slu_active(const ahk_engine* e, int mode, int method, int usc) {
+  if (!slu_wanted(e, mode)) return false;
+  auto f = e->slu_seq.find(std::vector<long long>{mode, method, usc});
+  return f == e->slu_seq.end() || !f->second.empty();
 }
 
 // The specialised kernel for (analysis, variant, launch shape, options, varied slots) —
@@ -671,14 +685,16 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
   const bool must = e->jit_mode == 1;
   const int ilp = jit_ilp_for(e, v, mode);
   // static elimination schedule: one lane per instance or replicated rows (jit_gen.hpp: slu_codegen)
-  std::vector<int> seq;
-  if (slu_wanted(e, mode) && v.NC > 0 && mode != JIT_MODE_AC && (v.G == 1 || v.R >= e->n) && v.R >= e->n && e->n <= 31) {
+  std::vector<std::vector<int> > seqs;
+  const bool all_rows = v.R >= e->n;
+  if (slu_active(e, mode, method, usc) && v.NC > 0 && all_rows && e->n <= 31) {
     auto f = e->slu_seq.find(std::vector<long long>{mode, method, usc});
-    seq = f != e->slu_seq.end() ? f->second : slu_guess(e->H, e->o.gmin, mode == MODE_TRAN ? e->slu_c1_hint : 0.0);
-    if (slu_codegen(e->H, seq).empty()) seq.clear();
+    if (f != e->slu_seq.end()) seqs = f->second;
+    else seqs.push_back(slu_guess(e->H, e->o.gmin, mode == MODE_TRAN ? e->slu_c1_hint : 0.0));
+    if (slu_codegen(e->H, seqs, mode == JIT_MODE_AC).empty()) seqs.clear();
   }
   std::vector<long long> key = {mode, vid, L.threads, reg_blocks, method, usc, ilp};
-  for (int q : seq) key.push_back(q);
+  for (auto& q : seqs) { key.push_back(-1); for (int t : q) key.push_back(t); }
   key.push_back(e->slots_epoch); key.push_back(e->opts_epoch);
   auto it = e->jit_cache.find(key);
   if (it == e->jit_cache.end()) {
@@ -686,7 +702,7 @@ int get_jit(ahk_engine* e, long long B, int mode, int vid, const VarInfo& v, con
     // reg_blocks > 0: resident 128-thread blocks the registers are capped for; < 0: -min_blocks of this block size
     const int minb = reg_blocks < 0 ? -reg_blocks : std::max(1, std::min(32, reg_blocks * 128 / L.threads));
     JitCfg cfg = {v.NC, v.R, v.G, L.threads, minb, mode, method, usc, ilp};
-    cfg.slu = seq; k.slu = !seq.empty();
+    cfg.slu = seqs; k.slu = !seqs.empty();
     std::string err;
     const std::string spec = jit_spec_source(e->H, e->o, Ly, cfg, ac);
     bool cached = false;
@@ -784,7 +800,7 @@ int prepare_small_uncached(ahk_engine* e, long long B, int mode, int method, int
         while (gdev < 8 && gdev < nd) gdev *= 2;
         if (gdev > G && B * gdev / 32 <= 2368) G = gdev;
         R = e->n;
-      } else if (slu_wanted(e, MODE_TRAN) && e->n <= 12) {
+      } else if (slu_active(e, MODE_TRAN, method, usc) && e->n <= 12) {
         //  * static-schedule LU (core.cuh: slu_solve_thread): the solve is a few dozen multiply-adds
         //    on literal indices, cheaper done redundantly by every lane than distributed — two
         //    replicated lanes per instance split the vector work of the step (C3: 2.67 ms at
@@ -905,23 +921,53 @@ int ensure_big_workspace(ahk_engine* e, long long B, const Layout& Ly, cudaStrea
 template <typename Launch1, typename Replan>
 int slu_calibrate(ahk_engine* e, int mode, int method, int usc, jit::Kernel*& jk, cudaStream_t s,
                   Launch1 launch1, Replan replan) {
-  for (int round = 0; round < 2 && jk && jk->slu && !jk->calibrated; round++) {
-    if (!e->d_pivrec) CK(cudaMalloc(&e->d_pivrec, 64 * sizeof(int)));
-    CK(cudaMemsetAsync(e->d_pivrec, 0, 64 * sizeof(int), s));
+  for (int round = 0; round < 3 && jk && jk->slu && !jk->calibrated; round++) {
+    if (!e->d_pivrec) CK(cudaMalloc(&e->d_pivrec, 32 * 256 * sizeof(int)));
+    CK(cudaMemsetAsync(e->d_pivrec, 0, 32 * 256 * sizeof(int), s));
     if (launch1(jk, e->d_pivrec)) return -1;
-    int rec[64];
-    CK(cudaMemcpyAsync(rec, e->d_pivrec, sizeof rec, cudaMemcpyDeviceToHost, s));
+    std::vector<int> all(32 * 256);
+    CK(cudaMemcpyAsync(all.data(), e->d_pivrec, all.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    jk->calibrated = true;
-    e->slu_stats[0]++; e->slu_stats[2] = rec[0]; e->slu_stats[3] = rec[40];
-    if (getenv("AHK_DEBUG"))
-      fprintf(stderr, "[ahk] static-schedule calibration: %d of %d solves of instance 0 left the schedule\n", rec[0], rec[40]);
-    if (rec[0] * 2 > rec[40] && round == 0) {
-      e->slu_seq[std::vector<long long>{mode, method, usc}] = std::vector<int>(rec + 1, rec + 1 + e->n);
-      e->prepared.clear();
-      e->slu_stats[1]++;
-      if (replan()) return -1;
+    // one record per lane of instance 0 (transients / OP: lane 0 only; AC: one per frequency chunk) -> merged
+    int rec[256] = {0};
+    for (int l = 0; l < 32; l++) {
+      const int* r = all.data() + 256 * l;
+      rec[0] += r[0]; rec[1] += r[1];
+      for (int i = 0; i < r[2] && i < 4; i++) {
+        int at = -1;
+        for (int j = 0; j < rec[2]; j++) if (std::equal(r + 16 + 32 * i, r + 16 + 32 * i + e->n, rec + 16 + 32 * j)) at = j;
+        if (at < 0 && rec[2] < 4) { at = rec[2]++; std::copy(r + 16 + 32 * i, r + 16 + 32 * i + e->n, rec + 16 + 32 * at); }
+        if (at >= 0) rec[8 + at] += r[8 + i];
+      }
     }
+    jk->calibrated = true;
+    const int off = rec[0], solves = rec[1];
+    e->slu_stats[0]++; e->slu_stats[2] = off; e->slu_stats[3] = solves;
+    if (getenv("AHK_DEBUG"))
+      fprintf(stderr, "[ahk] static-schedule calibration: %d of %d solves of instance 0 left the schedule (%d other sequences)\n", off, solves, rec[2]);
+    // more than 2 % off the schedule: the sequences they took (each >= 2 % of the solves) join
+    // it — or replace it, if nothing stayed on it — and the kernel is built again.  A circuit
+    // whose pivoting will not settle (a quarter of the solves still off after the last round, or
+    // nothing left to add) loses the schedule: its kernels are built with the pivoting LU.
+    if (off * 50 <= solves) break;
+    std::vector<std::vector<int> >& set = e->slu_seq[std::vector<long long>{mode, method, usc}];
+    bool added = false;
+    if (round < 2) {
+      if (off == solves) set.clear();
+      else if (set.empty()) set.push_back(slu_guess(e->H, e->o.gmin, mode == MODE_TRAN ? e->slu_c1_hint : 0.0));
+      for (int i = 0; i < rec[2] && i < 4; i++) {
+        if (rec[8 + i] * 50 <= solves || set.size() >= 4) continue;
+        set.push_back(std::vector<int>(rec + 16 + 32 * i, rec + 16 + 32 * i + e->n));
+        added = true;
+      }
+    }
+    if (!added) {
+      if (off * 4 <= solves) break;            // good enough: the rest goes through the fallback
+      set.clear();                             // (present but empty: get_jit builds without a schedule)
+    }
+    e->prepared.clear();
+    e->slu_stats[1]++;
+    if (replan()) return -1;
   }
   return 0;
 }
@@ -1119,7 +1165,7 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
                     int kind, int method, int use_step_control, int variant_id, int64_t* cubin_bytes) {
   // variant_id >= 1000 (OP / transient only): free shape, 1000 + rows_per_lane * 64 + lanes, compiled
   // with exactly n + 1 columns like the engine does for ahk_set_jit_shape
-  const bool free_shape = variant_id >= 1000 && kind != 2;
+  const bool free_shape = variant_id >= 1000;   // (AC: lane-per-chunk static-schedule kernel)
   if (!circ || !opts || kind < 0 || kind > 2 || variant_id < 2 ||
       (!free_shape && variant_id >= (kind == 2 ? AHK_N_AC_VARIANTS : AHK_N_REAL_VARIANTS)))
     return fail("ahk_jit_compile: bad argument");
@@ -1137,9 +1183,18 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
     Opts o; std::memcpy(&o, opts, sizeof(Opts));
     std::string spec;
     if (kind == 2) {
-      AcLayout AL = make_ac_layout(H, v.G, v.NC);
+      AcLayout AL = make_ac_layout(H, v.G, v.NC, false, free_shape);
       const JitAc ja = {AL.RS, AL.Ac, AL.xc, AL.dxc, AL.Nac, AL.pvc, AL.stride};
-      JitCfg cfg = {v.NC, v.R, v.G, 128, ac_min_blocks(v.NC), JIT_MODE_AC, 0, 0};
+      JitCfg cfg = {v.NC, v.R, v.G, free_shape ? 64 : 128, free_shape ? 1 : ac_min_blocks(v.NC), JIT_MODE_AC, 0, 0};
+      if (free_shape) {   // the static-schedule kernel (AHK_SLU_SEQ="8 9 9 ...;..." or the nominal guess)
+        if (const char* f = getenv("AHK_SLU_SEQ")) {
+          for (std::string part : split_semicolon(f)) {
+            std::istringstream is(part); int q; std::vector<int> sq;
+            while (is >> q) sq.push_back(q);
+            if (!sq.empty()) cfg.slu.push_back(sq);
+          }
+        } else cfg.slu.push_back(slu_guess(H, o.gmin));
+      }
       spec = jit_spec_source(H, o, AL.L, cfg, &ja);
     } else {
       const int mode = kind ? MODE_TRAN : MODE_OP;
@@ -1150,9 +1205,12 @@ int ahk_jit_compile(const ahk_circuit* circ, const ahk_options* opts, int n_vary
       if (const char* f = getenv("AHK_JIT_MINB")) cfg.min_blocks = std::max(1, atoi(f));             // tuning
       // AHK_SLU_SEQ="5 6 2 ..." (tools/jit_sass.py): the static-schedule build along that pivot sequence
       if (const char* f = getenv("AHK_SLU_SEQ")) {
-        std::istringstream is(f); int q;
-        while (is >> q) cfg.slu.push_back(q);
-      } else if (slu_wanted(nullptr, mode)) cfg.slu = slu_guess(H, o.gmin);
+        for (std::string part : split_semicolon(f)) {
+          std::istringstream is(part); int q; std::vector<int> sq;
+          while (is >> q) sq.push_back(q);
+          if (!sq.empty()) cfg.slu.push_back(sq);
+        }
+      } else if (slu_wanted(nullptr, mode)) cfg.slu.push_back(slu_guess(H, o.gmin));
       spec = jit_spec_source(H, o, Ly, cfg);
     }
     std::string err;
@@ -1473,6 +1531,58 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     CK(cudaGetLastError());
     g_launches++;
   }
+  // One lane per (instance, frequency chunk) with zgesv's LU along a static schedule
+  // (ac.cuh: zslu_solve_thread): the solve of a sparse circuit is a few hundred flop, and 16 lanes
+  // sharing a dense complex Gauss-Jordan spend theirs on zeros (C1: 0.84 ms -> see DESIGN.md).
+  if (wants_jit(e, batch->B) && !big && e->n <= 31 && e->force_ac_vid < 0 && slu_active(e, JIT_MODE_AC, 0, 0)) {
+    // lanes per instance = frequency chunks: every lane is a serial chain, so as many as keep
+    // >= 3 frequencies per lane (the group shares its instance's set-up; C1, 100 frequencies:
+    // 4 / 8 / 16 / 32 lanes = 0.57 / 0.45 / 0.38 / 0.34 ms, gpurun_out/r3i_c1.txt)
+    int Gc = 1;
+    while (Gc < 32 && npts / (Gc * 2) >= 3) Gc *= 2;
+    if (const char* f = getenv("AHK_AC_CHUNKS")) { Gc = 1; while (Gc * 2 <= atoi(f) && Gc < 32) Gc *= 2; }   // tuning
+    const VarInfo vs = {e->n + 1, e->n, Gc};
+    const int vids = 1000 + e->n * 64 + Gc;
+    const AcLayout ALs = make_ac_layout(e->H, Gc, vs.NC, false, true);
+    int thr = 64;
+    if (const char* f = getenv("AHK_AC_THREADS")) thr = std::max(32, std::min(256, atoi(f) / 32 * 32));   // tuning
+    Launch Ls;
+    Ls.vid = vids; Ls.G = Gc; Ls.threads = std::max(thr, Gc);
+    Ls.smem = (size_t)(Ls.threads / Gc) * ALs.stride * sizeof(double);
+    while (Ls.smem > e->smem_max && Ls.threads > 32 && Ls.threads / 2 >= Gc) { Ls.threads /= 2; Ls.smem = (size_t)(Ls.threads / Gc) * ALs.stride * sizeof(double); }
+    if (Ls.smem <= e->smem_max) {
+      const int ipb = Ls.threads / Gc;
+      Ls.blocks = (int)((batch->B + ipb - 1) / ipb);
+      const JitAc ja = {ALs.RS, ALs.Ac, ALs.xc, ALs.dxc, ALs.Nac, ALs.pvc, ALs.stride};
+      jit::Kernel* jk = nullptr;
+      int acminb = 1;
+      if (const char* f = getenv("AHK_AC_MINB")) acminb = std::max(1, std::min(16, atoi(f)));   // tuning
+      auto get = [&]() { return get_jit(e, batch->B, JIT_MODE_AC, vids, vs, ALs.L, Ls, -acminb, 0, 0, &jk, &ja); };
+      if (get()) return -1;
+      if (jk && jk->slu) {
+        KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, Gc, nullptr};
+        std::string err;
+        if (!jk->calibrated) {
+          if (slu_calibrate(e, JIT_MODE_AC, 0, 0, jk, s,
+                [&](jit::Kernel* q, int* rec) {
+                  kj.pivrec = rec;
+                  const bool ok = jit::launch(*q, 1, Ls.threads, Ls.smem, s, &kj, err);
+                  kj.pivrec = nullptr;
+                  return ok ? 0 : fail(err);
+                },
+                [&]() { return get(); })) return -1;
+          // (the calibration block may have flagged a singular instance: status is rewritten)
+          long long nb = (batch->B + 255) / 256;
+          k_fill_i32<<<(int)nb, 256, 0, s>>>(status, batch->B, AHK_ST_OK);
+          CK(cudaGetLastError());
+        }
+        if (jk && jk->slu) {
+          note_launch(e, vids, Ls, true, 2, true);
+          return jit_launched(jit::launch(*jk, Ls.blocks, Ls.threads, Ls.smem, s, &kj, err), err);
+        }
+      }
+    }
+  }
   if (wants_jit(e, batch->B) && v.NC > 0) {   // the kernel compiled for this circuit (jit_gen.hpp)
     VarInfo vj = v;
     vj.NC = e->n + 1;                         // exactly n + 1 columns, no padding
@@ -1484,7 +1594,7 @@ int ahk_ac(ahk_engine* e, const ahk_batch* batch, const double* x_op, const doub
     if (get_jit(e, batch->B, JIT_MODE_AC, vid, vj, ALj.L, Lj, ac_min_blocks(v.NC), 0, 0, &jk, &ja)) return -1;
     if (jk) {
       note_launch(e, vid, Lj, true, 2, true);
-      KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, nchunks};
+      KAcJ kj = {batch->vary, batch->B, AcArgs{x_op, e->d_scratch, npts, 0, npts, x_out, status}, nchunks, nullptr};
       std::string err;
       return jit_launched(jit::launch(*jk, Lj.blocks, Lj.threads, Lj.smem, s, &kj, err), err);
     }

@@ -35,7 +35,7 @@ struct JitCfg {
   int mode;                // MODE_OP / MODE_TRAN / JIT_MODE_AC
   int method, use_step_control;   // transient only
   int ilp = 1;             // devices a lane evaluates interleaved (ekv_eval_v), 1 = one at a time
-  std::vector<int> slu;    // pivot sequence of the static-schedule LU (slu_codegen), empty = pivoting LU
+  std::vector<std::vector<int> > slu;   // pivot sequences of the static-schedule LU (slu_codegen), empty = pivoting LU
 };
 enum { JIT_MODE_AC = 2 };
 // the complex arrays of the AC kernels' layout (ac.cuh: AcLayout) — offsets in doubles
@@ -68,73 +68,161 @@ void arr(std::ostringstream& s, const char* type, const char* name, const std::v
 
 }  // namespace jitgen
 
-// ---- static elimination schedule of the one-lane / replicated LU (core.cuh: slu_solve_thread) ----
-// seq[k] = the POSITION LAPACK's dgetf2 swaps into place k at step k (what lu_solve_thread's
-// pivot search returns); the rows are tracked through those swaps, the elimination is done
-// symbolically on the stamp pattern (every structural entry counts as non-zero), and the
-// statements come out on literal row / column indices.  Returns "" if the sequence is not a
-// valid pivot sequence for the pattern.
-inline std::string slu_codegen(const HostProg& H, const std::vector<int>& seq) {
+// ---- static elimination schedule of the one-lane / replicated LU (core.cuh: slu_solve_thread,
+// ac.cuh: the complex form) ---------------------------------------------------------------------
+// seq[k] = the POSITION LAPACK's dgetf2 / zgetf2 swaps into place k at step k (what the pivot
+// search of lu_solve_thread / zlu_solve_thread returns); the rows are tracked through those
+// swaps, the elimination is done symbolically on the stamp pattern (every structural entry
+// counts as non-zero), and the statements come out on literal row / column indices.
+// SEVERAL sequences form a trie: a common prefix is emitted once, and where they part the code
+// finds out which of the known continuations dgesv's rule takes for THIS matrix
+// (`if (p is the choice) {...} else if (q is the choice) {...} else same = false`) — C1's AC solves
+// take one sequence for 84 % of the (instance, frequency) pairs and another, different in the
+// last two steps only, for 16 %.  cx: complex entries `m[r][c]` (ac.cuh: cd, magnitude
+// |re| + |im| as izamax), else real `a[r][c]`.  Returns "" if no sequence is valid for the pattern.
+struct SluEmit {
+  const int n; const bool cx;
+  const HostProg* lazyH = nullptr;   // complex form: rows are ASSEMBLED inside the body, right before
+                                     // the first step that reads them (short live ranges: the whole
+                                     // 14 x 15 complex matrix of C1 does not fit in registers)
+  std::vector<std::string> out;
+  int ids = 0;
+  SluEmit(int n_, bool cx_) : n(n_), cx(cx_) {}
+  void need_row(unsigned& done, int r, int ind) {
+    if (!lazyH || ((done >> r) & 1u)) return;
+    done |= 1u << r;
+    const HostProg& H = *lazyH;
+    line(ind, "AHK_SLU_FENCE { cd acc = Nac[" + std::to_string(r) + "];");
+    for (int q = H.row_ptr[r]; q < H.row_ptr[r + 1]; q++) {
+      const int c = H.pcol[q];
+      line(ind + 1, "{ const cd v = cd{Bv[" + std::to_string(q) + "], om * Dv[" + std::to_string(q) + "]}; " + A(r, c) +
+                    " = v; acc = cadd(acc, cmul(v, x[" + std::to_string(c) + "])); }");
+    }
+    line(ind + 1, A(r, n) + " = cd{-acc.re, -acc.im}; }");
+  }
+  std::string A(int r, int c) const { return std::string(cx ? "m[" : "a[") + std::to_string(r) + "][" + std::to_string(c) + "]"; }
+  std::string mag(const std::string& e) const { return cx ? "(fabs(" + e + ".re) + fabs(" + e + ".im))" : "fabs(" + e + ")"; }
+  void line(int ind, const std::string& t) { out.push_back(std::string((size_t)ind * 2, ' ') + t); }
+
+  struct State {
+    std::vector<unsigned> pat; std::vector<int> rowat, prow; std::vector<unsigned> ucols; std::vector<std::string> inv;
+    unsigned done = 0;     // rows assembled so far (lazy form)
+  };
+  static bool valid(const std::vector<unsigned>& pat0, const std::vector<int>& seq, int n) {
+    if ((int)seq.size() != n) return false;
+    std::vector<unsigned> pat = pat0; std::vector<int> rowat(n);
+    for (int i = 0; i < n; i++) rowat[i] = i;
+    for (int k = 0; k < n; k++) {
+      const int p = seq[k];
+      if (p < k || p >= n) return false;
+      const int pr = rowat[p];
+      if (!((pat[pr] >> k) & 1u)) return false;
+      const unsigned uc = pat[pr] & ~((2u << k) - 1u);
+      for (int q = k; q < n; q++) {
+        const int r = rowat[q];
+        if (r != pr && ((pat[r] >> k) & 1u)) pat[r] = (pat[r] | uc) & ~(1u << k);
+      }
+      rowat[p] = rowat[k]; rowat[k] = pr;
+    }
+    return true;
+  }
+  // elimination of step k with the pivot at position p (state advanced in place)
+  void eliminate(State& S, int k, int p, const std::string& ivname, int ind) {
+    const int pr = S.rowat[p];
+    std::vector<int> cand;
+    for (int q = k; q < n; q++) { const int r = S.rowat[q]; if (r != pr && ((S.pat[r] >> k) & 1u)) cand.push_back(r); }
+    S.rowat[p] = S.rowat[k]; S.rowat[k] = pr; S.prow[k] = pr;
+    const unsigned uc = S.pat[pr] & ~((2u << k) - 1u);
+    S.ucols[k] = uc; S.inv[k] = ivname;
+    for (int r : cand) {
+      line(ind, std::string("{ const ") + (cx ? "cd l = cmul(" + A(r, k) + ", " + ivname + ");" : "double l = " + A(r, k) + " * " + ivname + ";"));
+      for (int j = k + 1; j <= n; j++)
+        if (j == n || ((uc >> j) & 1u))
+          line(ind + 1, cx ? A(r, j) + " = csub(" + A(r, j) + ", cmul(l, " + A(pr, j) + "));" : A(r, j) + " -= l * " + A(pr, j) + ";");
+      line(ind, "}");
+      S.pat[r] = (S.pat[r] | uc) & ~(1u << k);
+    }
+  }
+  void back(const State& S, int ind) {
+    for (int k = n - 1; k >= 0; k--) {
+      const int pr = S.prow[k];
+      const std::string xk = "slux" + std::to_string(k);
+      line(ind, std::string("{ ") + (cx ? "cd" : "double") + " s = " + A(pr, n) + ";");
+      for (int j = k + 1; j < n; j++)
+        if ((S.ucols[k] >> j) & 1u)
+          line(ind + 1, cx ? "s = csub(s, cmul(" + A(pr, j) + ", slux" + std::to_string(j) + "));" : "s -= " + A(pr, j) + " * slux" + std::to_string(j) + ";");
+      line(ind + 1, cx ? xk + " = cmul(s, " + S.inv[k] + "); dx[" + std::to_string(k) + "] = " + xk + "; }"
+                       : xk + " = s * " + S.inv[k] + "; dx[" + std::to_string(k) + "] = " + xk + "; }");
+    }
+  }
+  void gen(State S, int k, std::vector<const std::vector<int>*> seqs, int ind) {
+    if (k == n) { back(S, ind); return; }
+    std::vector<int> kids;                       // distinct positions the sequences take at step k
+    for (auto* q : seqs) if (std::find(kids.begin(), kids.end(), (*q)[k]) == kids.end()) kids.push_back((*q)[k]);
+    std::sort(kids.begin(), kids.end());
+    // magnitudes of the structural candidates of column k, in LAPACK's search order
+    std::vector<int> cq;
+    for (int q = k; q < n; q++) if ((S.pat[S.rowat[q]] >> k) & 1u) cq.push_back(q);
+    for (int q : cq) need_row(S.done, S.rowat[q], ind);
+    const int id = ids++;
+    auto mg = [&](int q) { return "mg" + std::to_string(id) + "_" + std::to_string(q); };
+    for (int q : cq) line(ind, "const double " + mg(q) + " = " + mag(A(S.rowat[q], k)) + ";");
+    auto cond = [&](int p) {                     // position p holds the first maximum, and it is non-zero
+      std::string c = "(" + mg(p) + " > 0.0)";
+      for (int q : cq) if (q != p) c += " && (" + mg(q) + (q < p ? " < " : " <= ") + mg(p) + ")";
+      return c;
+    };
+    const std::string iv = "iv" + std::to_string(id);
+    auto rcp = [&](int p) { return cx ? "crecip(" + A(S.rowat[p], k) + ")" : "fm::rcp(" + A(S.rowat[p], k) + ")"; };
+    if (kids.size() == 1) {                      // one continuation: verified, not branched on
+      const int p = kids[0];
+      line(ind, "if (!(" + cond(p) + ")) same = false;");
+      line(ind, std::string("const ") + (cx ? "cd " : "double ") + iv + " = " + rcp(p) + ";");
+      eliminate(S, k, p, iv, ind);
+      gen(S, k + 1, seqs, ind);
+      return;
+    }
+    for (size_t i = 0; i < kids.size(); i++) {
+      const int p = kids[i];
+      line(ind, std::string(i ? "} else if (" : "if (") + cond(p) + ") {");
+      State T = S;
+      line(ind + 1, std::string("const ") + (cx ? "cd " : "double ") + iv + " = " + rcp(p) + ";");
+      eliminate(T, k, p, iv, ind + 1);
+      std::vector<const std::vector<int>*> sub;
+      for (auto* q : seqs) if ((*q)[k] == p) sub.push_back(q);
+      gen(T, k + 1, sub, ind + 1);
+    }
+    line(ind, "} else same = false;");
+  }
+};
+
+inline std::string slu_codegen(const HostProg& H, const std::vector<std::vector<int> >& seqs_in, bool cx = false) {
   const int n = H.hdr.n;
-  if ((int)seq.size() != n || n > 31) return "";
+  if (n > 31 || seqs_in.empty()) return "";
   std::vector<unsigned> pat(n, 0u);
   for (int r = 0; r < n; r++)
     for (int q = H.row_ptr[r]; q < H.row_ptr[r + 1]; q++) pat[r] |= 1u << H.pcol[q];
-  std::vector<int> rowat(n), prow(n);
-  for (int i = 0; i < n; i++) rowat[i] = i;
-  std::vector<unsigned> ucols(n, 0u);
-  std::vector<std::string> st;
-  auto A = [](int r, int c) { return "a[" + std::to_string(r) + "][" + std::to_string(c) + "]"; };
-  for (int k = 0; k < n; k++) {
-    const int p = seq[k];
-    if (p < k || p >= n) return "";
-    const int pr = rowat[p];
-    if (!((pat[pr] >> k) & 1u)) return "";
-    // candidates: the other rows not yet used with a structural entry in column k; `<` for the
-    // ones LAPACK's search meets before the pivot row, `<=` after it (first maximum wins)
-    st.push_back("{ const double piv = " + A(pr, k) + ", ap = fabs(piv); if (!(ap > 0.0)) same = false;");
-    std::vector<int> cand;
-    for (int q = k; q < n; q++) {
-      const int r = rowat[q];
-      if (r == pr || !((pat[r] >> k) & 1u)) continue;
-      cand.push_back(r);
-      st.push_back(std::string("  if (!(fabs(") + A(r, k) + ") " + (q < p ? "<" : "<=") + " ap)) same = false;");
-    }
-    rowat[p] = rowat[k]; rowat[k] = pr; prow[k] = pr;
-    const unsigned uc = pat[pr] & ~((2u << k) - 1u);
-    ucols[k] = uc;
-    st.push_back("  const double iv" + std::to_string(k) + " = fm::rcp(piv);");
-    for (int r : cand) {
-      st.push_back("  { const double l = " + A(r, k) + " * iv" + std::to_string(k) + ";");
-      for (int j = k + 1; j < n; j++)
-        if ((uc >> j) & 1u) st.push_back("    " + A(r, j) + " -= l * " + A(pr, j) + ";");
-      st.push_back("    " + A(r, n) + " -= l * " + A(pr, n) + "; }");
-      pat[r] = (pat[r] | uc) & ~(1u << k);
-    }
-    st.push_back("  (void)iv" + std::to_string(k) + "; }");
+  std::vector<const std::vector<int>*> seqs;
+  for (auto& q : seqs_in) {
+    if (!SluEmit::valid(pat, q, n)) continue;
+    bool dup = false;
+    for (auto* o : seqs) if (*o == q) dup = true;
+    if (!dup) seqs.push_back(&q);
   }
-  // (the reciprocals are block-scoped above: keep them for the back-substitution)
-  std::vector<std::string> out;
-  for (int k = 0; k < n; k++) out.push_back("double sluinv" + std::to_string(k) + " = 0.0, slux" + std::to_string(k) + " = 0.0;");
-  for (auto& t : st) {
-    // "const double ivK = fm::rcp(piv);" -> also kept in sluinvK
-    out.push_back(t);
-    const size_t at = t.find("const double iv");
-    if (at != std::string::npos && t.find("fm::rcp") != std::string::npos) {
-      const std::string kk = t.substr(at + 15, t.find(' ', at + 15) - (at + 15));
-      out.push_back("  sluinv" + kk + " = iv" + kk + ";");
-    }
-  }
-  for (int k = n - 1; k >= 0; k--) {
-    const int pr = prow[k];
-    out.push_back("{ double s = " + A(pr, n) + ";");
-    for (int j = k + 1; j < n; j++)
-      if ((ucols[k] >> j) & 1u) out.push_back("  s -= " + A(pr, j) + " * slux" + std::to_string(j) + ";");
-    out.push_back("  slux" + std::to_string(k) + " = s * sluinv" + std::to_string(k) + "; dx[" + std::to_string(k) + "] = slux" + std::to_string(k) + "; }");
-  }
+  if (seqs.empty()) return "";
+  SluEmit E(n, cx);
+  if (cx) E.lazyH = &H;
+  for (int k = 0; k < n; k++) E.line(0, std::string(cx ? "cd" : "double") + " slux" + std::to_string(k) + (cx ? " = cd{0.0, 0.0};" : " = 0.0;"));
+  SluEmit::State S;
+  S.pat = pat; S.rowat.resize(n); S.prow.assign(n, 0); S.ucols.assign(n, 0u); S.inv.assign(n, "");
+  for (int i = 0; i < n; i++) S.rowat[i] = i;
+  E.gen(S, 0, seqs, 0);
   std::string body;
-  for (auto& t : out) body += "  " + t + " \\\n";
+  for (auto& t : E.out) body += "  " + t + " \\\n";
   return body;
+}
+inline std::string slu_codegen(const HostProg& H, const std::vector<int>& seq, bool cx = false) {
+  return slu_codegen(H, std::vector<std::vector<int> >{seq}, cx);
 }
 
 // Nominal guess of the pivot sequence (before the calibration launch has seen the real one):
@@ -202,8 +290,8 @@ inline std::string jit_spec_source(const HostProg& H, const Opts& o, const Layou
     for (const DevOp& q : H.dev) if (q.type != AHK_EKV || !q.active) all_ekv = false;
     s << "#define AHK_JIT_ILP " << (cfg.ilp > 1 ? cfg.ilp : 1) << "\n#define AHK_JIT_ALL_EKV " << (all_ekv ? 1 : 0) << "\n";
   }
-  if (!cfg.slu.empty() && (cfg.G == 1 || (cfg.R >= h.n && cfg.mode != JIT_MODE_AC))) {
-    const std::string body = slu_codegen(H, cfg.slu);
+  if (!cfg.slu.empty() && cfg.R >= h.n) {   // every lane holds all rows (AC: lane per frequency chunk)
+    const std::string body = slu_codegen(H, cfg.slu, cfg.mode == JIT_MODE_AC);
     if (!body.empty()) s << "#define AHK_JIT_SLU 1\n#define AHK_JIT_SLU_BODY \\\n" << body << "\n";
   }
   s << "#include \"program.h\"\n";

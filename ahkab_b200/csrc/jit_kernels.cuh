@@ -34,6 +34,12 @@ __device__ const AcLayout jit_aclayout{};
 extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_ac(const __grid_constant__ KAcJ k) {   // unit = (instance, frequency chunk), as k_ac.cu
   Ctx c; long long u;
+#ifdef AHK_JIT_SLU
+  // static-schedule kernel: unit = instance, the G lanes of its group are its frequency chunks
+  if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_aclayout.L, AcLayout::stride, k.vary, k.B, k.B, u)) return;
+  c.pivrec = k.pivrec;
+  run_ac<JitVar>(c, jit_aclayout, k.a);
+#else
   if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_aclayout.L, AcLayout::stride, k.vary, k.B,
                            k.B * k.nchunks, u)) return;
   c.inst = u / k.nchunks;
@@ -43,6 +49,7 @@ ahk_jit_ac(const __grid_constant__ KAcJ k) {   // unit = (instance, frequency ch
   a.f0 = ch * per;
   a.f1 = min(a.npts, a.f0 + per);
   run_ac<JitVar>(c, jit_aclayout, a);
+#endif
 }
 #else
 extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)

@@ -624,10 +624,10 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
     e2e_api = None
     if world == 1:
         # the same step through the drop-in API (host numpy in, host numpy out), host wall clock
-        # (two untimed calls at least: the caller holds the previous result while the next call
+        # (three untimed calls: the caller holds the previous result while the next call
         # runs, so the engine's pool of pinned result buffers settles at two — pinning the
         # 1.4 GB of a C4 result set costs ~0.3 s once)
-        for _ in range(3 if name not in ('c3', 'c4') else 2):
+        for _ in range(3):
             out_api = r.api()
         torch.cuda.synchronize()
         asteps = steps if name not in ('c3', 'c4') else min(steps, 3)

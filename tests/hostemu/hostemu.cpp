@@ -187,9 +187,17 @@ int emu_jit_source(const ahk_circuit* c, const ahk_options* o, int n_vary, const
     Opts q; copy_opts(o, q);
     Layout L = make_layout(H, mode, method, usc, G, NC, R, true);
     JitCfg cfg = {NC, R, G, threads, min_blocks, mode, method, usc, ilp > 1 ? ilp : 1};
-    if (const char* f = getenv("AHK_SLU_SEQ")) {   // static-schedule LU along this pivot sequence (tests)
-      std::istringstream is(f); int v;
-      while (is >> v) cfg.slu.push_back(v);
+    if (const char* f = getenv("AHK_SLU_SEQ")) {   // static-schedule LU along these pivot sequences, ';' between them (tests)
+      std::string cur;
+      for (const char* z = f;; z++) {
+        if (*z == ';' || *z == 0) {
+          std::istringstream is(cur); int v; std::vector<int> sq;
+          while (is >> v) sq.push_back(v);
+          if (!sq.empty()) cfg.slu.push_back(sq);
+          cur.clear();
+          if (*z == 0) break;
+        } else cur += *z;
+      }
     }
     std::string t = jit_spec_source(H, q, L, cfg);
     if (buf && cap > 0) {

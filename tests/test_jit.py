@@ -135,6 +135,7 @@ def test_specialised_host_build_is_bit_identical_tran(ilp, always):
 
 @pytest.mark.parametrize('seq,what', [('0 1 4 3 4', 'the sequence dgesv takes'),
                                       ('2 2 4 3 4', 'another valid sequence: every solve falls back'),
+                                      ('2 2 4 3 4;0 1 4 3 4;0 2 4 3 4', 'a trie of three sequences: the code branches on the pivot'),
                                       ('4 1 2 3 4', 'a sequence with a structurally zero pivot: no schedule')])
 def test_static_schedule_lu_host_build_is_bit_identical(seq, what, monkeypatch):
     """core.cuh slu_solve_thread / jit_gen.hpp slu_codegen: the LU eliminated symbolically along a
@@ -340,6 +341,25 @@ def test_gpu_static_schedule_lu_matches_pivoting_lu(name):
         assert np.array_equal(_np(a['t'])[valid], _np(r['t'])[valid])
         xa, xr = _np(a['x'])[valid], _np(r['x'])[valid]
         assert np.abs(xa - xr).max() <= 1e-9 * (1 + np.abs(xa).max())
+
+
+@pytest.mark.gpu
+def test_gpu_static_schedule_lu_instances_that_pivot_differently_fall_back():
+    """C2's column 0 holds 1 / R1 next to the voltage source's 1: which one dgesv takes flips with
+    the instance's R1, so a schedule learned from instance 0 fits only part of the batch (and
+    the homotopy stages of the OP change it too).  With the static-schedule LU forced onto the
+    OP kernel (mode 2), every solve that leaves it goes through the pivoting LU: same results
+    as the kernel without a schedule, bit for bit (the scheduled form only skips exact zeros)."""
+    w = W.c2_diode_op(8192)
+    e = _engine(w)
+    e.set_jit('on')
+    e.set_variant(real=2)                                 # Var<4,3,1>: one lane per instance
+    e.set_slu(0); a = e.op()
+    e.set_slu(2); b = e.op()
+    assert e.slu_stats()['calibrations'] >= 1
+    assert e.last_launch()['jit'] == 1
+    assert (_np(a['status']) == _np(b['status'])).all() and (_np(a['iters']) == _np(b['iters'])).all()
+    assert np.array_equal(_np(a['x']), _np(b['x']))
 
 
 def test_generated_constants_do_not_depend_on_the_batch_values():
