@@ -196,7 +196,7 @@ struct Ctx {
   double C1;             // DF coefficient of x_{n+1} (0 outside transients)
   double gadd;           // Gmin added on the fly to node diagonals (OP/DC layouts: Bv is Mv)
   double* Ag = nullptr;  // large-n layout (Layout::big): this instance's n x RS matrix in the global workspace
-  int* pivrec = nullptr; // static-schedule kernels, calibration launch, written by instance 0 (layout: slu_record)
+  int* pivrec = nullptr; // static-schedule kernels, calibration launch: 32 records, one per instance / lane (layout: slu_record)
 
   // persistent parameter (staged in shared memory; index = SrcOp/DevOp ppb/pmb + k)
   AHK_MEM double PP(int pslot) const { return sm[L->Pv + pslot]; }
@@ -1324,13 +1324,14 @@ AHK_DEV int assemble_solve(Ctx& c) {
     if constexpr (V::G == 1 || REP) {
 #ifdef AHK_JIT_SLU
       int okk = slu_solve_thread<V>(c, a);
-      // calibration launch (engine.cu): instance 0 counts its solves and the ones that left the schedule
-      const bool rec_on = c.pivrec != nullptr && c.inst == 0 && c.sub == 0;
-      if (rec_on) c.pivrec[1]++;
+      // calibration launch (engine.cu): the first 32 instances each count their solves and the
+      // ones that left the schedule, in their own record (pivots may depend on the instance)
+      int* prec = (c.pivrec != nullptr && c.inst < 32 && c.sub == 0) ? c.pivrec + 256 * (int)c.inst : nullptr;
+      if (prec) prec[1]++;
       if (!okk) {
         int rec[R > 0 ? R : 1];
         okk = slu_fallback<V>(c, rec);
-        if (rec_on && okk) slu_record(c.pivrec, rec, n);   // ... and leaves the sequence dgesv took
+        if (prec && okk) slu_record(prec, rec, n);   // ... and leave the sequence dgesv took
       }
 #else
       const int okk = lu_solve_thread<V>(c, a);   // (REP: every lane stores the same dx)

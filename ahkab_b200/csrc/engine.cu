@@ -134,7 +134,7 @@ struct ahk_engine {
   // static-schedule LU of the specialised one-lane / replicated kernels (core.cuh: slu_solve_thread):
   // pivot sequences learned by calibration launches, per (mode, method, step control)
   std::map<std::vector<long long>, std::vector<std::vector<int> > > slu_seq;
-  int* d_pivrec = nullptr;     // [32][256] calibration records (instance 0 of the calibration launch; core.cuh: slu_record)
+  int* d_pivrec = nullptr;     // [32][256] calibration records (core.cuh: slu_record)
   int slu_mode = -1;           // ahk_set_jit_slu: -1 = AHK_SLU / default (transients), 0 off, 1 transients, 2 OP / DC too
   int slu_stats[4] = {0, 0, 0, 0};   // calibration launches, schedules replaced, last: solves off the schedule / solves
   double slu_c1_hint = 0.0;    // DF coefficient of the transient being planned (nominal step), for slu_guess
@@ -912,7 +912,7 @@ int ensure_big_workspace(ahk_engine* e, long long B, const Layout& Ly, cudaStrea
 }
 
 // Calibration of a static-schedule kernel (first launch of a freshly built one): ONE block of
-// the real call runs with the record buffer on, instance 0 counts its solves and those whose
+// the real call runs with the record buffer on, its first 32 instances count their solves and those whose
 // pivots left the schedule (they went through the pivoting LU: results are right either way).
 // If most of them did, the sequence it recorded becomes the schedule and the kernel is built
 // again — at most twice.  `launch1(jk, L, pivrec)` launches one block; `replan()` plans the
@@ -928,7 +928,7 @@ int slu_calibrate(ahk_engine* e, int mode, int method, int usc, jit::Kernel*& jk
     std::vector<int> all(32 * 256);
     CK(cudaMemcpyAsync(all.data(), e->d_pivrec, all.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    // one record per lane of instance 0 (transients / OP: lane 0 only; AC: one per frequency chunk) -> merged
+    // 32 records (transients / OP: the first 32 instances; AC: the frequency chunks of instance 0) -> merged
     int rec[256] = {0};
     for (int l = 0; l < 32; l++) {
       const int* r = all.data() + 256 * l;
@@ -944,7 +944,7 @@ int slu_calibrate(ahk_engine* e, int mode, int method, int usc, jit::Kernel*& jk
     const int off = rec[0], solves = rec[1];
     e->slu_stats[0]++; e->slu_stats[2] = off; e->slu_stats[3] = solves;
     if (getenv("AHK_DEBUG"))
-      fprintf(stderr, "[ahk] static-schedule calibration: %d of %d solves of instance 0 left the schedule (%d other sequences)\n", off, solves, rec[2]);
+      fprintf(stderr, "[ahk] static-schedule calibration: %d of %d solves of the calibration sample left the schedule (%d other sequences)\n", off, solves, rec[2]);
     // more than 2 % off the schedule: the sequences they took (each >= 2 % of the solves) join
     // it — or replace it, if nothing stayed on it — and the kernel is built again.  A circuit
     // whose pivoting will not settle (a quarter of the solves still off after the last round, or

@@ -56,7 +56,7 @@ extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_tran(const __grid_constant__ KTranJ k) {
   Ctx c; bool live;
   make_ctx_uniform<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, live);
-  c.pivrec = live ? k.pivrec : nullptr;
+  c.pivrec = live ? k.pivrec : nullptr;   // (padding groups repeat the last instance: they must not record)
   run_tran<JitVar>(c, k.x0, k.a, k.status, live);
 }
 #endif

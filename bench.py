@@ -678,6 +678,12 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
             "unit": "TFLOP/s", "frac": flop / step_s / 1e12 / fp64_peak if fp64_peak else None,
             "peak_source": "measured in this run: DFMA probe kernel (ahk_probe_fp64), best of 5",
             "algorithmic_flop_per_step": flop,
+            "flop_basis": ("SURVEY 8(d): measured iterations / steps / points x [dense LU(n) + residual "
+                           "mat-vec + device evaluations] of the reference's algorithm"
+                           + ("; the static-schedule kernels of this workload (core.cuh: slu_solve_thread, "
+                              "ac.cuh: zslu_solve_thread) execute the LU on the structural non-zeros only, "
+                              "i.e. fewer flop than counted here — executed FP64 instruction counts are in "
+                              "the ncu summaries under profiles/" if name in ('c1', 'c3', 'c4') else "")),
             "scope": "rank 0's kernels on its shard" if world > 1 else "the whole batch",
             "traffic": (measured_traffic(name) or {}).get("bytes"),
             "traffic_source": measured_traffic(name),

@@ -217,7 +217,8 @@ int ahk_set_jit_tuning(ahk_engine* e, int ilp, int threads, int min_blocks);
  * mode: -1 default (environment AHK_SLU, else transients), 0 off, 1 transients, 2 OP / DC too. */
 int ahk_set_jit_slu(ahk_engine* e, int mode);
 /* out4 = { calibration launches, schedules replaced by the observed sequence, solves of
- * instance 0 that left the schedule in the last calibration, solves of instance 0 in it }. */
+ * the calibration sample (first 32 instances; AC: the chunks of instance 0) that left the schedule
+ * in the last calibration, solves of the sample in it }. */
 int ahk_jit_slu_stats(const ahk_engine* e, int32_t* out4);
 /* Shape of the last small-circuit kernel launch of this engine (diagnostics, tests):
  * out8 = { variant id (>= 1000: free shape), matrix columns, rows per lane, lanes per
