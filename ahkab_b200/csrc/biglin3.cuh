@@ -217,6 +217,10 @@ AHK_DEV int big3_factor_one(const Big3K& k, long long inst) {
         const int* up = k.upd + st.upd0 + i * st.nu;
         for (int j = 0; j < st.nu; j++) V[(IT)up[j] * (IT)B] -= l * V[(IT)k.u_slot[st.u0 + j] * (IT)B];
       }
+      // the pivot's slot keeps its RECIPROCAL: the substitutions multiply (one division per
+      // pivot per instance instead of one per pivot per sweep point and pass; the slot of a used
+      // row's pivot is never read by a later elimination step)
+      V[(IT)st.piv * (IT)B] = inv;
     }
   }
   return BIG3_OK;
@@ -286,7 +290,7 @@ AHK_DEV void big3_solve_one(const Big3K& k, long long tid, double* b, IT bT) {
       double s = 0.0;
       for (int j = 0; j < st.nu; j++)
         s += V[(IT)k.u_slot[st.u0 + j] * (IT)B] * b[(IT)pr[k.u_col[st.u0 + j]] * bT];
-      b[(IT)pr[kk] * bT] = (b[(IT)pr[kk] * bT] - s) / V[(IT)st.piv * (IT)B];
+      b[(IT)pr[kk] * bT] = (b[(IT)pr[kk] * bT] - s) * V[(IT)st.piv * (IT)B];   // (stored reciprocal)
     }
     // x <- x + dx; gmin_check on pass 2 (results.py:493-523)
     for (int c = 0; c < n; c++) {

@@ -250,12 +250,11 @@ int BigLin::run(ahk_engine* e, const ahk_batch* batch, int src_elem, const doubl
         // 1.15 ms — the solve is a serial chain per thread, more threads in flight hide it
         int ptc = (int)std::max<long long>(1, std::min<long long>(npts, (1ll << 22) / std::max<long long>(1, B)));
         if (const char* f = getenv("AHK_BIGLIN3C_PTC")) ptc = std::max(1, std::min(npts, atoi(f)));   // tuning
-        // Solve blocks: the straight-line code is ~640 KB per thread and every warp streams it once —
-        // with 64-thread blocks the warps of an SM drifted apart and instruction fetch was the
-        // first stall (ncu r3c: no_instruction 11 cycles per issued instruction).  One block per SM,
-        // its warps kept inside the same block of steps by a barrier, fetches the code once per SM.
-        long long sthr = ((B * ptc + e->sm_count - 1) / e->sm_count + 31) / 32 * 32;
-        sthr = std::max<long long>(32, std::min<long long>(320, sthr));
+        // Solve blocks: the straight-line code is ~300 KB per thread and every warp streams it once
+        // (instruction fetch is the first stall, ncu r3c / r3p: no_instruction 10 cycles per issued
+        // instruction); a barrier per block of steps keeps the warps of a block in the same code
+        // window.  One big block per SM was tried and is not better than small blocks.
+        long long sthr = 64;   // (measured on C5: 64 / 128 / 288 threads = 0.542 / 0.557 / 0.569 ms, gpurun_out/r3u_c5.txt)
         if (const char* f = getenv("AHK_BIGLIN3C_THREADS")) sthr = std::max(32, std::min(320, atoi(f) / 32 * 32));   // tuning
         const long long sgrid_max = (B * ptc + sthr - 1) / sthr;
         // scratch of the solve threads: right-hand side and iterate, [2 n][threads of a launch]
