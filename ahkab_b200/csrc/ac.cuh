@@ -28,7 +28,9 @@ AHK_DEV cd cadd(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
 // reciprocal through the squared modulus: one division (pivots of circuit matrices are
 // far from the over/underflow range of |b|^2)
 AHK_DEV cd crecip(cd b) {
-  const double s = 1.0 / (b.re * b.re + b.im * b.im);
+  // (branch-free reciprocal: an IEEE division ends in a conditional call to its slow path that
+  // the compiler schedules nothing across — 14 of them per solve in the static-schedule kernel)
+  const double s = fm::rcp(b.re * b.re + b.im * b.im);
   return cd{b.re * s, -b.im * s};
 }
 AHK_DEV cd cdivv(cd a, cd b) {   // Smith's algorithm (what C / numpy use)
