@@ -49,6 +49,44 @@ AHK_DEV void run_dc(Ctx& c, const DcArgs& a) {
   }
 }
 
+#ifdef __CUDACC__
+// Operating point of the one-lane specialised kernel with BLOCK-COOPERATIVE result rows: a lane
+// that writes its own x[0..n) row puts 8-byte pieces 8 n bytes apart — partial sectors, which is
+// what made the zero-copy form of ahk_op_host (results written straight into the caller's pinned
+// buffers over PCIe) four times slower than a packed copy.  x and the residual already sit in the
+// lanes' shared-memory slices: after a block barrier consecutive THREADS write consecutive doubles
+// of the block's [instances][n] rows (256 contiguous bytes per warp store).  Warp-uniform: every
+// lane runs (`live` false for the padding lanes of the last block, which repeat the last instance
+// and write nothing).  One point (OP) only; sweeps keep run_dc.
+template <class V>
+__device__ __forceinline__ void run_op_rows(Ctx& c, const DcArgs& a, bool live) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = c.p->n;
+  init_ctx<V>(c);
+  build_values<V>(c, false);
+  double* x = c.x();
+  const bool have = a.x0 != nullptr;
+  if (have) for (int i = 0; i < n; i++) x[i] = a.x0[c.inst * n + i];
+  c.dc_src = a.src_elem;
+  if (a.src_elem >= 0) c.dc_val = a.sweep[0];
+  int it = 0;
+  const int st = op_analysis<V>(c, have, a.use_guess != 0, &it);
+  double* res = c.sm + c.L->res;
+  if (a.resid && !(st & AHK_ST_OK)) for (int i = 0; i < n; i++) res[i] = nan("");
+  if (live) { a.iters[c.inst] = it; a.status[c.inst] = st; }
+  __syncthreads();
+  const long long first = (long long)blockIdx.x * blockDim.x;
+  const long long left = c.B - first;
+  const int cnt = (int)(left < (long long)blockDim.x ? left : (long long)blockDim.x);   // instances of this block
+  const int stride = c.L->stride, ox = c.L->x, ores = c.L->res;
+  for (int j = threadIdx.x; j < cnt * n; j += blockDim.x) {
+    const int il = j / n, i = j - il * n;
+    a.x_out[first * n + j] = smem[il * stride + ox + i];
+    if (a.resid) a.resid[first * n + j] = smem[il * stride + ores + i];
+  }
+}
+#endif
+
 // transient.transient_analysis for one instance
 // (warp-uniform: EVERY lane of the warp calls it — `live` = false for the padding groups of a
 // partial last warp, whose c.inst names some valid instance to read parameters from)

@@ -24,6 +24,15 @@ typedef Var<AHK_JIT_NC, AHK_JIT_R, AHK_JIT_G> JitVar;
 #if AHK_JIT_MODE == 0
 extern "C" __global__ void __launch_bounds__(AHK_JIT_THREADS, AHK_JIT_MINB)
 ahk_jit_dc(const __grid_constant__ KDcJ k) {
+  if constexpr (JitVar::G == 1) {
+    if (k.a.npts == 1) {          // operating point, one lane per instance: coalesced result rows
+      Ctx c; bool live;
+      make_ctx_uniform<1>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, live);
+      c.pivrec = live ? k.pivrec : nullptr;
+      run_op_rows<JitVar>(c, k.a, live);
+      return;
+    }
+  }
   Ctx c; long long u;
   if (!make_ctx<JitVar::G>(c, &jit_prog, &jit_opts, &jit_layout, Layout::stride, k.vary, k.B, k.B, u)) return;
   c.pivrec = k.pivrec;

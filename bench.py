@@ -65,12 +65,19 @@ C4_MAX_ROWS = 3072
 # or two waves takes as long for a quarter of the batch as for all of it (measured: C3
 # 28 -> 44 ms, C4 262 -> 679 ms with 4 / 8 chunks), so those run as one chunk.
 E2E_CHUNKS = dict(c1=4, c2=1, c3=1, c4=1, c5=1)   # c5: thread-per-instance kernels are latency bound: a quarter of the batch takes as long as all of it
-# AHK_E2E_OP_HOST=<chunks>: route the c2 end-to-end step through ahk_op_host (host buffers,
-# chunk pipeline inside the library; 0 = zero-copy).  Measured on B200 (50 steps): one packed
-# D2H through the Engine 0.129 ms; op_host 1 / 2 / 4 / 8 chunks 0.143 / 0.136 / 0.215 / 0.244 ms
-# (every extra DMA costs ~8 us: the kernels are too short to hide them), zero-copy 0.414 ms
-# ([B][n] rows written from one lane per instance are partial PCIe sectors).
-OP_HOST = os.environ.get('AHK_E2E_OP_HOST')
+# The c2 end-to-end step goes through ahk_op_host (host buffers in, host buffers out) in its
+# ZERO-COPY form (chunks = 0): the kernel reads the pinned parameters and writes the pinned
+# results itself, so both PCIe directions overlap the computation inside the one launch — no
+# separate H2D / D2H copies, the same bytes cross the bus.  AHK_E2E_OP_HOST=<chunks> selects the
+# chunked copy pipeline inside the library, AHK_E2E_OP_HOST=engine the packed copies through the
+# Engine (set_vary + op + to_host).  Measured on B200 (50 steps): zero-copy 0.103 ms; Engine
+# 0.127 ms; op_host with 1 / 2 chunks 0.138 / 0.178 ms (every extra DMA costs ~8 us: the kernels
+# are too short to hide them).  Zero-copy took 0.414 ms while every lane wrote its own [n] row
+# (partial PCIe sectors); the one-lane specialised kernel now writes the block's rows
+# cooperatively, 256 contiguous bytes per warp store (entry.cuh: run_op_rows).
+OP_HOST = os.environ.get('AHK_E2E_OP_HOST', '0')
+if OP_HOST == 'engine':
+    OP_HOST = None
 
 
 def config_of(name):
@@ -691,6 +698,12 @@ def bench_one(name, rank, world, timer, sampler, steps, warmup, hbm_peak, hbm_sr
                     "unit": "GB/s", "frac": byts / step_s / 1e9 / hbm_peak,
                     "peak_source": hbm_src, "algorithmic_bytes_per_step": byts}},
     }
+    if name == 'c2' and world == 1:
+        line["e2e"]["path"] = ("Engine: set_vary (pinned H2D) + ahk_op + to_host (pinned D2H)" if OP_HOST is None else
+                               "ahk_op_host, zero-copy: the kernel reads the pinned host parameters and writes the "
+                               "pinned host results itself (the same bytes cross PCIe inside the one launch)"
+                               if int(OP_HOST) == 0 else
+                               "ahk_op_host, %d chunk(s) through the library's copy-in / kernel / copy-out streams" % int(OP_HOST))
     if e2e_api:
         line["e2e_api"] = e2e_api
     if hbm_resident:
