@@ -538,10 +538,58 @@ AHK_DEV void run_ac(Ctx& c, const AcLayout& AL, const AcArgs& a) {
     x += c.sub * n; dx += c.sub * n;
     if (c.sub) for (int i = 0; i < n; i++) x[i] = xs[i];
   }
+#if defined(AHK_JIT_SLU) && defined(__CUDACC__)
+  if constexpr (SLU1) {
+    // Every lane of the group runs the same number of rounds (one frequency of its chunk per
+    // round), and the result rows of a round leave through the WHOLE group: the 2 n doubles of a
+    // row by 2 n consecutive lanes — 224 contiguous bytes for C1 instead of 28 eight-byte pieces
+    // 224 bytes apart from lane to lane (what a zero-copy write into pinned host memory needs,
+    // and kinder to L2 for device buffers).  A lane whose matrix is singular fills its row with
+    // NaN and keeps writing it for the rest of its chunk, as the one-lane form did.
+    const int per = (a.npts + G - 1) / G;
+    const cd* xs0 = (const cd*)(c.sm + AL.xc);          // lane l's iterate: xs0 + l * n
+    bool dead = false;
+    for (int j = 0; j < per; j++) {
+      const int f = f0 + j;
+      if (f < f1 && !dead) {
+        const int R = V::R;
+        const double om = a.omegas[f];
+        int ok = zslu_solve_thread<V>(Bv, Dv, Nac, om, x, dx);
+        // calibration launch: every lane of instance 0 keeps its own record (engine.cu merges them)
+        int* prec = (c.pivrec != nullptr && c.inst == 0) ? c.pivrec + 256 * c.sub : nullptr;
+        if (prec) prec[1]++;
+        if (!ok) {
+          int rec[R > 0 ? R : 1];
+          ok = zslu_fallback<V>(c, AL, om, x, dx, rec);
+          if (prec && ok) slu_record(prec, rec, n);
+        }
+        if (ok) {
+          for (int i = 0; i < n; i++) x[i] = cadd(x[i], dx[i]);
+        } else {
+          dead = true; st = AHK_ST_SINGULAR;
+          const double qn = nan("");
+          for (int i = 0; i < n; i++) x[i] = cd{qn, qn};
+        }
+      }
+      Grp<G>::sync(c.mask);
+      for (int l = 0; l < G; l++) {
+        const int fl = l * per + j;                       // lane l's frequency of this round
+        if (fl >= a.npts) break;
+        const double* src = (const double*)(xs0 + l * n);
+        double* dst = a.x_out + ((c.inst * a.npts + fl) * n) * 2;
+        for (int i = c.sub; i < 2 * n; i += G) dst[i] = src[i];
+      }
+      Grp<G>::sync(c.mask);
+    }
+    // status[] is pre-filled with AHK_ST_OK by the caller; lanes only downgrade it
+    if (a.status && st != AHK_ST_OK) a.status[c.inst] = st;
+    return;
+  }
+#endif
   for (int f = f0; f < f1; f++) {
     const double om = a.omegas[f];
     int ok;
-#ifdef AHK_JIT_SLU
+#if defined(AHK_JIT_SLU) && !defined(__CUDACC__)
     if constexpr (SLU1) {
       const int R = V::R;
       ok = zslu_solve_thread<V>(Bv, Dv, Nac, om, x, dx);

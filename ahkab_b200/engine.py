@@ -443,6 +443,44 @@ class Engine(object):
             raise EngineError(self._err())
         return dict(x=torch.view_as_complex(xo), status=status, omegas=om, _packed=pk['_packed'])
 
+    def ac_host(self, omegas, x_op=None, vary_host=None):
+        """AC sweep from HOST parameters to HOST results without copies: the kernel reads the pinned
+        parameter matrix and writes the pinned result rows itself (unified addressing), so the
+        PCIe traffic overlaps the computation inside the launch — what `op_host(nchunks=0)` is
+        for the operating point.  vary_host: pinned [n_vary][B] float64 tensor (default: a pinned
+        copy of the batch the engine was built with).  Returns pinned host tensors, cached per
+        shape and reused by the next call; asynchronous on the current stream."""
+        om = np.ascontiguousarray(omegas, np.float64)
+        P = len(om)
+        if vary_host is None:
+            if self._vary_host is None:
+                self._vary_host = torch.empty(self.vary.shape, dtype=torch.float64, pin_memory=True)
+                self._vary_host.copy_(self.vary)
+                torch.cuda.synchronize(self.device)
+            vary_host = self._vary_host
+        B = vary_host.shape[1] if vary_host.numel() else self.B
+        x_op = self._x0(x_op)
+        if not hasattr(self, '_pinned'):
+            self._pinned = {}
+        key = ('ac_host', B, P)
+        out = self._pinned.get(key)
+        if out is None:
+            out = dict(x=torch.empty((B, P, self.n, 2), dtype=torch.float64, pin_memory=True),
+                       status=torch.empty((B,), dtype=torch.int32, pin_memory=True))
+            self._pinned[key] = out
+        b = _abi.ahk_batch()
+        b.B = B
+        b.n_vary = len(self._slots)
+        b.vary_slots = self._slots.ctypes.data_as(C.POINTER(C.c_int32))
+        b.vary = vary_host.data_ptr() if vary_host.numel() else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.ahk_ac(self._h, C.byref(b), _ptr(x_op),
+                                 om.ctypes.data_as(C.POINTER(C.c_double)), P,
+                                 _ptr(out['x']), _ptr(out['status']), self._stream())
+        if rc != 0:
+            raise EngineError(self._err())
+        return dict(x=torch.view_as_complex(out['x']), status=out['status'], omegas=om)
+
     def to_host(self, raw, keys=None, fresh=False):
         """Device->host read of a result dict into PINNED buffers (asynchronous on the
         current stream; synchronise before reading).  This is the D2H copy of an

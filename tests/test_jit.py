@@ -362,6 +362,23 @@ def test_gpu_static_schedule_lu_instances_that_pivot_differently_fall_back():
     assert np.array_equal(_np(a['x']), _np(b['x']))
 
 
+@pytest.mark.gpu
+def test_gpu_ac_host_zero_copy_matches_ac():
+    """Engine.ac_host: the lane-per-chunk AC kernel reading its parameters from and writing its
+    result rows into pinned host memory gives what the device-buffer call gives, bit for bit
+    (ragged batch: the last block is partial)."""
+    w = W.c1_butterworth(301)
+    e = _engine(w)
+    e.set_jit('on')
+    om = common.c1_omegas()
+    a = e.ac(om)
+    h = e.ac_host(om)
+    torch.cuda.synchronize()
+    assert e.last_launch()['jit'] == 1 and e.last_launch()['R'] == e.n       # the static-schedule kernel
+    assert (h['status'].numpy() == _np(a['status'])).all() and (h['status'].numpy() & 1).all()
+    assert np.array_equal(h['x'].numpy(), _np(a['x']))
+
+
 def test_generated_constants_do_not_depend_on_the_batch_values():
     """The text that keys the compiled-kernel cache must be the same for two batches that
     vary the same parameters with different values (else every run() call recompiles)."""
