@@ -383,7 +383,9 @@ AHK_DEV int zgj_solve(Ctx& c, const AcLayout& AL, cd (&a)[V::R > 0 ? V::R : 1][V
 
 #ifdef AHK_JIT_SLU
 #ifdef __CUDACC__
-#define AHK_SLU_FENCE asm volatile("" ::: "memory");
+// (an empty asm statement orders nothing for ptxas; a real shared-memory store that the row loads
+// behind it might alias does: dx[0] is rewritten by the back-substitution at the end of the body)
+#define AHK_SLU_FENCE { ((volatile double*)dx)[0] = 0.0; }
 #else
 #define AHK_SLU_FENCE
 #endif
